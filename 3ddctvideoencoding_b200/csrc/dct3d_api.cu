@@ -1,0 +1,817 @@
+// dct3d_api.cu -- the C ABI of libdct3d.so (include/dct3d.h) over the kernels in
+// dct3d_kernels.cuh.  CUDA only: there is no CPU code path behind these entry points.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/dct3d.h"
+#include "dct3d_kernels.cuh"
+
+using namespace dct3d;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n)
+    {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        const size_t want = n + n / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct Ctrl {               // small device control block, zeroed before every launch
+    unsigned int ticket;
+    unsigned int err;
+    unsigned int changed;
+    unsigned int pad;
+    unsigned long long end_bit;
+};
+
+}  // namespace
+
+struct dct3d_ctx {
+    int device = 0, W = 0, H = 0, C = 8;
+    int num_sms = 0;
+    int use_tma = 1;
+    long launches = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    DevBuf frames, bits, q, status, ctrl, seg, cubeoff, fa, fb;
+    Ctrl *h_ctrl = nullptr;          // pinned
+    unsigned long long *h_u64 = nullptr;  // pinned scratch (4 entries)
+    // streaming state
+    uint8_t carry_byte = 0;
+    int carry_bits = 0;
+};
+
+namespace {
+
+int fail(dct3d_ctx *ctx, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    if (ctx) ctx->err = buf;
+    return code;
+}
+
+#define CU_CHECK(ctx, call)                                                                          \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess)                                                                       \
+            return fail(ctx, DCT3D_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+Layout make_layout(int W, int H, int C, int nslabs)
+{
+    Layout L;
+    L.W = W; L.H = H; L.C = C;
+    L.bx = W / C; L.by = H / C;
+    const int cpb = kBoxW / C;
+    L.bxb = (L.bx + cpb - 1) / cpb;
+    L.nslabs = nslabs;
+    L.nboxes = (long long)nslabs * L.by * L.bxb;
+    const int bpt = kTileCubes / cpb;
+    L.ntiles = (L.nboxes + bpt - 1) / bpt;
+    L.ncubes = (long long)nslabs * L.by * L.bx;
+    return L;
+}
+
+// The reference's zig-zag order (CubeUtils.java:15-37 / CubeUtils.c:17-42), built here from its
+// definition: slices of constant x+y+z ascending; inside a slice y outer, z middle, x inner.
+void build_zz(int C, std::vector<int> &lin)
+{
+    lin.clear();
+    for (int s = 0; s <= 3 * (C - 1); s++)
+        for (int y = 0; y < C; y++)
+            for (int z = 0; z < C; z++) {
+                const int x = s - y - z;
+                if (x >= 0 && x < C) lin.push_back(x + y * C + z * C * C);
+            }
+}
+
+bool g_tables_ready[64] = {false};
+
+int upload_tables(dct3d_ctx *ctx)
+{
+    if (ctx->device < 64 && g_tables_ready[ctx->device]) return DCT3D_OK;
+    ZzTables t;
+    memset(&t, 0, sizeof t);
+    for (int C : {8, 4}) {
+        std::vector<int> lin;
+        build_zz(C, lin);
+        std::vector<int> pos(C * C * C);
+        for (int i = 0; i < (int)lin.size(); i++) pos[lin[i]] = i;
+        for (int i = 0; i < C * C * C; i++) (C == 8 ? t.lin8[i] : t.lin4[i]) = (uint16_t)lin[i];
+        for (int j = 0; j < C; j++)
+            for (int s = 0; s < 2 * C - 1; s++) {
+                const int k0min = s > C - 1 ? s - (C - 1) : 0, k0max = std::min(s, C - 1);
+                const int p0 = pos[(s - k0min) + j * C + k0min * C * C];
+                // the kernel relies on the run being contiguous and ordered by k0
+                for (int k0 = k0min; k0 <= k0max; k0++)
+                    if (pos[(s - k0) + j * C + k0 * C * C] != p0 + (k0 - k0min))
+                        return fail(ctx, DCT3D_E_INVALID, "zig-zag run property violated (C=%d j=%d s=%d)", C, j, s);
+                (C == 8 ? t.base8[j][s] : t.base4[j][s]) = (uint16_t)p0;
+            }
+    }
+    CU_CHECK(ctx, cudaMemcpyToSymbol(c_zz, &t, sizeof t));
+    if (ctx->device < 64) g_tables_ready[ctx->device] = true;
+    return DCT3D_OK;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_tiled()
+{
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// Tensor map over the u8 frame stack [F][H][W]; box = 128 px x 1 row x C frames, SWIZZLE_128B.
+bool make_tmap(CUtensorMap *tm, const void *frames, int W, int H, int F, int C)
+{
+    EncodeTiledFn fn = get_encode_tiled();
+    if (!fn) return false;
+    cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)F};
+    cuuint64_t strides[2] = {(cuuint64_t)W, (cuuint64_t)W * H};
+    cuuint32_t box[3] = {(cuuint32_t)kBoxW, 1u, (cuuint32_t)C};
+    cuuint32_t es[3] = {1, 1, 1};
+    return fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void *>(frames), dims, strides, box, es,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+int bind(dct3d_ctx *ctx)
+{
+    if (!ctx) return fail(nullptr, DCT3D_E_INVALID, "null context");
+    CU_CHECK(ctx, cudaSetDevice(ctx->device));
+    return DCT3D_OK;
+}
+
+cudaStream_t pick(dct3d_ctx *ctx, void *s) { return s ? (cudaStream_t)s : ctx->stream; }
+
+int check_frames(dct3d_ctx *ctx, int nframes)
+{
+    if (nframes < 0) return fail(ctx, DCT3D_E_INVALID, "negative frame count");
+    return DCT3D_OK;
+}
+
+template <int C, bool EMIT_Q>
+int launch_encode(dct3d_ctx *ctx, const EncParams &P, const CUtensorMap &tm, cudaStream_t st)
+{
+    auto kern = encode_kernel<C, EMIT_Q>;
+    const int smem = EncSmem<C>::TOTAL;
+    CU_CHECK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int occ = 0;
+    CU_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem));
+    if (occ < 1) return fail(ctx, DCT3D_E_CUDA, "encode kernel does not fit on an SM");
+    const long long grid = std::min<long long>(P.L.ntiles, (long long)ctx->num_sms * occ);
+    kern<<<(unsigned)grid, kThreads, smem, st>>>(tm, P);
+    ctx->launches++;
+    CU_CHECK(ctx, cudaGetLastError());
+    return DCT3D_OK;
+}
+
+// zero the control block and the look-back status array
+int reset_ctrl(dct3d_ctx *ctx, long long ntiles, cudaStream_t st)
+{
+    CU_CHECK(ctx, ctx->ctrl.reserve(sizeof(Ctrl)));
+    CU_CHECK(ctx, ctx->status.reserve((size_t)std::max<long long>(ntiles, 1) * 8));
+    CU_CHECK(ctx, cudaMemsetAsync(ctx->ctrl.p, 0, sizeof(Ctrl), st));
+    CU_CHECK(ctx, cudaMemsetAsync(ctx->status.p, 0, (size_t)std::max<long long>(ntiles, 1) * 8, st));
+    return DCT3D_OK;
+}
+
+int fetch_ctrl(dct3d_ctx *ctx, cudaStream_t st)
+{
+    CU_CHECK(ctx, cudaMemcpyAsync(ctx->h_ctrl, ctx->ctrl.p, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
+    CU_CHECK(ctx, cudaStreamSynchronize(st));
+    return DCT3D_OK;
+}
+
+// zero-fill the stream from the byte after start_bit's byte (the partial byte is kept)
+int zero_stream(dct3d_ctx *ctx, void *d_stream, size_t cap, uint64_t start_bit, cudaStream_t st)
+{
+    const size_t first = (size_t)((start_bit + 7) / 8);
+    if (start_bit % 8 == 0) {
+        if (cap > first) CU_CHECK(ctx, cudaMemsetAsync((uint8_t *)d_stream + first, 0, cap - first, st));
+    } else if (cap > first) {
+        CU_CHECK(ctx, cudaMemsetAsync((uint8_t *)d_stream + first, 0, cap - first, st));
+    }
+    return DCT3D_OK;
+}
+
+#define H2D(ctx, dst, src, n) CU_CHECK(ctx, cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, ctx->stream))
+#define D2H(ctx, dst, src, n) CU_CHECK(ctx, cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, ctx->stream))
+#define SYNC(ctx) CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream))
+
+
+template <int C>
+static int launch_reconstruct(dct3d_ctx *ctx, const Layout &L, const void *d_q, void *d_frames, cudaStream_t st)
+{
+    const int smem = kWarps * Xch<C, float>::WARP_BYTES;
+    const long long groups = (L.ncubes + Geo<C>::CPW - 1) / Geo<C>::CPW;
+    const long long grid = std::min<long long>((groups + kWarps - 1) / kWarps, (long long)ctx->num_sms * 8);
+    reconstruct_kernel<C><<<(unsigned)grid, kThreads, smem, st>>>(L, (const int16_t *)d_q, (uint8_t *)d_frames);
+    ctx->launches++;
+    CU_CHECK(ctx, cudaGetLastError());
+    return DCT3D_OK;
+}
+
+template <typename T, bool CUBEMAJOR, bool INVERSE>
+static int transform_dev(dct3d_ctx *ctx, const void *d_in, void *d_out, int nslabs, void *cuda_stream)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (nslabs < 0) return fail(ctx, DCT3D_E_INVALID, "negative slab count");
+    if (nslabs == 0) return DCT3D_OK;
+    if (!d_in || !d_out) return fail(ctx, DCT3D_E_INVALID, "null pointer");
+    if (((uintptr_t)d_in | (uintptr_t)d_out) & 15) return fail(ctx, DCT3D_E_INVALID, "buffers must be 16-byte aligned");
+    if (!CUBEMAJOR && (ctx->W * sizeof(T)) % 16) return fail(ctx, DCT3D_E_INVALID, "planar rows must be 16-byte multiples");
+    const Layout L = make_layout(ctx->W, ctx->H, ctx->C, nslabs);
+    cudaStream_t st = pick(ctx, cuda_stream);
+    const int cpw = 32 / ctx->C;
+    const long long groups = (L.ncubes + cpw - 1) / cpw;
+    const long long grid = std::min<long long>((groups + kWarps - 1) / kWarps, (long long)ctx->num_sms * 8);
+    if (ctx->C == 8) {
+        const int smem = kWarps * Xch<8, T>::WARP_BYTES;
+        transform_kernel<8, T, CUBEMAJOR, INVERSE><<<(unsigned)grid, kThreads, smem, st>>>(L, (const T *)d_in, (T *)d_out);
+    } else {
+        const int smem = kWarps * Xch<4, T>::WARP_BYTES;
+        transform_kernel<4, T, CUBEMAJOR, INVERSE><<<(unsigned)grid, kThreads, smem, st>>>(L, (const T *)d_in, (T *)d_out);
+    }
+    ctx->launches++;
+    CU_CHECK(ctx, cudaGetLastError());
+    return DCT3D_OK;
+}
+
+template <typename T>
+static int transform_host(dct3d_ctx *ctx, const T *in, T *out, size_t count, int arg,
+                          int (*dev)(dct3d_ctx *, const void *, void *, int, void *))
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (count == 0) return DCT3D_OK;
+    if (!in || !out) return fail(ctx, DCT3D_E_INVALID, "null pointer");
+    CU_CHECK(ctx, ctx->fa.reserve(count * sizeof(T)));
+    CU_CHECK(ctx, ctx->fb.reserve(count * sizeof(T)));
+    H2D(ctx, ctx->fa.p, in, count * sizeof(T));
+    if ((rc = dev(ctx, ctx->fa.p, ctx->fb.p, arg, nullptr))) return rc;
+    D2H(ctx, out, ctx->fb.p, count * sizeof(T));
+    SYNC(ctx);
+    return DCT3D_OK;
+}
+
+}  // namespace
+
+// ============================================================================================
+extern "C" {
+
+int dct3d_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return fail(nullptr, DCT3D_E_CUDA, "no CUDA device"); }
+    return n;
+}
+
+int dct3d_list_devices(char *buf, size_t cap)
+{
+    int n = dct3d_device_count();
+    if (n < 0) return n;
+    std::string s;
+    for (int i = 0; i < n; i++) {
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, i) != cudaSuccess) continue;
+        char line[256];
+        snprintf(line, sizeof line, "%d - %s (sm_%d%d, %d SMs, %.1f GiB)\n", i, p.name, p.major, p.minor,
+                 p.multiProcessorCount, (double)p.totalGlobalMem / (1 << 30));
+        s += line;
+    }
+    if (buf && cap) { snprintf(buf, cap, "%s", s.c_str()); }
+    return n;
+}
+
+int dct3d_create(dct3d_ctx **out, int device, int width, int height, int cube)
+{
+    if (!out) return fail(nullptr, DCT3D_E_INVALID, "null output pointer");
+    *out = nullptr;
+    if (cube != 8 && cube != 4) return fail(nullptr, DCT3D_E_INVALID, "cube edge must be 8 or 4, got %d", cube);
+    if (width <= 0 || height <= 0 || width % cube || height % cube)
+        return fail(nullptr, DCT3D_E_INVALID, "frame %dx%d is not a positive multiple of the cube edge %d", width, height, cube);
+    int n = dct3d_device_count();
+    if (n <= 0) return fail(nullptr, DCT3D_E_CUDA, "no CUDA device available (libdct3d has no CPU fallback)");
+    if (device < 0 || device >= n) return fail(nullptr, DCT3D_E_INVALID, "device %d out of range (0..%d)", device, n - 1);
+    dct3d_ctx *ctx = new dct3d_ctx();
+    ctx->device = device; ctx->W = width; ctx->H = height; ctx->C = cube;
+    ctx->use_tma = (width % 16 == 0) ? 1 : 0;
+    int rc = bind(ctx);
+    if (rc == DCT3D_OK) {
+        cudaError_t e = cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaMallocHost((void **)&ctx->h_ctrl, sizeof(Ctrl));
+        if (e == cudaSuccess) e = cudaMallocHost((void **)&ctx->h_u64, 4 * sizeof(unsigned long long));
+        if (e != cudaSuccess) rc = fail(ctx, DCT3D_E_CUDA, "context setup failed: %s", cudaGetErrorString(e));
+    }
+    if (rc == DCT3D_OK) rc = upload_tables(ctx);
+    if (rc != DCT3D_OK) { std::string keep = ctx->err; dct3d_destroy(ctx); g_last_error = keep; return rc; }
+    *out = ctx;
+    return DCT3D_OK;
+}
+
+void dct3d_destroy(dct3d_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    for (DevBuf *b : {&ctx->frames, &ctx->bits, &ctx->q, &ctx->status, &ctx->ctrl, &ctx->seg, &ctx->cubeoff, &ctx->fa, &ctx->fb}) b->release();
+    if (ctx->h_ctrl) cudaFreeHost(ctx->h_ctrl);
+    if (ctx->h_u64) cudaFreeHost(ctx->h_u64);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *dct3d_last_error(const dct3d_ctx *ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
+
+int dct3d_set_option(dct3d_ctx *ctx, const char *key, long value)
+{
+    if (!ctx || !key) return fail(ctx, DCT3D_E_INVALID, "null argument");
+    if (!strcmp(key, "tma")) {
+        if (value && ctx->W % 16) return fail(ctx, DCT3D_E_INVALID, "TMA loads need width %% 16 == 0");
+        if (value && !get_encode_tiled()) return fail(ctx, DCT3D_E_CUDA, "cuTensorMapEncodeTiled unavailable");
+        ctx->use_tma = value ? 1 : 0;
+        return DCT3D_OK;
+    }
+    return fail(ctx, DCT3D_E_INVALID, "unknown option '%s'", key);
+}
+
+long dct3d_get_stat(const dct3d_ctx *ctx, const char *key)
+{
+    if (!ctx || !key) return -1;
+    if (!strcmp(key, "launches")) return ctx->launches;
+    if (!strcmp(key, "tma")) return ctx->use_tma;
+    if (!strcmp(key, "num_sms")) return ctx->num_sms;
+    return -1;
+}
+
+// ---- device-resident entry points -----------------------------------------------------------
+
+static int encode_common(dct3d_ctx *ctx, const void *d_frames, int nframes, void *d_stream, size_t cap,
+                         uint64_t start_bit, uint64_t *end_bit, void *cuda_stream, void *d_qcubes)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if ((rc = check_frames(ctx, nframes))) return rc;
+    const int C = ctx->C;
+    const int nslabs = nframes / C;
+    cudaStream_t st = pick(ctx, cuda_stream);
+    const bool emit_q = d_qcubes != nullptr;
+    if (!emit_q) {
+        if (!d_stream || ((uintptr_t)d_stream & 3)) return fail(ctx, DCT3D_E_INVALID, "stream buffer must be non-null and 4-byte aligned");
+        if (cap < start_bit / 8 + 16) return fail(ctx, DCT3D_E_OVERFLOW, "stream capacity %zu too small", cap);
+        if ((rc = zero_stream(ctx, d_stream, cap, start_bit, st))) return rc;
+    }
+    if (nslabs == 0) { if (end_bit) *end_bit = start_bit; return DCT3D_OK; }
+    if (!d_frames) return fail(ctx, DCT3D_E_INVALID, "null frame pointer");
+    EncParams P;
+    memset(&P, 0, sizeof P);
+    P.L = make_layout(ctx->W, ctx->H, C, nslabs);
+    if ((rc = reset_ctrl(ctx, P.L.ntiles, st))) return rc;
+    Ctrl *dc = (Ctrl *)ctx->ctrl.p;
+    P.frames = (const uint8_t *)d_frames;
+    P.out_words = (uint32_t *)d_stream;
+    P.cap_bits = (unsigned long long)(cap / 4) * 32;
+    P.start_bit = start_bit;
+    P.tile_status = (unsigned long long *)ctx->status.p;
+    P.ticket = &dc->ticket; P.err = &dc->err; P.end_bit = &dc->end_bit;
+    P.qcubes = (int16_t *)d_qcubes;
+    P.use_tma = ctx->use_tma && !((uintptr_t)d_frames & 15);
+    CUtensorMap tm;
+    memset(&tm, 0, sizeof tm);
+    if (P.use_tma && !make_tmap(&tm, d_frames, ctx->W, ctx->H, nslabs * C, C))
+        return fail(ctx, DCT3D_E_CUDA, "cuTensorMapEncodeTiled failed (set option tma=0 to use plain loads)");
+    if (C == 8) rc = emit_q ? launch_encode<8, true>(ctx, P, tm, st) : launch_encode<8, false>(ctx, P, tm, st);
+    else rc = emit_q ? launch_encode<4, true>(ctx, P, tm, st) : launch_encode<4, false>(ctx, P, tm, st);
+    if (rc) return rc;
+    if (end_bit || emit_q) {
+        if ((rc = fetch_ctrl(ctx, st))) return rc;
+        if (ctx->h_ctrl->err & 16u) return fail(ctx, DCT3D_E_CUDA, "TMA tile load timed out");
+        if (ctx->h_ctrl->err & 8u) return fail(ctx, DCT3D_E_CUDA, "tile look-back timed out");
+        if (ctx->h_ctrl->err & 1u) return fail(ctx, DCT3D_E_OVERFLOW, "stream buffer of %zu bytes is too small", cap);
+        if (end_bit) *end_bit = ctx->h_ctrl->end_bit;
+    }
+    return DCT3D_OK;
+}
+
+int dct3d_encode_u8_dev(dct3d_ctx *ctx, const void *d_frames, int nframes, void *d_stream, size_t cap,
+                        uint64_t start_bit, uint64_t *end_bit, void *cuda_stream)
+{
+    return encode_common(ctx, d_frames, nframes, d_stream, cap, start_bit, end_bit, cuda_stream, nullptr);
+}
+
+int dct3d_quantize_u8_dev(dct3d_ctx *ctx, const void *d_frames, int nframes, void *d_qcubes, void *cuda_stream)
+{
+    if (!d_qcubes) return fail(ctx, DCT3D_E_INVALID, "null output pointer");
+    return encode_common(ctx, d_frames, nframes, nullptr, 0, 0, nullptr, cuda_stream, d_qcubes);
+}
+
+int dct3d_eg_encode_i16_dev(dct3d_ctx *ctx, const void *d_qcubes, size_t ncubes, uint64_t start_bit,
+                            void *d_stream, size_t cap, uint64_t *end_bit, void *cuda_stream)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    cudaStream_t st = pick(ctx, cuda_stream);
+    if (!d_stream || ((uintptr_t)d_stream & 3)) return fail(ctx, DCT3D_E_INVALID, "stream buffer must be non-null and 4-byte aligned");
+    if (cap < start_bit / 8 + 16) return fail(ctx, DCT3D_E_OVERFLOW, "stream capacity %zu too small", cap);
+    if ((rc = zero_stream(ctx, d_stream, cap, start_bit, st))) return rc;
+    if (ncubes == 0) { if (end_bit) *end_bit = start_bit; return DCT3D_OK; }
+    if (!d_qcubes) return fail(ctx, DCT3D_E_INVALID, "null cube pointer");
+    EncParams P;
+    memset(&P, 0, sizeof P);
+    P.L = make_layout(ctx->W, ctx->H, ctx->C, 0);
+    P.L.ncubes = (long long)ncubes;
+    P.L.ntiles = ((long long)ncubes + kTileCubes - 1) / kTileCubes;
+    if ((rc = reset_ctrl(ctx, P.L.ntiles, st))) return rc;
+    Ctrl *dc = (Ctrl *)ctx->ctrl.p;
+    P.qcubes_in = (const int16_t *)d_qcubes;
+    P.out_words = (uint32_t *)d_stream;
+    P.cap_bits = (unsigned long long)(cap / 4) * 32;
+    P.start_bit = start_bit;
+    P.tile_status = (unsigned long long *)ctx->status.p;
+    P.ticket = &dc->ticket; P.err = &dc->err; P.end_bit = &dc->end_bit;
+    const long long grid = std::min<long long>(P.L.ntiles, (long long)ctx->num_sms * 4);
+    if (ctx->C == 8) eg_encode_kernel<8><<<(unsigned)grid, kThreads, 0, st>>>(P);
+    else eg_encode_kernel<4><<<(unsigned)grid, kThreads, 0, st>>>(P);
+    ctx->launches++;
+    CU_CHECK(ctx, cudaGetLastError());
+    if (end_bit) {
+        if ((rc = fetch_ctrl(ctx, st))) return rc;
+        if (ctx->h_ctrl->err & 8u) return fail(ctx, DCT3D_E_CUDA, "tile look-back timed out");
+        if (ctx->h_ctrl->err & 1u) return fail(ctx, DCT3D_E_OVERFLOW, "stream buffer of %zu bytes is too small", cap);
+        *end_bit = ctx->h_ctrl->end_bit;
+    }
+    return DCT3D_OK;
+}
+
+// Index discovery + parse: stream -> natural-order int16 cubes in ctx->q (or d_qcubes).
+static int parse_common(dct3d_ctx *ctx, const void *d_stream, size_t nbytes, uint64_t start_bit, size_t ncubes,
+                        void *d_qcubes, uint64_t *end_bit, cudaStream_t st)
+{
+    int rc;
+    const int C = ctx->C, CS = C * C * C;
+    if (!d_stream || ((uintptr_t)d_stream & 3)) return fail(ctx, DCT3D_E_INVALID, "stream buffer must be non-null and 4-byte aligned");
+    if ((uint64_t)nbytes * 8 <= start_bit) return fail(ctx, DCT3D_E_NEED_MORE, "stream holds no data past the start bit");
+    DecParams P;
+    memset(&P, 0, sizeof P);
+    P.L = make_layout(ctx->W, ctx->H, C, 0);
+    P.L.ncubes = (long long)ncubes;
+    P.words = (const uint32_t *)d_stream;
+    P.nwords = ((unsigned long long)nbytes + 3) / 4;
+    P.nbits_total = (unsigned long long)nbytes * 8;
+    P.start_bit = start_bit;
+    P.seg_bits = 4096;
+    P.nseg = (P.nbits_total - start_bit + P.seg_bits - 1) / P.seg_bits;
+    // seg arrays: count[nseg] over[nseg+1] used[nseg] (u32) first[nseg+1] (u64)
+    const size_t n = (size_t)P.nseg;
+    const size_t off_first = ((3 * n + 1) * 4 + 7) & ~(size_t)7;
+    CU_CHECK(ctx, ctx->seg.reserve(off_first + (n + 1) * 8));
+    CU_CHECK(ctx, ctx->cubeoff.reserve((ncubes + 1) * 8));
+    CU_CHECK(ctx, ctx->ctrl.reserve(sizeof(Ctrl)));
+    P.seg_count = (unsigned int *)ctx->seg.p;
+    P.seg_over = P.seg_count + n;
+    P.seg_used = P.seg_over + n + 1;
+    P.seg_first = (unsigned long long *)((uint8_t *)ctx->seg.p + off_first);
+    Ctrl *dc = (Ctrl *)ctx->ctrl.p;
+    P.changed = &dc->changed; P.err = &dc->err;
+    P.cube_off = (unsigned long long *)ctx->cubeoff.p;
+    P.qcubes = (int16_t *)d_qcubes;
+    CU_CHECK(ctx, cudaMemsetAsync(ctx->ctrl.p, 0, sizeof(Ctrl), st));
+    CU_CHECK(ctx, cudaMemsetAsync(P.seg_over, 0, (n + 1) * 4, st));
+    CU_CHECK(ctx, cudaMemsetAsync(P.cube_off, 0xff, (ncubes + 1) * 8, st));
+    CU_CHECK(ctx, cudaMemsetAsync(d_qcubes, 0, ncubes * CS * sizeof(int16_t), st));
+    const unsigned sb = 128, sg = (unsigned)((P.nseg + sb - 1) / sb);
+    seg_scan_kernel<<<sg, sb, 0, st>>>(P, 1);
+    ctx->launches++;
+    // fix-up rounds: re-scan segments whose entry overhang differs from the one assumed
+    for (unsigned long long round = 0; round <= P.nseg; round++) {
+        CU_CHECK(ctx, cudaMemsetAsync(&dc->changed, 0, 4, st));
+        seg_scan_kernel<<<sg, sb, 0, st>>>(P, 0);
+        ctx->launches++;
+        if ((rc = fetch_ctrl(ctx, st))) return rc;
+        if (!ctx->h_ctrl->changed) break;
+    }
+    if (ctx->h_ctrl->err & 2u) return fail(ctx, DCT3D_E_STREAM, "malformed Exp-Golomb code in stream");
+    seg_prefix_kernel<<<1, 1024, 0, st>>>(P);
+    ctx->launches++;
+    CU_CHECK(ctx, cudaMemcpyAsync(ctx->h_u64, P.seg_first + n, 8, cudaMemcpyDeviceToHost, st));
+    CU_CHECK(ctx, cudaStreamSynchronize(st));
+    if (ctx->h_u64[0] < (unsigned long long)ncubes * CS)
+        return fail(ctx, DCT3D_E_NEED_MORE, "stream holds %llu codes, %llu needed", ctx->h_u64[0], (unsigned long long)ncubes * CS);
+    if (C == 8) cube_index_kernel<512><<<sg, sb, 0, st>>>(P); else cube_index_kernel<64><<<sg, sb, 0, st>>>(P);
+    ctx->launches++;
+    const unsigned pb = 128, pg = (unsigned)((ncubes + pb - 1) / pb);
+    if (C == 8) cube_parse_kernel<8><<<pg, pb, 0, st>>>(P); else cube_parse_kernel<4><<<pg, pb, 0, st>>>(P);
+    ctx->launches++;
+    CU_CHECK(ctx, cudaGetLastError());
+    if (end_bit) {
+        CU_CHECK(ctx, cudaMemcpyAsync(ctx->h_u64, P.cube_off + ncubes, 8, cudaMemcpyDeviceToHost, st));
+        if ((rc = fetch_ctrl(ctx, st))) return rc;
+        if (ctx->h_ctrl->err & 2u) return fail(ctx, DCT3D_E_STREAM, "malformed Exp-Golomb code in stream");
+        if (ctx->h_ctrl->err & 4u) return fail(ctx, DCT3D_E_STREAM, "Exp-Golomb stream truncated");
+        *end_bit = ctx->h_u64[0];
+    }
+    return DCT3D_OK;
+}
+
+int dct3d_eg_decode_i16_dev(dct3d_ctx *ctx, const void *d_stream, size_t nbytes, uint64_t start_bit,
+                            size_t ncubes, void *d_qcubes, uint64_t *end_bit, void *cuda_stream)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (ncubes == 0) { if (end_bit) *end_bit = start_bit; return DCT3D_OK; }
+    if (!d_qcubes) return fail(ctx, DCT3D_E_INVALID, "null cube pointer");
+    return parse_common(ctx, d_stream, nbytes, start_bit, ncubes, d_qcubes, end_bit, pick(ctx, cuda_stream));
+}
+
+int dct3d_reconstruct_i16_dev(dct3d_ctx *ctx, const void *d_qcubes, int nframes, void *d_frames, void *cuda_stream)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if ((rc = check_frames(ctx, nframes))) return rc;
+    const int nslabs = nframes / ctx->C;
+    if (nslabs == 0) return DCT3D_OK;
+    if (!d_qcubes || !d_frames) return fail(ctx, DCT3D_E_INVALID, "null pointer");
+    const Layout L = make_layout(ctx->W, ctx->H, ctx->C, nslabs);
+    cudaStream_t st = pick(ctx, cuda_stream);
+    return ctx->C == 8 ? launch_reconstruct<8>(ctx, L, d_qcubes, d_frames, st) : launch_reconstruct<4>(ctx, L, d_qcubes, d_frames, st);
+}
+
+int dct3d_decode_u8_dev(dct3d_ctx *ctx, const void *d_stream, size_t nbytes, uint64_t start_bit,
+                        int nframes, void *d_frames, uint64_t *end_bit, void *cuda_stream)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if ((rc = check_frames(ctx, nframes))) return rc;
+    const int C = ctx->C, nslabs = nframes / C;
+    if (nslabs == 0) { if (end_bit) *end_bit = start_bit; return DCT3D_OK; }
+    if (!d_frames) return fail(ctx, DCT3D_E_INVALID, "null frame pointer");
+    const Layout L = make_layout(ctx->W, ctx->H, C, nslabs);
+    cudaStream_t st = pick(ctx, cuda_stream);
+    CU_CHECK(ctx, ctx->q.reserve((size_t)L.ncubes * C * C * C * sizeof(int16_t)));
+    uint64_t end = 0;
+    if ((rc = parse_common(ctx, d_stream, nbytes, start_bit, (size_t)L.ncubes, ctx->q.p, &end, st))) return rc;
+    if (end_bit) *end_bit = end;
+    return C == 8 ? launch_reconstruct<8>(ctx, L, ctx->q.p, d_frames, st) : launch_reconstruct<4>(ctx, L, ctx->q.p, d_frames, st);
+}
+
+int dct3d_forward_f32_dev(dct3d_ctx *c, const void *i, void *o, int n, void *s) { return transform_dev<float, true, false>(c, i, o, n, s); }
+int dct3d_inverse_f32_dev(dct3d_ctx *c, const void *i, void *o, int n, void *s) { return transform_dev<float, true, true>(c, i, o, n, s); }
+int dct3d_forward_f64_dev(dct3d_ctx *c, const void *i, void *o, int nframes, void *s)
+{ return c ? transform_dev<double, false, false>(c, i, o, nframes / c->C, s) : fail(nullptr, DCT3D_E_INVALID, "null context"); }
+int dct3d_inverse_f64_dev(dct3d_ctx *c, const void *i, void *o, int nframes, void *s)
+{ return c ? transform_dev<double, false, true>(c, i, o, nframes / c->C, s) : fail(nullptr, DCT3D_E_INVALID, "null context"); }
+
+// ---- host-buffer entry points ---------------------------------------------------------------
+
+static size_t frame_bytes(const dct3d_ctx *ctx, int nframes) { return (size_t)ctx->W * ctx->H * (size_t)(nframes - nframes % ctx->C); }
+
+int dct3d_encode_u8(dct3d_ctx *ctx, const uint8_t *frames, int nframes, uint8_t *stream, size_t cap,
+                    uint64_t *nbits, size_t *nbytes)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if ((rc = check_frames(ctx, nframes))) return rc;
+    if (!stream || cap == 0) return fail(ctx, DCT3D_E_INVALID, "null stream buffer");
+    const size_t n = frame_bytes(ctx, nframes);
+    if (n && !frames) return fail(ctx, DCT3D_E_INVALID, "null frame pointer");
+    // device stream capacity: the caller's cap, rounded up to words, plus slack
+    const size_t dcap = ((cap + 3) & ~(size_t)3) + 64;
+    CU_CHECK(ctx, ctx->frames.reserve(n + 16));
+    CU_CHECK(ctx, ctx->bits.reserve(dcap));
+    if (n) H2D(ctx, ctx->frames.p, frames, n);
+    uint64_t end = 0;
+    if ((rc = dct3d_encode_u8_dev(ctx, ctx->frames.p, nframes, ctx->bits.p, dcap, 0, &end, nullptr))) return rc;
+    const size_t nb = (size_t)(end / 8) + 1;
+    if (nb > cap) return fail(ctx, DCT3D_E_OVERFLOW, "stream needs %zu bytes, buffer has %zu", nb, cap);
+    D2H(ctx, stream, ctx->bits.p, nb);
+    SYNC(ctx);
+    if (nbits) *nbits = end;
+    if (nbytes) *nbytes = nb;
+    return DCT3D_OK;
+}
+
+int dct3d_decode_u8(dct3d_ctx *ctx, const uint8_t *stream, size_t nbytes, int nframes, uint8_t *frames)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if ((rc = check_frames(ctx, nframes))) return rc;
+    const size_t n = frame_bytes(ctx, nframes);
+    if (n == 0) return DCT3D_OK;
+    if (!stream || !frames) return fail(ctx, DCT3D_E_INVALID, "null pointer");
+    const size_t padded = ((nbytes + 3) & ~(size_t)3) + 8;
+    CU_CHECK(ctx, ctx->bits.reserve(padded));
+    CU_CHECK(ctx, ctx->frames.reserve(n + 16));
+    CU_CHECK(ctx, cudaMemsetAsync((uint8_t *)ctx->bits.p + (nbytes & ~(size_t)3), 0, padded - (nbytes & ~(size_t)3), ctx->stream));
+    H2D(ctx, ctx->bits.p, stream, nbytes);
+    uint64_t end = 0;
+    rc = dct3d_decode_u8_dev(ctx, ctx->bits.p, nbytes, 0, nframes, ctx->frames.p, &end, nullptr);
+    if (rc == DCT3D_E_NEED_MORE) return fail(ctx, DCT3D_E_STREAM, "Exp-Golomb stream truncated: %s", ctx->err.c_str());
+    if (rc) return rc;
+    D2H(ctx, frames, ctx->frames.p, n);
+    SYNC(ctx);
+    return DCT3D_OK;
+}
+
+int dct3d_stream_begin(dct3d_ctx *ctx)
+{
+    if (!ctx) return fail(nullptr, DCT3D_E_INVALID, "null context");
+    ctx->carry_byte = 0;
+    ctx->carry_bits = 0;
+    return DCT3D_OK;
+}
+
+int dct3d_stream_encode(dct3d_ctx *ctx, const uint8_t *frames, int nframes, int last, uint8_t *out, size_t cap, size_t *nbytes)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if ((rc = check_frames(ctx, nframes))) return rc;
+    if (nframes % ctx->C) return fail(ctx, DCT3D_E_INVALID, "streaming encode needs a multiple of %d frames", ctx->C);
+    if (!out) return fail(ctx, DCT3D_E_INVALID, "null output buffer");
+    const size_t n = frame_bytes(ctx, nframes);
+    const size_t dcap = ((cap + 3) & ~(size_t)3) + 64;
+    CU_CHECK(ctx, ctx->frames.reserve(n + 16));
+    CU_CHECK(ctx, ctx->bits.reserve(dcap));
+    // the carried partial byte becomes byte 0 of the device buffer
+    CU_CHECK(ctx, cudaMemsetAsync(ctx->bits.p, 0, 4, ctx->stream));
+    CU_CHECK(ctx, cudaMemcpyAsync(ctx->bits.p, &ctx->carry_byte, 1, cudaMemcpyHostToDevice, ctx->stream));
+    if (n) H2D(ctx, ctx->frames.p, frames, n);
+    uint64_t end = 0;
+    if ((rc = dct3d_encode_u8_dev(ctx, ctx->frames.p, nframes, ctx->bits.p, dcap, (uint64_t)ctx->carry_bits, &end, nullptr))) return rc;
+    const size_t full = (size_t)(end / 8);
+    const size_t give = last ? full + 1 : full;
+    if (give > cap) return fail(ctx, DCT3D_E_OVERFLOW, "stream needs %zu bytes, buffer has %zu", give, cap);
+    if (give) D2H(ctx, out, ctx->bits.p, give);
+    uint8_t tail = 0;
+    CU_CHECK(ctx, cudaMemcpyAsync(&tail, (uint8_t *)ctx->bits.p + full, 1, cudaMemcpyDeviceToHost, ctx->stream));
+    SYNC(ctx);
+    ctx->carry_byte = last ? 0 : tail;
+    ctx->carry_bits = last ? 0 : (int)(end % 8);
+    if (nbytes) *nbytes = give;
+    return DCT3D_OK;
+}
+
+int dct3d_stream_decode(dct3d_ctx *ctx, const uint8_t *in, size_t nbytes, uint64_t *bitpos, int nframes, uint8_t *frames)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if ((rc = check_frames(ctx, nframes))) return rc;
+    if (!bitpos) return fail(ctx, DCT3D_E_INVALID, "null bit position");
+    const size_t n = frame_bytes(ctx, nframes);
+    if (n == 0) return DCT3D_OK;
+    if (!in || !frames) return fail(ctx, DCT3D_E_INVALID, "null pointer");
+    const size_t padded = ((nbytes + 3) & ~(size_t)3) + 8;
+    CU_CHECK(ctx, ctx->bits.reserve(padded));
+    CU_CHECK(ctx, ctx->frames.reserve(n + 16));
+    CU_CHECK(ctx, cudaMemsetAsync((uint8_t *)ctx->bits.p + (nbytes & ~(size_t)3), 0, padded - (nbytes & ~(size_t)3), ctx->stream));
+    H2D(ctx, ctx->bits.p, in, nbytes);
+    uint64_t end = 0;
+    if ((rc = dct3d_decode_u8_dev(ctx, ctx->bits.p, nbytes, *bitpos, nframes, ctx->frames.p, &end, nullptr))) return rc;
+    D2H(ctx, frames, ctx->frames.p, n);
+    SYNC(ctx);
+    *bitpos = end;
+    return DCT3D_OK;
+}
+
+int dct3d_forward_f32(dct3d_ctx *ctx, const float *in, float *out, int nslabs)
+{
+    if (!ctx || nslabs < 0) return fail(ctx, DCT3D_E_INVALID, "bad argument");
+    return transform_host<float>(ctx, in, out, (size_t)ctx->W * ctx->H * ctx->C * nslabs, nslabs, dct3d_forward_f32_dev);
+}
+int dct3d_inverse_f32(dct3d_ctx *ctx, const float *in, float *out, int nslabs)
+{
+    if (!ctx || nslabs < 0) return fail(ctx, DCT3D_E_INVALID, "bad argument");
+    return transform_host<float>(ctx, in, out, (size_t)ctx->W * ctx->H * ctx->C * nslabs, nslabs, dct3d_inverse_f32_dev);
+}
+int dct3d_forward_f64(dct3d_ctx *ctx, const double *in, double *out, int nframes)
+{
+    if (!ctx || nframes < 0) return fail(ctx, DCT3D_E_INVALID, "bad argument");
+    return transform_host<double>(ctx, in, out, frame_bytes(ctx, nframes), nframes, dct3d_forward_f64_dev);
+}
+int dct3d_inverse_f64(dct3d_ctx *ctx, const double *in, double *out, int nframes)
+{
+    if (!ctx || nframes < 0) return fail(ctx, DCT3D_E_INVALID, "bad argument");
+    return transform_host<double>(ctx, in, out, frame_bytes(ctx, nframes), nframes, dct3d_inverse_f64_dev);
+}
+
+int dct3d_quantize_u8(dct3d_ctx *ctx, const uint8_t *frames, int nframes, int16_t *qcubes)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if ((rc = check_frames(ctx, nframes))) return rc;
+    const size_t n = frame_bytes(ctx, nframes);
+    if (n == 0) return DCT3D_OK;
+    if (!frames || !qcubes) return fail(ctx, DCT3D_E_INVALID, "null pointer");
+    CU_CHECK(ctx, ctx->frames.reserve(n + 16));
+    CU_CHECK(ctx, ctx->q.reserve(n * 2));
+    H2D(ctx, ctx->frames.p, frames, n);
+    if ((rc = dct3d_quantize_u8_dev(ctx, ctx->frames.p, nframes, ctx->q.p, nullptr))) return rc;
+    D2H(ctx, qcubes, ctx->q.p, n * 2);
+    SYNC(ctx);
+    return DCT3D_OK;
+}
+
+int dct3d_reconstruct_i16(dct3d_ctx *ctx, const int16_t *qcubes, int nframes, uint8_t *frames)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if ((rc = check_frames(ctx, nframes))) return rc;
+    const size_t n = frame_bytes(ctx, nframes);
+    if (n == 0) return DCT3D_OK;
+    if (!frames || !qcubes) return fail(ctx, DCT3D_E_INVALID, "null pointer");
+    CU_CHECK(ctx, ctx->frames.reserve(n + 16));
+    CU_CHECK(ctx, ctx->q.reserve(n * 2));
+    H2D(ctx, ctx->q.p, qcubes, n * 2);
+    if ((rc = dct3d_reconstruct_i16_dev(ctx, ctx->q.p, nframes, ctx->frames.p, nullptr))) return rc;
+    D2H(ctx, frames, ctx->frames.p, n);
+    SYNC(ctx);
+    return DCT3D_OK;
+}
+
+int dct3d_eg_encode_i16(dct3d_ctx *ctx, const int16_t *qcubes, size_t ncubes, uint64_t start_bit,
+                        uint8_t *stream, size_t cap, uint64_t *end_bit)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (!stream || cap == 0) return fail(ctx, DCT3D_E_INVALID, "null stream buffer");
+    const size_t cs = (size_t)ctx->C * ctx->C * ctx->C;
+    const size_t first = (size_t)(start_bit / 8);
+    if (first >= cap) return fail(ctx, DCT3D_E_OVERFLOW, "start bit beyond the buffer");
+    const size_t dcap = ((cap + 3) & ~(size_t)3) + 64;
+    CU_CHECK(ctx, ctx->q.reserve(ncubes * cs * 2 + 16));
+    CU_CHECK(ctx, ctx->bits.reserve(dcap));
+    if (ncubes) H2D(ctx, ctx->q.p, qcubes, ncubes * cs * 2);
+    // bytes up to and including the partial byte come from the caller
+    CU_CHECK(ctx, cudaMemsetAsync(ctx->bits.p, 0, ((first + 4) & ~(size_t)3), ctx->stream));
+    H2D(ctx, ctx->bits.p, stream, first + ((start_bit % 8) ? 1 : 0));
+    uint64_t end = 0;
+    if ((rc = dct3d_eg_encode_i16_dev(ctx, ctx->q.p, ncubes, start_bit, ctx->bits.p, dcap, &end, nullptr))) return rc;
+    const size_t nb = (size_t)(end / 8) + 1;
+    if (nb > cap) return fail(ctx, DCT3D_E_OVERFLOW, "stream needs %zu bytes, buffer has %zu", nb, cap);
+    D2H(ctx, stream + first, (uint8_t *)ctx->bits.p + first, nb - first);
+    SYNC(ctx);
+    if (end_bit) *end_bit = end;
+    return DCT3D_OK;
+}
+
+int dct3d_eg_decode_i16(dct3d_ctx *ctx, const uint8_t *stream, size_t nbytes, uint64_t start_bit,
+                        size_t ncubes, int16_t *qcubes, uint64_t *end_bit)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (ncubes == 0) { if (end_bit) *end_bit = start_bit; return DCT3D_OK; }
+    if (!stream || !qcubes) return fail(ctx, DCT3D_E_INVALID, "null pointer");
+    const size_t cs = (size_t)ctx->C * ctx->C * ctx->C;
+    const size_t padded = ((nbytes + 3) & ~(size_t)3) + 8;
+    CU_CHECK(ctx, ctx->bits.reserve(padded));
+    CU_CHECK(ctx, ctx->q.reserve(ncubes * cs * 2 + 16));
+    CU_CHECK(ctx, cudaMemsetAsync((uint8_t *)ctx->bits.p + (nbytes & ~(size_t)3), 0, padded - (nbytes & ~(size_t)3), ctx->stream));
+    H2D(ctx, ctx->bits.p, stream, nbytes);
+    uint64_t end = 0;
+    rc = dct3d_eg_decode_i16_dev(ctx, ctx->bits.p, nbytes, start_bit, ncubes, ctx->q.p, &end, nullptr);
+    if (rc == DCT3D_E_NEED_MORE) return fail(ctx, DCT3D_E_STREAM, "Exp-Golomb stream truncated: %s", ctx->err.c_str());
+    if (rc) return rc;
+    D2H(ctx, qcubes, ctx->q.p, ncubes * cs * 2);
+    SYNC(ctx);
+    if (end_bit) *end_bit = end;
+    return DCT3D_OK;
+}
+
+}  // extern "C"

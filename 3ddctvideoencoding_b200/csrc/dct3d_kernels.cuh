@@ -1,0 +1,842 @@
+// dct3d_kernels.cuh -- CUDA kernels (sm_100a) for the 3D-DCT codec hot path.
+//
+// Design (see DESIGN.md for the full account):
+//   * A "tile" is 32 consecutive cubes of the stream order.  Pixels arrive as TMA boxes of
+//     128 px x 1 row x C frames (one op per row, SWIZZLE_128B) straight from the planar frame
+//     stack -- this is what replaces the host-side u8 -> float cube reshuffle readCubes /
+//     writeCubes (reference 3d-DCT-video-encoding-OpenCL/encoder.c:10-45, decoder.c:10-46).
+//   * Transform: C threads own one cube.  Thread t first holds the CxC plane of frame t in
+//     registers and runs the 1D butterflies along x and y, the cube is then transposed through
+//     a swizzled shared-memory exchange so that thread j holds all (k0, k2) for row-frequency
+//     k1 = j, and the butterflies along t follow.  24 -> 13.5 flops/sample vs the naive form.
+//   * The quantiser is one FFMA per coefficient (reciprocal table per lane + magic rounding).
+//   * In that layout the elements a thread owns on one diagonal k0+k2 are CONTIGUOUS in the
+//     reference's zig-zag order (CubeUtils.c:17-42: slices of constant x+y+z, y outer, z middle),
+//     so the zig-zag reorder is 64 STS.U16 with per-lane base registers and immediate offsets.
+//   * Entropy stage: one lane of warp 0 per cube (32 cubes in flight): count pass, warp scan,
+//     decoupled look-back across tiles for the global bit offset, write pass straight to the
+//     global stream (plain stores inside a cube, OR-merge for the two boundary words).
+//     The bitstream never visits the host (reference: ExpGolomb.c:32-64 on one host thread).
+//   * Decode mirrors it: stream index discovery (segment scan + fix-up), one thread per cube
+//     parse, then dequantise + inverse butterflies + clamp + truncate to u8.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "dct_math.h"
+#include "eg_bits.h"
+
+namespace dct3d {
+
+constexpr int kTileCubes = 32;   // cubes per tile = lanes of the entropy warp
+constexpr int kBoxW = 128;       // pixels (bytes) per TMA box row
+constexpr int kWarps = 4;        // transform warps per CTA
+constexpr int kThreads = kWarps * 32;
+
+template <int C>
+struct Geo {
+    static constexpr int CS = C * C * C;
+    static constexpr int CPW = 32 / C;                       // cubes per warp pass
+    static constexpr int CUBES_PER_BOX = kBoxW / C;          // 16 (C=8) / 32 (C=4)
+    static constexpr int BOXES_PER_TILE = kTileCubes / CUBES_PER_BOX;
+    static constexpr int ROW_BYTES = kBoxW * C;              // one TMA op: C frames of one row
+    static constexpr int BOX_BYTES = ROW_BYTES * C;
+    static constexpr int IN_BYTES = BOX_BYTES * BOXES_PER_TILE;
+    static constexpr int PASSES = kTileCubes / (kWarps * CPW);
+    static constexpr int ZZ_STRIDE = CS + 8;                 // int16 units; odd multiple of 16 B
+    static constexpr int NDIAG = 2 * C - 1;
+    static constexpr int CHUNKS = CS / 16;                   // 16-coefficient chunks per cube
+};
+
+// Frame / cube geometry shared by host and device.
+struct Layout {
+    int W, H, C;
+    int bx, by;          // cubes per row / cube rows
+    int bxb;             // boxes per cube row
+    int nslabs;
+    long long nboxes, ntiles, ncubes;
+};
+
+struct EncParams {
+    Layout L;
+    const uint8_t *frames;
+    uint32_t *out_words;            // stream as 32-bit words (memory byte order)
+    unsigned long long cap_bits;    // capacity of out_words in bits
+    unsigned long long start_bit;
+    unsigned long long *tile_status;  // [ntiles], zeroed: flag<<62 | inclusive bit count
+    unsigned int *ticket;             // zeroed
+    unsigned int *err;                // zeroed; bit0 = overflow
+    unsigned long long *end_bit;      // out: start_bit + total bits
+    int16_t *qcubes;                  // EMIT_Q: natural-order int16 cubes out
+    const int16_t *qcubes_in;         // EG-only kernel: natural-order int16 cubes in
+    int use_tma;
+};
+
+// ------------------------------------------------------------------------------------------
+// zig-zag tables (filled by the host from the CubeUtils.diagonalSlices order)
+// ------------------------------------------------------------------------------------------
+struct ZzTables {
+    uint16_t base8[8][15];   // zig-zag index of the first element of thread j's run on diagonal s'
+    uint16_t base4[4][7];
+    uint16_t lin8[512];      // zig-zag position -> natural index k2 + 8*k1 + 64*k0
+    uint16_t lin4[64];
+};
+__constant__ ZzTables c_zz;
+
+template <int C> __device__ __forceinline__ uint16_t zz_base(int j, int s) { return C == 8 ? c_zz.base8[j][s] : c_zz.base4[j][s]; }
+template <int C> __device__ __forceinline__ const uint16_t *zz_lin() { return C == 8 ? c_zz.lin8 : c_zz.lin4; }
+
+// ------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + TMA
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *tmap, int x, int y, int z, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(smem_u32(dst)), "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------
+// Box geometry
+// ------------------------------------------------------------------------------------------
+struct BoxPos { int slab, byi, bxb, nvalid; long long cube0; };
+
+template <int C>
+__device__ __forceinline__ BoxPos box_pos(const Layout &L, long long b)
+{
+    BoxPos p;
+    const int per_slab = L.by * L.bxb;
+    p.slab = (int)(b / per_slab);
+    const int rem = (int)(b - (long long)p.slab * per_slab);
+    p.byi = rem / L.bxb;
+    p.bxb = rem - p.byi * L.bxb;
+    const int bxi0 = p.bxb * Geo<C>::CUBES_PER_BOX;
+    p.nvalid = min(Geo<C>::CUBES_PER_BOX, L.bx - bxi0);
+    p.cube0 = ((long long)p.slab * L.by + p.byi) * L.bx + bxi0;
+    return p;
+}
+
+// Shared-memory address of byte xb of row (y, t) inside a box, SWIZZLE_128B pattern: the box
+// is C blocks (one per y) of C rows (t) of 128 B; the 16-byte chunk index is XORed with
+// bits [7:9] of the byte offset.
+template <int C>
+__device__ __forceinline__ int in_offset(int y, int t, int xb)
+{
+    const int row = y * C + t;
+    return row * 128 + ((((xb >> 4) ^ row) & 7) << 4) + (xb & 15);
+}
+
+// ------------------------------------------------------------------------------------------
+// Exchange (transpose between "thread = frame t" and "thread = row frequency k1") through a
+// per-warp shared buffer of CPW cubes x C*C 16-byte vectors.  One round moves vector h of
+// every row; chunk (t, k1) sits at t*C + (k1 ^ t) so both the 8 writers (t = 0..7, fixed k1)
+// and the 8 readers (k1 = 0..7, fixed t) of a quarter warp hit 8 distinct bank groups.
+// ------------------------------------------------------------------------------------------
+template <int C, typename T>
+struct Xch {
+    static constexpr int VEC = 16 / sizeof(T);          // elements per 16-byte vector
+    static constexpr int VPR = C / VEC;                 // vectors per row (rounds)
+    static constexpr int CUBE_BYTES = C * C * 16;
+    static constexpr int WARP_BYTES = (32 / C) * CUBE_BYTES;
+
+    // a[k1][k2] (thread = t)  ->  b[t][k2] (thread = j = k1)
+    static __device__ __forceinline__ void transpose(uint8_t *wbuf, int cl, int r, const T (&a)[C][C], T (&b)[C][C])
+    {
+        uint4 *base = reinterpret_cast<uint4 *>(wbuf + cl * CUBE_BYTES);
+#pragma unroll
+        for (int h = 0; h < VPR; h++) {
+#pragma unroll
+            for (int k1 = 0; k1 < C; k1++) {
+                uint4 v;
+                T *pv = reinterpret_cast<T *>(&v);
+#pragma unroll
+                for (int e = 0; e < VEC; e++) pv[e] = a[k1][h * VEC + e];
+                base[r * C + (k1 ^ r)] = v;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int t = 0; t < C; t++) {
+                const uint4 v = base[t * C + (r ^ t)];
+                const T *pv = reinterpret_cast<const T *>(&v);
+#pragma unroll
+                for (int e = 0; e < VEC; e++) b[t][h * VEC + e] = pv[e];
+            }
+            __syncwarp();
+        }
+    }
+};
+
+template <int C, typename T>
+__device__ __forceinline__ void fwd_xy(T (&a)[C][C])
+{
+#pragma unroll
+    for (int y = 0; y < C; y++) Dct1D<C, T>::template fwd<1>(&a[y][0]);
+#pragma unroll
+    for (int x = 0; x < C; x++) Dct1D<C, T>::template fwd<C>(&a[0][x]);
+}
+template <int C, typename T>
+__device__ __forceinline__ void inv_yx(T (&a)[C][C])
+{
+#pragma unroll
+    for (int x = 0; x < C; x++) Dct1D<C, T>::template inv<C>(&a[0][x]);
+#pragma unroll
+    for (int y = 0; y < C; y++) Dct1D<C, T>::template inv<1>(&a[y][0]);
+}
+template <int C, typename T>
+__device__ __forceinline__ void fwd_t(T (&b)[C][C])
+{
+#pragma unroll
+    for (int x = 0; x < C; x++) Dct1D<C, T>::template fwd<C>(&b[0][x]);
+}
+template <int C, typename T>
+__device__ __forceinline__ void inv_t(T (&b)[C][C])
+{
+#pragma unroll
+    for (int x = 0; x < C; x++) Dct1D<C, T>::template inv<C>(&b[0][x]);
+}
+
+// u8 -> f32 without the conversion pipe: PRMT the byte into the mantissa of 2^23, subtract.
+__device__ __forceinline__ float byte_to_float(uint32_t word, int i)
+{
+    return __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7540u + i)) - 8388608.0f;
+}
+
+// ------------------------------------------------------------------------------------------
+// Entropy stage, shared by the fused encoder and the int16-cube encoder.
+// ------------------------------------------------------------------------------------------
+struct GlobalSink {
+    uint32_t *words;
+    __device__ __forceinline__ void put(uint64_t idx, uint32_t be, bool shared)
+    {
+        if (shared) atomicOr(words + idx, be); else words[idx] = be;
+    }
+};
+
+constexpr unsigned long long kFlagAgg = 1ull << 62;
+constexpr unsigned long long kFlagPrefix = 2ull << 62;
+constexpr unsigned long long kValMask = (1ull << 62) - 1;
+
+__device__ __forceinline__ unsigned long long ld_status(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_status(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Called by ONE full warp.  total = this tile's bit count.  Returns the absolute bit offset of
+// the tile (decoupled look-back over the predecessors' status words).
+__device__ __forceinline__ unsigned long long tile_lookback(unsigned long long *status, long long tile,
+                                                            unsigned long long total, unsigned long long start_bit, int lane,
+                                                            unsigned int *err)
+{
+    if (tile == 0) {
+        if (lane == 0) st_status(status, kFlagPrefix | (start_bit + total));
+        return start_bit;
+    }
+    if (lane == 0) st_status(status + tile, kFlagAgg | total);
+    unsigned long long excl = 0;
+    long long look = tile - 1;
+    for (;;) {
+        const long long idx = look - lane;
+        unsigned long long st;
+        if (idx >= 0) {
+            unsigned spins = 0;
+            do {
+                st = ld_status(status + idx);
+                // a predecessor always holds an earlier ticket and is therefore resident; the bound only
+                // turns a logic error into a reported failure instead of a hung GPU
+                if ((st >> 62) == 0 && ++spins > (1u << 24)) { atomicOr(err, 8u); st = kFlagPrefix; }
+            } while ((st >> 62) == 0);
+        } else {
+            st = (idx == -1) ? (kFlagPrefix | start_bit) : kFlagAgg;  // virtual tile -1 carries start_bit
+        }
+        const unsigned pmask = __ballot_sync(0xffffffffu, (st >> 62) == 2);
+        const int first = pmask ? (__ffs((int)pmask) - 1) : 32;
+        unsigned long long v = (lane <= first) ? (st & kValMask) : 0ull;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+        excl += v;
+        if (pmask) break;
+        look -= 32;
+    }
+    if (lane == 0) st_status(status + tile, kFlagPrefix | (excl + total));
+    return excl;
+}
+
+// Warp 0: lane = cube slot of the tile.  zz/cmask in shared memory.
+template <int C>
+__device__ __forceinline__ void entropy_stage(const EncParams &P, long long tile, const int16_t *s_zz,
+                                              const uint32_t *s_cmask, uint32_t validmask, int lane)
+{
+    using G = Geo<C>;
+    const bool valid = (validmask >> lane) & 1u;
+    const int16_t *zz = s_zz + lane * G::ZZ_STRIDE;
+    const uint32_t cm = valid ? s_cmask[lane] : 0u;
+    const uint32_t nb = valid ? eg_count_cube<G::CS>(zz, cm) : 0u;
+    uint32_t incl = nb;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    const unsigned long long tile_off = tile_lookback(P.tile_status, tile, total, P.start_bit, lane, P.err);
+    if (tile == P.L.ntiles - 1 && lane == 0) *P.end_bit = tile_off + total;
+    if (valid) {
+        const unsigned long long off = tile_off + (incl - nb);
+        if (off + nb + 64 > P.cap_bits) {
+            atomicOr(P.err, 1u);
+        } else {
+            GlobalSink sink{P.out_words};
+            eg_write_cube<G::CS>(zz, cm, off, sink);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Fused encoder: u8 frames -> Exp-Golomb stream (EMIT_Q = false) or -> int16 cubes (true).
+// Persistent CTAs take tiles from an atomic ticket, in stream order.
+// ------------------------------------------------------------------------------------------
+template <int C>
+struct EncSmem {
+    using G = Geo<C>;
+    static constexpr int IN_OFF = 0;
+    static constexpr int XCH_OFF = IN_OFF + G::IN_BYTES;
+    static constexpr int ZZ_OFF = XCH_OFF + kWarps * Xch<C, float>::WARP_BYTES;
+    static constexpr int CM_OFF = ZZ_OFF + kTileCubes * G::ZZ_STRIDE * 2;
+    static constexpr int BAR_OFF = CM_OFF + kTileCubes * 4;
+    static constexpr int TOTAL = BAR_OFF + 32;
+};
+
+template <int C, bool EMIT_Q>
+__global__ void __launch_bounds__(kThreads, 3)
+encode_kernel(const __grid_constant__ CUtensorMap tmap, const EncParams P)
+{
+    using G = Geo<C>;
+    using S = EncSmem<C>;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t *s_in = smem + S::IN_OFF;
+    uint8_t *s_xch = smem + S::XCH_OFF;
+    int16_t *s_zz = reinterpret_cast<int16_t *>(smem + S::ZZ_OFF);
+    uint32_t *s_cmask = reinterpret_cast<uint32_t *>(smem + S::CM_OFF);
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem + S::BAR_OFF);
+    long long *s_tile = reinterpret_cast<long long *>(smem + S::BAR_OFF + 8);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int cl = lane / C, r = lane % C;   // cube within the warp pass; t (stage 1) or k1 (stage 2)
+    const Layout &L = P.L;
+
+    if (tid == 0 && P.use_tma) mbar_init(s_bar, 1);
+
+    // per-lane constants: reciprocal quantiser and zig-zag run bases for k1 = r
+    float rq[G::NDIAG];
+    uint32_t zb[G::NDIAG];
+#pragma unroll
+    for (int s = 0; s < G::NDIAG; s++) {
+        rq[s] = 1.0f / (float)quant_divisor(s + r);
+        zb[s] = zz_base<C>(r, s);
+    }
+    uint32_t parity = 0;
+    __syncthreads();
+
+    for (;;) {
+        if (tid == 0) {
+            const long long tile = (long long)atomicAdd(P.ticket, 1u);
+            *s_tile = tile;
+            if (P.use_tma && tile < L.ntiles) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_expect_tx(s_bar, G::IN_BYTES);
+#pragma unroll 1
+                for (int bi = 0; bi < G::BOXES_PER_TILE; bi++) {
+                    const long long b = tile * G::BOXES_PER_TILE + bi;
+                    // a box past the end of the clip is loaded from coordinates outside the tensor: zero fill
+                    const BoxPos bp = b < L.nboxes ? box_pos<C>(L, b) : BoxPos{L.nslabs, 0, 0, 0, 0};
+#pragma unroll 1
+                    for (int y = 0; y < C; y++)
+                        tma_load_3d(s_in + bi * G::BOX_BYTES + y * G::ROW_BYTES, &tmap, bp.bxb * kBoxW, bp.byi * C + y,
+                                    bp.slab * C, s_bar);
+                }
+            }
+        }
+        __syncthreads();
+        const long long tile = *s_tile;
+        if (tile >= L.ntiles) break;
+
+        uint32_t validmask = 0;
+#pragma unroll
+        for (int bi = 0; bi < G::BOXES_PER_TILE; bi++) {
+            const long long b = tile * G::BOXES_PER_TILE + bi;
+            if (b < L.nboxes) {
+                const int nv = box_pos<C>(L, b).nvalid;
+                validmask |= (nv >= 32 ? 0xffffffffu : ((1u << nv) - 1u)) << (bi * G::CUBES_PER_BOX);
+            }
+        }
+
+        if (!P.use_tma) {
+            // plain loader: C-byte pieces (always aligned since W % C == 0), same swizzled layout
+            constexpr int PIECES = G::IN_BYTES / C;
+            for (int i = tid; i < PIECES; i += kThreads) {
+                const int bi = i / (G::BOX_BYTES / C);
+                const int rem = i - bi * (G::BOX_BYTES / C);
+                const int row = rem / (kBoxW / C);          // y*C + t
+                const int cb = rem - row * (kBoxW / C);     // cube in box
+                const int y = row / C, t = row - y * C;
+                const long long b = tile * G::BOXES_PER_TILE + bi;
+                uint32_t lo = 0, hi = 0;
+                if (b < L.nboxes) {
+                    const BoxPos bp = box_pos<C>(L, b);
+                    if (cb < bp.nvalid) {
+                        const uint8_t *src = P.frames + ((size_t)(bp.slab * C + t) * L.H + (bp.byi * C + y)) * L.W +
+                                             bp.bxb * kBoxW + cb * C;
+                        if (C == 8) { const uint2 v = *reinterpret_cast<const uint2 *>(src); lo = v.x; hi = v.y; }
+                        else lo = *reinterpret_cast<const uint32_t *>(src);
+                    }
+                }
+                uint8_t *dst = s_in + bi * G::BOX_BYTES + in_offset<C>(y, t, cb * C);
+                if (C == 8) *reinterpret_cast<uint2 *>(dst) = make_uint2(lo, hi);
+                else *reinterpret_cast<uint32_t *>(dst) = lo;
+            }
+            __syncthreads();
+        } else {
+            unsigned spins = 0;
+            while (!mbar_try_wait(s_bar, parity)) {
+                if (++spins > (1u << 22)) { if (tid == 0) atomicOr(P.err, 16u); break; }   // never hang the GPU
+            }
+            parity ^= 1;
+        }
+
+        // ---- transform passes -----------------------------------------------------------
+#pragma unroll 1
+        for (int p = 0; p < G::PASSES; p++) {
+            const int slot = p * (kWarps * G::CPW) + warp * G::CPW + cl;
+            const int bi = slot / G::CUBES_PER_BOX, cb = slot % G::CUBES_PER_BOX;
+            float a[C][C], bq[C][C];
+            const uint8_t *box = s_in + bi * G::BOX_BYTES;
+#pragma unroll
+            for (int y = 0; y < C; y++) {
+                const uint8_t *src = box + in_offset<C>(y, r, cb * C);
+                if (C == 8) {
+                    const uint2 v = *reinterpret_cast<const uint2 *>(src);
+#pragma unroll
+                    for (int x = 0; x < 4; x++) { a[y][x] = byte_to_float(v.x, x); a[y][(x + 4) % C] = byte_to_float(v.y, x); }
+                } else {
+                    const uint32_t v = *reinterpret_cast<const uint32_t *>(src);
+#pragma unroll
+                    for (int x = 0; x < 4; x++) a[y][x % C] = byte_to_float(v, x);
+                }
+            }
+            fwd_xy<C, float>(a);
+            Xch<C, float>::transpose(s_xch + warp * Xch<C, float>::WARP_BYTES, cl, r, a, bq);
+            fwd_t<C, float>(bq);
+            // bq[k0][k2] is coefficient (k0, k1 = r, k2)
+            if (EMIT_Q) {
+                if ((validmask >> slot) & 1u) {
+                    const BoxPos bp = box_pos<C>(L, tile * G::BOXES_PER_TILE + bi);
+                    int16_t *dst = P.qcubes + (size_t)(bp.cube0 + cb) * G::CS + r * C;
+#pragma unroll
+                    for (int k0 = 0; k0 < C; k0++) {
+                        uint32_t w[C / 2];
+#pragma unroll
+                        for (int k2 = 0; k2 < C; k2 += 2) {
+                            const uint32_t q0 = (uint32_t)quantize_f32(bq[k0][k2], rq[k0 + k2]) & 0xffffu;
+                            const uint32_t q1 = (uint32_t)quantize_f32(bq[k0][k2 + 1], rq[k0 + k2 + 1]) & 0xffffu;
+                            w[k2 / 2] = q0 | (q1 << 16);
+                        }
+                        if (C == 8) *reinterpret_cast<uint4 *>(dst + k0 * C * C) = make_uint4(w[0], w[1], w[2 % (C / 2)], w[3 % (C / 2)]);
+                        else *reinterpret_cast<uint2 *>(dst + k0 * C * C) = make_uint2(w[0], w[1]);
+                    }
+                }
+            } else {
+                int16_t *zz = s_zz + slot * G::ZZ_STRIDE;
+#pragma unroll
+                for (int k0 = 0; k0 < C; k0++) {
+#pragma unroll
+                    for (int k2 = 0; k2 < C; k2++) {
+                        const int s = k0 + k2;
+                        const int k0min = s > C - 1 ? s - (C - 1) : 0;
+                        zz[zb[s] + (k0 - k0min)] = (int16_t)quantize_f32(bq[k0][k2], rq[s]);
+                    }
+                }
+                __syncwarp();
+                // 16-coefficient chunk masks of this pass's cubes
+                constexpr int ITER = (G::CPW * G::CHUNKS) / 32;   // 4 (C=8) / 1 (C=4)
+                const int slot0 = p * (kWarps * G::CPW) + warp * G::CPW;
+#pragma unroll
+                for (int it = 0; it < ITER; it++) {
+                    const int ci = it * 32 + lane;
+                    const int cube = ci / G::CHUNKS, chunk = ci % G::CHUNKS;
+                    const uint4 *q = reinterpret_cast<const uint4 *>(s_zz + (slot0 + cube) * G::ZZ_STRIDE + chunk * 16);
+                    const uint4 v0 = q[0], v1 = q[1];
+                    const uint32_t any = v0.x | v0.y | v0.z | v0.w | v1.x | v1.y | v1.z | v1.w;
+                    const uint32_t bal = __ballot_sync(0xffffffffu, any != 0);
+                    if (G::CHUNKS == 32) { if (lane == 0) s_cmask[slot0 + it] = bal; }
+                    else { if (lane < 32 / G::CHUNKS) s_cmask[slot0 + lane] = (bal >> (lane * G::CHUNKS)) & ((1u << (G::CHUNKS & 31)) - 1u); }
+                }
+            }
+        }
+        __syncthreads();
+        if (!EMIT_Q && warp == 0) entropy_stage<C>(P, tile, s_zz, s_cmask, validmask, lane);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Exp-Golomb encoder for int16 cubes already in global memory (natural order): gathers the
+// cubes of a tile into the zig-zag buffer, then the same entropy stage.
+// ------------------------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(kThreads)
+eg_encode_kernel(const EncParams P)
+{
+    using G = Geo<C>;
+    __shared__ __align__(16) int16_t s_zz[kTileCubes * G::ZZ_STRIDE];
+    __shared__ uint32_t s_cmask[kTileCubes];
+    __shared__ long long s_tile;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint16_t *lin = zz_lin<C>();
+    for (;;) {
+        if (tid == 0) s_tile = (long long)atomicAdd(P.ticket, 1u);
+        __syncthreads();
+        const long long tile = s_tile;
+        if (tile >= P.L.ntiles) break;
+        const long long cube0 = tile * kTileCubes;
+        const int nv = (int)min((long long)kTileCubes, P.L.ncubes - cube0);
+        for (int i = tid; i < nv * G::CS; i += kThreads) {
+            const int cube = i / G::CS, pos = i % G::CS;
+            s_zz[cube * G::ZZ_STRIDE + pos] = P.qcubes_in[(size_t)(cube0 + cube) * G::CS + lin[pos]];
+        }
+        __syncthreads();
+        // chunk masks: one warp per 8 cubes
+        for (int cube = warp; cube < nv; cube += kWarps) {
+            uint32_t m = 0;
+            for (int c0 = 0; c0 < G::CHUNKS; c0 += 32) {
+                const int chunk = c0 + lane;
+                uint32_t any = 0;
+                if (chunk < G::CHUNKS) {
+                    const uint4 *q = reinterpret_cast<const uint4 *>(s_zz + cube * G::ZZ_STRIDE + chunk * 16);
+                    const uint4 v0 = q[0], v1 = q[1];
+                    any = v0.x | v0.y | v0.z | v0.w | v1.x | v1.y | v1.z | v1.w;
+                }
+                m |= __ballot_sync(0xffffffffu, any != 0);
+            }
+            if (lane == 0) s_cmask[cube] = m;
+        }
+        __syncthreads();
+        if (warp == 0) entropy_stage<C>(P, tile, s_zz, s_cmask, nv >= 32 ? 0xffffffffu : ((1u << nv) - 1u), lane);
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Decode side
+// ------------------------------------------------------------------------------------------
+struct StreamSource {
+    const uint32_t *words; unsigned long long nwords;
+    __device__ __forceinline__ uint32_t word(uint64_t i) const { return i < nwords ? bswap32(__ldg(words + i)) : 0u; }
+};
+
+struct DecParams {
+    Layout L;
+    const uint32_t *words; unsigned long long nwords; unsigned long long nbits_total;  // stream
+    unsigned long long start_bit;
+    // index discovery
+    unsigned int seg_bits; unsigned long long nseg;
+    unsigned int *seg_count;            // [nseg] codes starting in the segment
+    unsigned int *seg_over;             // [nseg+1] overhang INTO segment k (seg_over[0] = 0)
+    unsigned int *seg_used;             // [nseg] entry overhang used for the current count
+    unsigned long long *seg_first;      // [nseg+1] exclusive prefix of seg_count
+    unsigned int *changed;              // fix-up flag
+    unsigned long long *cube_off;       // [ncubes+1] absolute bit offset of every cube
+    unsigned int *err;                  // bit1 = malformed, bit2 = truncated
+    int16_t *qcubes;                    // natural-order cubes
+    uint8_t *frames;
+};
+
+// Pass 1 / fix-up: every thread scans one segment from its current entry overhang.
+__global__ void seg_scan_kernel(const DecParams P, int first_pass)
+{
+    const unsigned long long k = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    if (k >= P.nseg) return;
+    const unsigned int entry = first_pass ? (k == 0 ? 0u : 0u) : P.seg_over[k];
+    if (!first_pass && entry == P.seg_used[k]) return;
+    const unsigned long long seg0 = P.start_bit + k * (unsigned long long)P.seg_bits;
+    unsigned long long lim = seg0 + P.seg_bits;
+    if (lim > P.nbits_total) lim = P.nbits_total;
+    StreamSource src{P.words, P.nwords};
+    uint32_t n = 0; uint64_t next = 0;
+    if (seg0 + entry >= lim) { n = 0; next = seg0 + entry; }
+    else if (!eg_scan_segment(src, seg0 + entry, lim, P.nbits_total, n, next)) { atomicOr(P.err, 2u); next = lim; }
+    P.seg_count[k] = n;
+    P.seg_used[k] = entry;
+    const unsigned int over = (unsigned int)(next > lim ? next - lim : 0);
+    if (first_pass || P.seg_over[k + 1] != over) { P.seg_over[k + 1] = over; if (!first_pass) *P.changed = 1u; }
+}
+
+// Exclusive prefix sum of seg_count (single CTA, 1024 threads, sequential over chunks).
+__global__ void seg_prefix_kernel(const DecParams P)
+{
+    __shared__ unsigned long long s_warp[32];
+    __shared__ unsigned long long s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (unsigned long long base = 0; base < P.nseg; base += 1024) {
+        const unsigned long long k = base + tid;
+        const unsigned long long v = k < P.nseg ? P.seg_count[k] : 0ull;
+        unsigned long long incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const unsigned long long o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned long long w = s_warp[lane], wi = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const unsigned long long o = __shfl_up_sync(0xffffffffu, wi, d); if (lane >= d) wi += o; }
+            s_warp[lane] = wi - w;
+        }
+        __syncthreads();
+        const unsigned long long carry = s_carry;
+        if (k < P.nseg) P.seg_first[k] = carry + s_warp[warp] + incl - v;
+        __syncthreads();
+        if (tid == 1023) s_carry = carry + s_warp[warp] + incl;
+        __syncthreads();
+    }
+    if (tid == 0) P.seg_first[P.nseg] = s_carry;
+}
+
+// Every thread re-walks its segment and records the bit offset of each cube boundary in it.
+template <int CS>
+__global__ void cube_index_kernel(const DecParams P)
+{
+    const unsigned long long k = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    if (k >= P.nseg) return;
+    unsigned long long idx = P.seg_first[k];                      // index of the first code starting here
+    const unsigned long long nxt = P.seg_first[k + 1];
+    const unsigned long long ncodes = (unsigned long long)P.L.ncubes * CS;
+    if (idx >= nxt) return;
+    // first cube boundary at or after idx
+    unsigned long long target = ((idx + CS - 1) / CS) * CS;
+    if (target > ncodes || target >= nxt) return;
+    const unsigned long long seg0 = P.start_bit + k * (unsigned long long)P.seg_bits;
+    StreamSource src{P.words, P.nwords};
+    BitReader<StreamSource> br(src, seg0 + P.seg_over[k]);
+    while (idx < nxt) {
+        if (idx == target) {
+            P.cube_off[target / CS] = br.pos;
+            target += CS;
+            if (target > ncodes || target >= nxt) return;
+        }
+        br.refill();
+        const uint64_t inv = ~br.buf;
+        int ones = inv ? clz64(inv) : 64;
+        if (ones > br.navail) ones = br.navail;
+        if (ones > 0) {
+            const unsigned long long room = target - idx;
+            if ((unsigned long long)ones > room) ones = (int)room;
+            idx += ones;
+            br.skip(ones);
+            continue;
+        }
+        const int z = clz64(br.buf);
+        if (z > 16) return;
+        idx++;
+        br.skip(2 * z + 1);
+    }
+}
+
+struct CubeOut {
+    int16_t *o;
+    __device__ __forceinline__ void put(int idx, int16_t v) { o[idx] = v; }
+};
+
+// One thread per cube: parse 512 (64) codes, scatter the non-zero ones (qcubes pre-zeroed).
+template <int C>
+__global__ void cube_parse_kernel(const DecParams P)
+{
+    using G = Geo<C>;
+    const long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (c >= P.L.ncubes) return;
+    StreamSource src{P.words, P.nwords};
+    CubeOut out{P.qcubes + (size_t)c * G::CS};
+    const unsigned long long start = P.cube_off[c];
+    if (start == ~0ull) { atomicOr(P.err, 4u); return; }   // the stream holds fewer codes than the clip needs
+    const uint64_t end = eg_parse_cube<G::CS>(src, start, zz_lin<C>(), out);
+    if (end == ~0ull) atomicOr(P.err, 2u);
+    else if (end > P.nbits_total) atomicOr(P.err, 4u);
+    else if (c == P.L.ncubes - 1) P.cube_off[P.L.ncubes] = end;
+}
+
+// int16 natural-order cubes -> u8 frames: dequantise, inverse butterflies, clamp, truncate.
+// (reference Decoder.java:78-117, decoder.c:48-59 + 3dDCT.cl:164-265 + decoder.c:29)
+template <int C>
+__global__ void __launch_bounds__(kThreads, 4)
+reconstruct_kernel(const Layout L, const int16_t *__restrict__ qcubes, uint8_t *__restrict__ frames)
+{
+    using G = Geo<C>;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int cl = lane / C, r = lane % C;
+    float dq[G::NDIAG];
+#pragma unroll
+    for (int s = 0; s < G::NDIAG; s++) dq[s] = (float)quant_divisor(s + r);
+    const long long ngroups = (L.ncubes + G::CPW - 1) / G::CPW;
+    for (long long g = (long long)blockIdx.x * kWarps + warp; g < ngroups; g += (long long)gridDim.x * kWarps) {
+        const long long cube = g * G::CPW + cl;
+        const bool valid = cube < L.ncubes;
+        float b[C][C], a[C][C];
+        // thread = k1 = r: rows (k0, k1) of the cube, C int16 each
+        const int16_t *src = qcubes + (size_t)(valid ? cube : 0) * G::CS + r * C;
+#pragma unroll
+        for (int k0 = 0; k0 < C; k0++) {
+            uint32_t w[4] = {0, 0, 0, 0};
+            if (valid) {
+                if (C == 8) { const uint4 v = __ldg(reinterpret_cast<const uint4 *>(src + k0 * C * C)); w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w; }
+                else { const uint2 v = __ldg(reinterpret_cast<const uint2 *>(src + k0 * C * C)); w[0] = v.x; w[1] = v.y; }
+            }
+#pragma unroll
+            for (int k2 = 0; k2 < C; k2++) {
+                const int q = (int)(int16_t)((w[k2 / 2] >> ((k2 & 1) * 16)) & 0xffffu);
+                b[k0][k2] = (float)q * dq[k0 + k2];
+            }
+        }
+        inv_t<C, float>(b);
+        // b[t][k2] (thread = k1) -> a[k1][k2] (thread = t): the exchange is its own inverse
+        Xch<C, float>::transpose(smem + warp * Xch<C, float>::WARP_BYTES, cl, r, b, a);
+        inv_yx<C, float>(a);
+        if (valid) {
+            const int per_slab = L.by * L.bx;
+            const int slab = (int)(cube / per_slab);
+            const int rem = (int)(cube - (long long)slab * per_slab);
+            const int byi = rem / L.bx, bxi = rem - byi * L.bx;
+            uint8_t *dst = frames + ((size_t)(slab * C + r) * L.H + byi * C) * L.W + bxi * C;
+#pragma unroll
+            for (int y = 0; y < C; y++) {
+                uint32_t w[2] = {0, 0};
+#pragma unroll
+                for (int x = 0; x < C; x++) {
+                    // clamp to [0,255], truncate: add 2^23 rounding toward zero, byte lands in the mantissa
+                    const float v = fminf(fmaxf(a[y][x], 0.0f), 255.0f);
+                    const uint32_t bits = __float_as_uint(__fadd_rz(v, 8388608.0f)) & 0xffu;
+                    w[x / 4] |= bits << ((x & 3) * 8);
+                }
+                if (C == 8) *reinterpret_cast<uint2 *>(dst + (size_t)y * L.W) = make_uint2(w[0], w[1]);
+                else *reinterpret_cast<uint32_t *>(dst + (size_t)y * L.W) = w[0];
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Transform-only seams.
+//   CUBEMAJOR = true : T cube-major in, T cube-major out (the C codec's device boundary)
+//   CUBEMAJOR = false: T planar [F][H][W] in and out      (Java's Transform boundary)
+// ------------------------------------------------------------------------------------------
+// C contiguous elements of T as 16-byte vectors (rows are 16-byte aligned in both layouts).
+template <int C, typename T>
+__device__ __forceinline__ void load_row(const T *p, T (&row)[C], bool valid)
+{
+    constexpr int NV = C * sizeof(T) / 16, VEC = 16 / sizeof(T);
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (valid) v = __ldg(reinterpret_cast<const uint4 *>(p) + i);
+        const T *pv = reinterpret_cast<const T *>(&v);
+#pragma unroll
+        for (int e = 0; e < VEC; e++) row[i * VEC + e] = pv[e];
+    }
+}
+template <int C, typename T>
+__device__ __forceinline__ void store_row(T *p, const T (&row)[C])
+{
+    constexpr int NV = C * sizeof(T) / 16, VEC = 16 / sizeof(T);
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+        uint4 v;
+        T *pv = reinterpret_cast<T *>(&v);
+#pragma unroll
+        for (int e = 0; e < VEC; e++) pv[e] = row[i * VEC + e];
+        reinterpret_cast<uint4 *>(p)[i] = v;
+    }
+}
+
+template <int C, typename T, bool CUBEMAJOR, bool INVERSE>
+__global__ void __launch_bounds__(kThreads)
+transform_kernel(const Layout L, const T *__restrict__ in, T *__restrict__ out)
+{
+    using G = Geo<C>;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int cl = lane / C, r = lane % C;
+    const long long ngroups = (L.ncubes + G::CPW - 1) / G::CPW;
+    const size_t fs = (size_t)L.W * L.H;
+    for (long long g = (long long)blockIdx.x * kWarps + warp; g < ngroups; g += (long long)gridDim.x * kWarps) {
+        const long long cube = g * G::CPW + cl;
+        const bool valid = cube < L.ncubes;
+        const long long cc = valid ? cube : 0;
+        const int per_slab = L.by * L.bx;
+        const int slab = (int)(cc / per_slab);
+        const int rem = (int)(cc - (long long)slab * per_slab);
+        const int byi = rem / L.bx, bxi = rem - byi * L.bx;
+        // element (i0 = frame / k0, i1 = row / k1, i2 = col / k2) of this cube
+        auto addr = [&](int i0, int i1, int i2) -> size_t {
+            return CUBEMAJOR ? (size_t)cc * G::CS + (size_t)(i0 * C + i1) * C + i2
+                             : (size_t)(slab * C + i0) * fs + (size_t)(byi * C + i1) * L.W + bxi * C + i2;
+        };
+        T a[C][C], b[C][C];
+        if (!INVERSE) {
+#pragma unroll
+            for (int y = 0; y < C; y++) load_row<C, T>(in + addr(r, y, 0), a[y], valid);
+            fwd_xy<C, T>(a);
+            Xch<C, T>::transpose(smem + warp * Xch<C, T>::WARP_BYTES, cl, r, a, b);
+            fwd_t<C, T>(b);
+            if (valid) {
+#pragma unroll
+                for (int k0 = 0; k0 < C; k0++) store_row<C, T>(out + addr(k0, r, 0), b[k0]);
+            }
+        } else {
+#pragma unroll
+            for (int k0 = 0; k0 < C; k0++) load_row<C, T>(in + addr(k0, r, 0), b[k0], valid);
+            inv_t<C, T>(b);
+            Xch<C, T>::transpose(smem + warp * Xch<C, T>::WARP_BYTES, cl, r, b, a);
+            inv_yx<C, T>(a);
+            if (valid) {
+#pragma unroll
+                for (int y = 0; y < C; y++) {
+#pragma unroll
+                    for (int x = 0; x < C; x++) {
+                        const T v = a[y][x];
+                        a[y][x] = v > (T)255 ? (T)255 : (v < (T)0 ? (T)0 : v);   // InverseDCT.java:74-80, 3dDCT.cl:255-262
+                    }
+                    store_row<C, T>(out + addr(r, y, 0), a[y]);
+                }
+            }
+        }
+    }
+}
+
+}  // namespace dct3d

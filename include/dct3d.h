@@ -1,0 +1,156 @@
+/*
+ * dct3d.h -- C ABI of libdct3d.so: the 3D-DCT video codec hot path on NVIDIA B200
+ * (sm_100a).  Plain pointers and sizes only; no C++ or torch types.
+ *
+ * The reference (julianopiccoli/3dDCTVideoEncoding) has no FFI of its own; each entry point
+ * below names the reference code it stands in for.  Paths are relative to the reference
+ * root:  J/ = 3d-DCT-video-encoding/src/br/jpiccoli/video/ ,  C/ = 3d-DCT-video-encoding-OpenCL/ .
+ *
+ * Conventions
+ *   - every function returns DCT3D_OK (0) or a negative DCT3D_E_* code; a description of the
+ *     last failure is available from dct3d_last_error();
+ *   - the caller owns every buffer it passes; a context is not thread-safe (one per thread);
+ *   - raw video = frames x height x width unsigned bytes, frame-major, no header
+ *     (J/Encoder.java:47-56, C/encoder.c:21-35); width and height must be multiples of the
+ *     cube edge, trailing frames that do not fill a cube are ignored (J/Encoder.java:39-40);
+ *   - the Exp-Golomb stream is MSB-first and bit-continuous across cubes and slabs; its length
+ *     in bytes is floor(bits/8)+1 (J/Encoder.java:117, C/encoder.c:270).  zlib wrapping stays
+ *     with the caller, as in the reference (J/Encoder.java:114-125, C/encoder.c:266-274);
+ *   - cube-major order is [slab][block row][block col][k0=frame][k1=row][k2=col]
+ *     (J/Encoder.java:75-89, C/encoder.c:29-41);
+ *   - there is no CPU fallback: without a CUDA device every call fails with DCT3D_E_CUDA.
+ */
+#ifndef DCT3D_H_
+#define DCT3D_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DCT3D_OK 0
+#define DCT3D_E_INVALID (-1)   /* bad argument (dimensions, cube size, null pointer) */
+#define DCT3D_E_CUDA (-2)      /* CUDA runtime / driver error, or no device */
+#define DCT3D_E_OVERFLOW (-3)  /* output buffer too small for the stream */
+#define DCT3D_E_STREAM (-4)    /* malformed or truncated Exp-Golomb stream */
+#define DCT3D_E_NEED_MORE (-5) /* streaming decode: not enough input buffered yet */
+
+typedef struct dct3d_ctx dct3d_ctx;
+
+/* ---- devices and contexts ------------------------------------------------------------- */
+
+/* Number of CUDA devices (negative on error). */
+int dct3d_device_count(void);
+
+/* Writes a newline-separated list "index - name (SMs, memory)" into buf.
+ * Replaces `codec list_platforms` / printAvailablePlatforms (C/OpenCLUtils.h:13, C/main.c:17-18). */
+int dct3d_list_devices(char *buf, size_t cap);
+
+/* Creates a context bound to one GPU for frames of width x height and cubes of edge `cube`
+ * (8 or 4; DCT_BLOCK_WIDTH/HEIGHT/DEPTH in C/codec.h:11-13, cubeWidth/Height/Depth in
+ * J/Encoder.java:28-30).  Replaces getDeviceId + clCreateContext + buildKernel + clCreateBuffer
+ * + clCreateCommandQueue + clCreateKernel (C/encoder.c:148-197, C/decoder.c:153-202). */
+int dct3d_create(dct3d_ctx **out, int device, int width, int height, int cube);
+void dct3d_destroy(dct3d_ctx *ctx);
+
+/* Last error text of the context (or of the last failed dct3d_create if ctx is NULL). */
+const char *dct3d_last_error(const dct3d_ctx *ctx);
+
+/* Options: "tma" (1 = TMA tile loads [default when width % 16 == 0], 0 = plain vector loads).
+ * Statistics (dct3d_get_stat): "launches" = kernels launched by the context so far,
+ * "flips_near_tie" is reported by the tests, not here. */
+int dct3d_set_option(dct3d_ctx *ctx, const char *key, long value);
+long dct3d_get_stat(const dct3d_ctx *ctx, const char *key);
+
+/* ---- fused hot path, host buffers ------------------------------------------------------- */
+
+/* u8 frames -> Exp-Golomb stream: DCT + quantise + zig-zag + Exp-Golomb in one pass on the GPU.
+ * Replaces J/Encoder.java:51-111 and, per slab, readCubes + the cl* sequence + applyQuantization
+ * + applyExpGolombCoding (C/encoder.c:206-263).  On success *nbits = stream length in bits and
+ * *nbytes = floor(nbits/8)+1 bytes were written to `stream` (unused trailing bits zero). */
+int dct3d_encode_u8(dct3d_ctx *ctx, const uint8_t *frames, int nframes,
+                    uint8_t *stream, size_t cap, uint64_t *nbits, size_t *nbytes);
+
+/* Exp-Golomb stream -> u8 frames: parse + dequantise + inverse DCT + clamp + truncate.
+ * Replaces J/Decoder.java:61-117 and, per slab, C/decoder.c:229-295. */
+int dct3d_decode_u8(dct3d_ctx *ctx, const uint8_t *stream, size_t nbytes, int nframes, uint8_t *frames);
+
+/* ---- streaming (the C codec's slab loop with a carried bit position) -------------------- */
+
+/* Resets the carried bit state (expGolomb_createStream, C/ExpGolomb.c:24-30). */
+int dct3d_stream_begin(dct3d_ctx *ctx);
+
+/* Encodes `nframes` more frames (a multiple of the cube edge).  Writes the COMPLETE bytes
+ * produced so far to `out` and keeps the partial byte inside the context, exactly as
+ * applyExpGolombCoding + expGolomb_freeBuffer do (C/encoder.c:263-268, C/ExpGolomb.c:112-122).
+ * With last != 0 the partial byte is flushed too (C/encoder.c:269-271: size+1 bytes). */
+int dct3d_stream_encode(dct3d_ctx *ctx, const uint8_t *frames, int nframes, int last,
+                        uint8_t *out, size_t cap, size_t *nbytes);
+
+/* Decodes `nframes` frames from `in`, starting at bit *bitpos of `in` (0..7 after the caller
+ * dropped consumed bytes, as expGolomb_freeBuffer(..., 0) does, C/decoder.c:229-235).  If the
+ * buffered input does not hold all codes yet returns DCT3D_E_NEED_MORE and changes nothing;
+ * otherwise advances *bitpos to the first unread bit. */
+int dct3d_stream_decode(dct3d_ctx *ctx, const uint8_t *in, size_t nbytes, uint64_t *bitpos,
+                        int nframes, uint8_t *frames);
+
+/* ---- transform seams, host buffers ------------------------------------------------------ */
+
+/* float cube-major slabs in, float cube-major coefficients out: the reference's own device
+ * boundary, replacing clEnqueueWriteBuffer + dct_calculate_partial_sums +
+ * dct_aggregate_partial_sums + clEnqueueReadBuffer (C/encoder.c:209-254, C/3dDCT.cl:43-143). */
+int dct3d_forward_f32(dct3d_ctx *ctx, const float *cubes_in, float *coef_out, int nslabs);
+/* inverse + clamp to [0,255] (C/decoder.c:249-292, C/3dDCT.cl:164-265). */
+int dct3d_inverse_f32(dct3d_ctx *ctx, const float *coef_in, float *pixels_out, int nslabs);
+
+/* double planar [frames][height][width] in and out: `new DCT(in, out, w, h, c, c, c).run()`
+ * (J/Encoder.java:63-64, J/dct/DCT.java:41-59) and `new InverseDCT(...).run()`
+ * (J/Decoder.java:102-103, J/dct/InverseDCT.java:33-82; clamps to [0,255]).  fp64 arithmetic. */
+int dct3d_forward_f64(dct3d_ctx *ctx, const double *planar_in, double *planar_out, int nframes);
+int dct3d_inverse_f64(dct3d_ctx *ctx, const double *planar_in, double *planar_out, int nframes);
+
+/* ---- codec stages, host buffers (flow-preserving mode and parity tests) ------------------ */
+
+/* u8 frames -> quantised cube-major int16 cubes, natural order inside the cube.
+ * DCT + round(coef / max(1, 5*(k0+k1+k2))) (J/Encoder.java:69-89, C/encoder.c:47-58). */
+int dct3d_quantize_u8(dct3d_ctx *ctx, const uint8_t *frames, int nframes, int16_t *qcubes);
+/* quantised cubes -> u8 frames (J/Decoder.java:78-117, C/decoder.c:48-59 + inverse + :29). */
+int dct3d_reconstruct_i16(dct3d_ctx *ctx, const int16_t *qcubes, int nframes, uint8_t *frames);
+/* quantised cubes -> Exp-Golomb stream in zig-zag order, starting at bit `start_bit` of
+ * `stream` (which must be zero from that bit on).  Bit-exact with applyExpGolombCoding
+ * (C/encoder.c:60-71) / J/Encoder.java:101-111 on identical cubes. */
+int dct3d_eg_encode_i16(dct3d_ctx *ctx, const int16_t *qcubes, size_t ncubes, uint64_t start_bit,
+                        uint8_t *stream, size_t cap, uint64_t *end_bit);
+/* stream -> quantised cubes (J/Decoder.java:61-76, C/decoder.c:229-239). */
+int dct3d_eg_decode_i16(dct3d_ctx *ctx, const uint8_t *stream, size_t nbytes, uint64_t start_bit,
+                        size_t ncubes, int16_t *qcubes, uint64_t *end_bit);
+
+/* ---- device-resident variants ------------------------------------------------------------
+ * All pointers are device pointers on the context's GPU; `cuda_stream` is a cudaStream_t (NULL =
+ * the context's own stream).  Work is enqueued on that stream; scalar results are written to
+ * host memory after an internal stream synchronisation unless the pointer is NULL.
+ * d_stream must be 4-byte aligned, zero-filled from start_bit on, and `cap` must include 8
+ * bytes of slack. */
+int dct3d_encode_u8_dev(dct3d_ctx *ctx, const void *d_frames, int nframes, void *d_stream, size_t cap,
+                        uint64_t start_bit, uint64_t *end_bit, void *cuda_stream);
+/* slab_bit_offsets (host array of nframes/cube+1 entries, may be NULL): side information from
+ * the encoder; when NULL the cube boundaries are discovered from the stream itself. */
+int dct3d_decode_u8_dev(dct3d_ctx *ctx, const void *d_stream, size_t nbytes, uint64_t start_bit,
+                        int nframes, void *d_frames, uint64_t *end_bit, void *cuda_stream);
+int dct3d_forward_f32_dev(dct3d_ctx *ctx, const void *d_cubes_in, void *d_coef_out, int nslabs, void *cuda_stream);
+int dct3d_inverse_f32_dev(dct3d_ctx *ctx, const void *d_coef_in, void *d_pixels_out, int nslabs, void *cuda_stream);
+int dct3d_forward_f64_dev(dct3d_ctx *ctx, const void *d_planar_in, void *d_planar_out, int nframes, void *cuda_stream);
+int dct3d_inverse_f64_dev(dct3d_ctx *ctx, const void *d_planar_in, void *d_planar_out, int nframes, void *cuda_stream);
+int dct3d_quantize_u8_dev(dct3d_ctx *ctx, const void *d_frames, int nframes, void *d_qcubes, void *cuda_stream);
+int dct3d_reconstruct_i16_dev(dct3d_ctx *ctx, const void *d_qcubes, int nframes, void *d_frames, void *cuda_stream);
+int dct3d_eg_encode_i16_dev(dct3d_ctx *ctx, const void *d_qcubes, size_t ncubes, uint64_t start_bit,
+                            void *d_stream, size_t cap, uint64_t *end_bit, void *cuda_stream);
+int dct3d_eg_decode_i16_dev(dct3d_ctx *ctx, const void *d_stream, size_t nbytes, uint64_t start_bit,
+                            size_t ncubes, void *d_qcubes, uint64_t *end_bit, void *cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DCT3D_H_ */

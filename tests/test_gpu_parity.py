@@ -1,0 +1,248 @@
+"""GPU parity tests (run with -m gpu on the B200 box): every call goes through the C ABI of
+libdct3d.so (ctypes), and is compared with the CPU oracle on the same seeded inputs.
+
+Parity rules (BASELINE.json north_star):
+  (1) float DCT coefficients within 1e-4 relative (to the block's magnitude) of the fp64 oracle;
+  (2) quantised cubes identical except +-1 flips at rounding near-ties, counted and bounded;
+  (3) Exp-Golomb stream bit-exact given identical quantised cubes;
+  (4) decoded pixels within +-1.
+"""
+import numpy as np
+import pytest
+
+from conftest import pkg
+
+pytestmark = pytest.mark.gpu
+
+FLIP_RATE_MAX = 2e-5   # fp32 near-tie flips; SURVEY.md App. D measured 1.4e-6
+
+
+@pytest.fixture(scope="module")
+def codec_mod():
+    return pkg("codec")
+
+
+def make(codec_mod, W, H, cube=8, tma=None):
+    c = codec_mod.Codec(W, H, cube)
+    if tma is not None:
+        c.set_option("tma", tma)
+    return c
+
+
+CLIPS = [
+    # name, W, H, F, cube, generator, seed
+    ("golden", 64, 48, 24, 8, "natural", 1),
+    ("wide", 384, 16, 8, 8, "natural", 3),
+    ("ragged", 200, 24, 16, 8, "natural", 4),      # 25 cubes per row: partial boxes, W % 16 != 0 -> plain loads
+    ("noise", 128, 32, 8, 8, "noise", 2),
+    ("const", 32, 16, 8, 8, "constant", 0),
+    ("tail", 32, 32, 19, 8, "natural", 5),         # 3 trailing frames dropped
+    ("c4", 128, 16, 8, 4, "natural", 6),
+    ("c4ragged", 40, 12, 12, 4, "noise", 7),
+]
+
+
+def gen(synth, kind, W, H, F, seed):
+    if kind == "natural":
+        return synth.natural(W, H, F, seed)
+    if kind == "noise":
+        return synth.noise(W, H, F, seed)
+    return synth.constant(W, H, F, 128)
+
+
+@pytest.mark.parametrize("name,W,H,F,cube,kind,seed", CLIPS)
+@pytest.mark.parametrize("tma", [1, 0])
+def test_quantised_cubes_match_oracle(codec_mod, oracle, synth, name, W, H, F, cube, kind, seed, tma):
+    if tma and W % 16:
+        pytest.skip("TMA needs 16-byte row pitch")
+    clip = gen(synth, kind, W, H, F, seed)
+    with make(codec_mod, W, H, cube, tma) as c:
+        q = c.quantize_u8(clip).astype(np.int32)
+    ref = oracle.quantized_cubes(clip, cube, mode=0)
+    ref_c = oracle.quantized_cubes(clip, cube, mode=1)
+    assert q.shape == ref.shape
+    diff = np.abs(q - ref)
+    flips = int((diff != 0).sum())
+    print(f"[{name} tma={tma}] near-tie flips vs fp64 oracle: {flips} / {q.size}")
+    assert diff.max(initial=0) <= 1
+    assert flips <= max(2, FLIP_RATE_MAX * q.size)
+    # Java and C rounding agree except on exact ties, which do not occur
+    assert (ref == ref_c).all()
+
+
+@pytest.mark.parametrize("cube", [8, 4])
+def test_forward_inverse_f32_seam(codec_mod, oracle, synth, cube):
+    W, H, F = 96, 32, 2 * cube
+    clip = synth.natural(W, H, F, 11)
+    cubes = oracle.frames_to_cubes(clip, cube).astype(np.float32)
+    with make(codec_mod, W, H, cube) as c:
+        coef = c.forward_f32(cubes).reshape(cubes.shape)
+        ref = oracle.frames_to_cubes(oracle.dct_sep(clip.astype(np.float64), cube), cube)
+        blockmax = np.abs(ref).reshape(ref.shape[0], -1).max(axis=1).reshape(-1, 1, 1, 1)
+        rel = np.abs(coef - ref) / np.maximum(blockmax, 1.0)
+        assert rel.max() <= 1e-4            # rule (1)
+        assert np.abs(coef - ref).max() < 2e-3
+        back = c.inverse_f32(coef).reshape(cubes.shape)
+        assert np.abs(back - cubes).max() < 2e-3
+        # clamp: coefficients of an out-of-range signal
+        big = c.inverse_f32(c.forward_f32(cubes * 4.0 - 300.0))
+        assert big.min() >= 0.0 and big.max() <= 255.0
+
+
+@pytest.mark.parametrize("cube", [8, 4])
+def test_forward_inverse_f64_seam(codec_mod, oracle, synth, cube):
+    W, H, F = 64, 24, 2 * cube
+    px = synth.noise(W, H, F, 12).astype(np.float64)
+    with make(codec_mod, W, H, cube) as c:
+        coef = c.forward_f64(px)
+        ref = oracle.dct_sep(px, cube)
+        assert np.abs(coef - ref).max() <= 1e-10 * np.abs(ref).max()
+        back = c.inverse_f64(coef)
+        assert np.abs(back - px).max() < 1e-9
+    # Java-shaped object API
+    out = np.zeros_like(px)
+    codec_mod.DCT(px, out, W, H, cube, cube, cube).run()
+    assert np.abs(out - ref).max() <= 1e-10 * np.abs(ref).max()
+    pix = np.zeros_like(px)
+    codec_mod.InverseDCT(out, pix, W, H, cube, cube, cube).run()
+    assert np.abs(pix - px).max() < 1e-9
+
+
+def _rand_cubes(rng, ncubes, cs, density, hi):
+    q = np.zeros((ncubes, cs), np.int16)
+    m = rng.random((ncubes, cs)) < density
+    q[m] = rng.integers(-hi - 1, hi + 1, size=int(m.sum())).astype(np.int16)
+    return q
+
+
+@pytest.mark.parametrize("cube", [8, 4])
+@pytest.mark.parametrize("ncubes,density,hi,start", [(1, 0.03, 300, 0), (33, 0.0, 1, 3), (70, 0.05, 5770, 13),
+                                                     (97, 1.0, 32767, 0), (1000, 0.03, 200, 7)])
+def test_expgolomb_bit_exact(codec_mod, oracle, cube, ncubes, density, hi, start):
+    """Rule (3): identical cubes -> identical bits, for any start phase, plus decode round trip."""
+    cs = cube ** 3
+    rng = np.random.default_rng(ncubes + cube)
+    q = _rand_cubes(rng, ncubes, cs, density, hi).reshape(-1, cube, cube, cube)
+    ref, ref_end = oracle.eg_encode_cubes(q.astype(np.int32), cube, start_bit=start)
+    prefix = np.array([0xA0], np.uint8) if start else None     # pre-existing bits of the partial byte survive
+    if start:
+        ref = ref.copy()
+        ref[0] |= 0xA0      # 101 then zeros: only bits before start_bit (>= 3) are set
+    with make(codec_mod, 8 * cube, 8 * cube, cube) as c:
+        out, end = c.eg_encode_i16(q, start, prefix)
+        assert end == ref_end
+        assert out.tobytes() == ref.tobytes()
+        back, dend = c.eg_decode_i16(out, ncubes, start)
+        assert dend == ref_end
+        assert (back == q).all()
+
+
+def test_reference_golden_stream(codec_mod, oracle, golden):
+    """The reference CLI's own stream and pixels (tests/golden/make_golden.py)."""
+    stream, refq = golden["flow_stream"], golden["flow_qcubes"]
+    with make(codec_mod, 64, 48, 8) as c:
+        q, end = c.eg_decode_i16(stream, refq.shape[0])
+        assert end == int(golden["flow_bits"]) == 84744
+        assert (q == refq).all()
+        out, oend = c.eg_encode_i16(refq)
+        assert oend == 84744 and out.tobytes() == stream.tobytes()
+        dec = c.decode_u8(stream, 24)
+        assert np.abs(dec.astype(int) - golden["flow_decoded"].astype(int)).max() <= 1   # rule (4)
+        assert (dec != golden["flow_decoded"]).mean() < 0.01
+
+
+@pytest.mark.parametrize("name,W,H,F,cube,kind,seed", CLIPS)
+def test_fused_encode_decode(codec_mod, oracle, synth, name, W, H, F, cube, kind, seed):
+    clip = gen(synth, kind, W, H, F, seed)
+    Fe = F - F % cube
+    with make(codec_mod, W, H, cube) as c:
+        q = c.quantize_u8(clip)
+        stream, nbits = c.encode_u8(clip)
+        # the fused kernel's stream is exactly the Exp-Golomb coding of the cubes it quantised
+        ref, ref_bits = oracle.eg_encode_cubes(q.astype(np.int32), cube)
+        assert nbits == ref_bits and stream.size == nbits // 8 + 1
+        assert stream.tobytes() == ref.tobytes()
+        oq = oracle.quantized_cubes(clip, cube, 0)
+        if (oq == q).all():
+            full, fbits = oracle.encode_u8(clip, cube, 0)
+            assert fbits == nbits and full.tobytes() == stream.tobytes()
+        dec = c.decode_u8(stream, F)
+        assert dec.shape == (Fe, H, W)
+        odec = oracle.decode_u8(stream, W, H, F, cube)
+        d = np.abs(dec.astype(int) - odec.astype(int))
+        print(f"[{name}] decoded pixels differing from oracle: {(d != 0).mean():.2e}")
+        assert d.max(initial=0) <= 1                                        # rule (4)
+        rec = c.reconstruct_i16(q, F)
+        assert (rec == dec).all()
+
+
+def test_streaming_equals_one_shot(codec_mod, oracle, synth):
+    W, H, F = 64, 48, 24
+    clip = synth.natural(W, H, F, 1)
+    with make(codec_mod, W, H, 8) as c:
+        one, nbits = c.encode_u8(clip)
+        c.stream_begin()
+        parts = [c.stream_encode(clip[i:i + 8], last=(i + 8 >= F)) for i in range(0, F, 8)]
+        cat = np.concatenate(parts)
+        assert cat.tobytes() == one.tobytes()     # C/encoder.c:263-271 slab loop == Java one-shot
+        # slab-by-slab decode with a carried bit position
+        pos, frames, buf = 0, [], one
+        for i in range(0, F, 8):
+            res = c.stream_decode(buf, pos, 8)
+            assert res is not None
+            fr, pos = res
+            frames.append(fr)
+            buf, pos = buf[pos // 8:], pos % 8
+        assert (np.concatenate(frames) == c.decode_u8(one, F)).all()
+        assert c.stream_decode(one[: one.size // 2], 0, F) is None   # not enough input yet
+
+
+def test_error_behaviour(codec_mod, synth):
+    with pytest.raises(codec_mod.Dct3dError):
+        codec_mod.Codec(100, 48, 8)            # width not a multiple of the cube edge
+    with pytest.raises(codec_mod.Dct3dError):
+        codec_mod.Codec(64, 48, 5)
+    with pytest.raises(codec_mod.Dct3dError):
+        codec_mod.Codec(64, 48, 8, device=99)
+    clip = synth.noise(64, 48, 8, 1)
+    with make(codec_mod, 64, 48, 8) as c:
+        L = c.L
+        out = np.zeros(64, np.uint8)
+        import ctypes as C
+        nb, ny = C.c_uint64(), C.c_size_t()
+        rc = L.dct3d_encode_u8(c.h, clip.ctypes.data, 8, out.ctypes.data, out.size, C.byref(nb), C.byref(ny))
+        assert rc == -3 and b"small" in L.dct3d_last_error(c.h)            # DCT3D_E_OVERFLOW
+        stream, _ = c.encode_u8(clip)
+        with pytest.raises(codec_mod.Dct3dError) as e:
+            c.decode_u8(stream[: stream.size // 3], 8)
+        assert e.value.code == -4                                           # DCT3D_E_STREAM
+        with pytest.raises(codec_mod.Dct3dError):
+            c.decode_u8(np.zeros(4096, np.uint8), 8)                        # endless zero prefix: malformed
+        empty, bits = c.encode_u8(np.zeros((3, 48, 64), np.uint8))          # fewer frames than a cube
+        assert bits == 0 and empty.size == 1
+
+
+def test_full_hd_slabs_properties(codec_mod, oracle, synth):
+    """1080p, 16 frames: size-independent properties + oracle spot check on the first cube row."""
+    W, H, F = 1920, 1080, 16
+    rng = np.random.default_rng(21)
+    base = synth.natural(W, 136, F, 8)
+    clip = np.tile(base, (1, 8, 1))[:, :H, :].copy()
+    clip[:, 500:508, :] = rng.integers(0, 256, size=(F, 8, W), dtype=np.uint8)
+    with make(codec_mod, W, H, 8) as c:
+        stream, nbits = c.encode_u8(clip)
+        q = c.quantize_u8(clip)
+        ref, ref_bits = oracle.eg_encode_cubes(q.astype(np.int32), 8)
+        assert ref_bits == nbits and ref.tobytes() == stream.tobytes()
+        qd, end = c.eg_decode_i16(stream, q.shape[0])
+        assert end == nbits and (qd == q).all()
+        dec = c.decode_u8(stream, F)
+        assert (dec == c.reconstruct_i16(q, F)).all()
+        # oracle on the first row of cubes of both slabs
+        oq = oracle.quantized_cubes(clip[:, :8, :], 8, 0)
+        mine = q.reshape(2, 135, 240, 512)[:, 0].reshape(-1, 8, 8, 8)
+        assert np.abs(mine.astype(int) - oq).max() <= 1 and (mine != oq).sum() <= 3
+        # TMA and plain loads agree bit for bit
+        c.set_option("tma", 0)
+        s2, b2 = c.encode_u8(clip)
+        assert b2 == nbits and s2.tobytes() == stream.tobytes()
