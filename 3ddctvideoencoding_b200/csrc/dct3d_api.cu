@@ -528,11 +528,11 @@ static int parse_common(dct3d_ctx *ctx, const void *d_stream, size_t nbytes, uin
         if ((rc = fetch_ctrl(ctx, st))) return rc;
         if (!ctx->h_ctrl->changed) break;
     }
-    if (ctx->h_ctrl->err & 2u) return fail(ctx, DCT3D_E_STREAM, "malformed Exp-Golomb code in stream");
     seg_prefix_kernel<<<1, 1024, 0, st>>>(P);
     ctx->launches++;
     CU_CHECK(ctx, cudaMemcpyAsync(ctx->h_u64, P.seg_first + n, 8, cudaMemcpyDeviceToHost, st));
-    CU_CHECK(ctx, cudaStreamSynchronize(st));
+    if ((rc = fetch_ctrl(ctx, st))) return rc;
+    if (ctx->h_ctrl->err & 2u) return fail(ctx, DCT3D_E_STREAM, "malformed Exp-Golomb code in stream");
     if (ctx->h_u64[0] < (unsigned long long)ncubes * CS)
         return fail(ctx, DCT3D_E_NEED_MORE, "stream holds %llu codes, %llu needed", ctx->h_u64[0], (unsigned long long)ncubes * CS);
     if (C == 8) cube_index_kernel<512><<<sg, sb, 0, st>>>(P); else cube_index_kernel<64><<<sg, sb, 0, st>>>(P);

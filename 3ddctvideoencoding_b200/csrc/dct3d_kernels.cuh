@@ -589,9 +589,12 @@ __global__ void seg_scan_kernel(const DecParams P, int first_pass)
     if (lim > P.nbits_total) lim = P.nbits_total;
     StreamSource src{P.words, P.nwords};
     uint32_t n = 0; uint64_t next = 0;
+    // A scan from a wrongly assumed entry point may run into an impossible code; that is only an
+    // error if it is still there once the entry points have converged, so it is recorded per segment.
+    unsigned int bad = 0;
     if (seg0 + entry >= lim) { n = 0; next = seg0 + entry; }
-    else if (!eg_scan_segment(src, seg0 + entry, lim, P.nbits_total, n, next)) { atomicOr(P.err, 2u); next = lim; }
-    P.seg_count[k] = n;
+    else if (!eg_scan_segment(src, seg0 + entry, lim, P.nbits_total, n, next)) { bad = 0x80000000u; n = 0; next = lim; }
+    P.seg_count[k] = n | bad;
     P.seg_used[k] = entry;
     const unsigned int over = (unsigned int)(next > lim ? next - lim : 0);
     if (first_pass || P.seg_over[k + 1] != over) { P.seg_over[k + 1] = over; if (!first_pass) *P.changed = 1u; }
@@ -607,7 +610,8 @@ __global__ void seg_prefix_kernel(const DecParams P)
     __syncthreads();
     for (unsigned long long base = 0; base < P.nseg; base += 1024) {
         const unsigned long long k = base + tid;
-        const unsigned long long v = k < P.nseg ? P.seg_count[k] : 0ull;
+        unsigned long long v = k < P.nseg ? P.seg_count[k] : 0ull;
+        if (v & 0x80000000ull) { atomicOr(P.err, 2u); v &= 0x7fffffffull; }
         unsigned long long incl = v;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { const unsigned long long o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }

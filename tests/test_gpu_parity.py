@@ -50,24 +50,41 @@ def gen(synth, kind, W, H, F, seed):
     return synth.constant(W, H, F, 128)
 
 
+def classify_flips(q, ref, coef_planar, oracle, cube):
+    """Every mismatch must be a +-1 flip at a rounding tie of the fp64 value: an EXACT tie (the 4^3
+    transform has rational coefficients, e.g. DC = sum/8; the reference's own Java and C results differ
+    there) or a NEAR tie within fp32 error.  Returns (exact, near)."""
+    bad = np.argwhere(q != ref)
+    if bad.size == 0:
+        return 0, 0
+    assert np.abs(q - ref).max() <= 1
+    cc = oracle.frames_to_cubes(coef_planar, cube)
+    k = np.indices((cube, cube, cube)).sum(axis=0)
+    div = np.maximum(1, 5 * k)[None]
+    v = (cc / div)[tuple(bad.T)]
+    dist = np.abs(np.abs(v - np.floor(v)) - 0.5)
+    assert dist.max() < 2e-3, "a quantised value differs from the oracle away from any rounding tie"
+    exact = int((dist < 1e-9).sum())
+    return exact, int(bad.shape[0] - exact)
+
+
 @pytest.mark.parametrize("name,W,H,F,cube,kind,seed", CLIPS)
 @pytest.mark.parametrize("tma", [1, 0])
 def test_quantised_cubes_match_oracle(codec_mod, oracle, synth, name, W, H, F, cube, kind, seed, tma):
+    """Rule (2): identical quantised cubes except counted +-1 flips at rounding ties."""
     if tma and W % 16:
         pytest.skip("TMA needs 16-byte row pitch")
     clip = gen(synth, kind, W, H, F, seed)
     with make(codec_mod, W, H, cube, tma) as c:
         q = c.quantize_u8(clip).astype(np.int32)
-    ref = oracle.quantized_cubes(clip, cube, mode=0)
-    ref_c = oracle.quantized_cubes(clip, cube, mode=1)
+    ref, coef = oracle.quantized_cubes(clip, cube, mode=0, want_coef=True)
     assert q.shape == ref.shape
-    diff = np.abs(q - ref)
-    flips = int((diff != 0).sum())
-    print(f"[{name} tma={tma}] near-tie flips vs fp64 oracle: {flips} / {q.size}")
-    assert diff.max(initial=0) <= 1
-    assert flips <= max(2, FLIP_RATE_MAX * q.size)
-    # Java and C rounding agree except on exact ties, which do not occur
-    assert (ref == ref_c).all()
+    exact, near = classify_flips(q, ref, coef, oracle, cube)
+    print(f"[{name} tma={tma}] flips vs fp64 oracle: {exact} at exact ties, {near} at near ties, of {q.size}")
+    assert near <= max(2, FLIP_RATE_MAX * q.size)
+    if cube == 8:
+        assert exact == 0      # the 8^3 basis is irrational: no exact ties (DESIGN.md)
+        assert (ref == oracle.quantized_cubes(clip, cube, mode=1)).all()   # Java and C rounding agree
 
 
 @pytest.mark.parametrize("cube", [8, 4])
