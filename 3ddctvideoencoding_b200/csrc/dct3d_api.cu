@@ -49,10 +49,11 @@ struct dct3d_ctx {
     int device = 0, W = 0, H = 0, C = 8;
     int num_sms = 0;
     int use_tma = 1;
+    int debug = 0;
     long launches = 0;
     cudaStream_t stream = nullptr;
     std::string err;
-    DevBuf frames, bits, q, status, ctrl, seg, cubeoff, fa, fb;
+    DevBuf frames, bits, q, status, ctrl, seg, cubeoff, fa, fb, zz, cmask;
     Ctrl *h_ctrl = nullptr;          // pinned
     unsigned long long *h_u64 = nullptr;  // pinned scratch (4 entries)
     // streaming state
@@ -90,8 +91,7 @@ Layout make_layout(int W, int H, int C, int nslabs)
     L.bxb = (L.bx + cpb - 1) / cpb;
     L.nslabs = nslabs;
     L.nboxes = (long long)nslabs * L.by * L.bxb;
-    const int bpt = kTileCubes / cpb;
-    L.ntiles = (L.nboxes + bpt - 1) / bpt;
+    L.ntiles = L.nboxes;      // fused encoder: one tile = one TMA box
     L.ncubes = (long long)nslabs * L.by * L.bx;
     return L;
 }
@@ -186,10 +186,10 @@ int check_frames(dct3d_ctx *ctx, int nframes)
     return DCT3D_OK;
 }
 
-template <int C, bool EMIT_Q>
+template <int C, int MODE>
 int launch_encode(dct3d_ctx *ctx, const EncParams &P, const CUtensorMap &tm, cudaStream_t st)
 {
-    auto kern = encode_kernel<C, EMIT_Q>;
+    auto kern = encode_kernel<C, MODE>;
     const int smem = EncSmem<C>::TOTAL;
     CU_CHECK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int occ = 0;
@@ -352,7 +352,7 @@ void dct3d_destroy(dct3d_ctx *ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    for (DevBuf *b : {&ctx->frames, &ctx->bits, &ctx->q, &ctx->status, &ctx->ctrl, &ctx->seg, &ctx->cubeoff, &ctx->fa, &ctx->fb}) b->release();
+    for (DevBuf *b : {&ctx->frames, &ctx->bits, &ctx->q, &ctx->status, &ctx->ctrl, &ctx->seg, &ctx->cubeoff, &ctx->fa, &ctx->fb, &ctx->zz, &ctx->cmask}) b->release();
     if (ctx->h_ctrl) cudaFreeHost(ctx->h_ctrl);
     if (ctx->h_u64) cudaFreeHost(ctx->h_u64);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -370,6 +370,7 @@ int dct3d_set_option(dct3d_ctx *ctx, const char *key, long value)
         ctx->use_tma = value ? 1 : 0;
         return DCT3D_OK;
     }
+    if (!strcmp(key, "debug")) { ctx->debug = (int)value; return DCT3D_OK; }
     return fail(ctx, DCT3D_E_INVALID, "unknown option '%s'", key);
 }
 
@@ -383,6 +384,42 @@ long dct3d_get_stat(const dct3d_ctx *ctx, const char *key)
 }
 
 // ---- device-resident entry points -----------------------------------------------------------
+
+// Kernel 2 (bit packing) over ctx->zz / ctx->cmask.  P.L.ncubes must be set.
+static int run_pack_noreset(dct3d_ctx *ctx, EncParams &P, void *d_stream, size_t cap, uint64_t start_bit, uint64_t *end_bit, cudaStream_t st)
+{
+    int rc;
+    const long long ptiles = (P.L.ncubes + kPackThreads - 1) / kPackThreads;
+    Ctrl *dc = (Ctrl *)ctx->ctrl.p;
+    P.out_words = (uint32_t *)d_stream;
+    P.cap_bits = (unsigned long long)(cap / 4) * 32;
+    P.start_bit = start_bit;
+    P.tile_status = (unsigned long long *)ctx->status.p;
+    P.ticket = &dc->ticket; P.err = &dc->err; P.end_bit = &dc->end_bit;
+    int occ = 0;
+    if (ctx->C == 8) CU_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, eg_pack_kernel<8>, kPackThreads, 0));
+    else CU_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, eg_pack_kernel<4>, kPackThreads, 0));
+    const long long grid = std::min<long long>(ptiles, (long long)ctx->num_sms * std::max(occ, 1));
+    if (ctx->C == 8) eg_pack_kernel<8><<<(unsigned)grid, kPackThreads, 0, st>>>(P);
+    else eg_pack_kernel<4><<<(unsigned)grid, kPackThreads, 0, st>>>(P);
+    ctx->launches++;
+    CU_CHECK(ctx, cudaGetLastError());
+    if (end_bit) {
+        if ((rc = fetch_ctrl(ctx, st))) return rc;
+        if (ctx->h_ctrl->err & 16u) return fail(ctx, DCT3D_E_CUDA, "TMA tile load timed out");
+        if (ctx->h_ctrl->err & 8u) return fail(ctx, DCT3D_E_CUDA, "tile look-back timed out");
+        if (ctx->h_ctrl->err & 1u) return fail(ctx, DCT3D_E_OVERFLOW, "stream buffer of %zu bytes is too small", cap);
+        *end_bit = ctx->h_ctrl->end_bit;
+    }
+    return DCT3D_OK;
+}
+
+static int run_pack(dct3d_ctx *ctx, EncParams &P, void *d_stream, size_t cap, uint64_t start_bit, uint64_t *end_bit, cudaStream_t st)
+{
+    const long long ptiles = (P.L.ncubes + kPackThreads - 1) / kPackThreads;
+    int rc = reset_ctrl(ctx, ptiles, st);
+    return rc ? rc : run_pack_noreset(ctx, P, d_stream, cap, start_bit, end_bit, st);
+}
 
 static int encode_common(dct3d_ctx *ctx, const void *d_frames, int nframes, void *d_stream, size_t cap,
                          uint64_t start_bit, uint64_t *end_bit, void *cuda_stream, void *d_qcubes)
@@ -404,31 +441,38 @@ static int encode_common(dct3d_ctx *ctx, const void *d_frames, int nframes, void
     EncParams P;
     memset(&P, 0, sizeof P);
     P.L = make_layout(ctx->W, ctx->H, C, nslabs);
-    if ((rc = reset_ctrl(ctx, P.L.ntiles, st))) return rc;
-    Ctrl *dc = (Ctrl *)ctx->ctrl.p;
     P.frames = (const uint8_t *)d_frames;
-    P.out_words = (uint32_t *)d_stream;
-    P.cap_bits = (unsigned long long)(cap / 4) * 32;
-    P.start_bit = start_bit;
-    P.tile_status = (unsigned long long *)ctx->status.p;
-    P.ticket = &dc->ticket; P.err = &dc->err; P.end_bit = &dc->end_bit;
     P.qcubes = (int16_t *)d_qcubes;
     P.use_tma = ctx->use_tma && !((uintptr_t)d_frames & 15);
+    P.debug = ctx->debug;
+    CU_CHECK(ctx, ctx->ctrl.reserve(sizeof(Ctrl)));
+    P.err = &((Ctrl *)ctx->ctrl.p)->err;
+    if (!emit_q) {
+        CU_CHECK(ctx, ctx->zz.reserve((size_t)P.L.ncubes * C * C * C * sizeof(int16_t)));
+        CU_CHECK(ctx, ctx->cmask.reserve((size_t)P.L.ncubes * 4));
+        P.zzg = (int16_t *)ctx->zz.p;
+        P.cmask = (uint32_t *)ctx->cmask.p;
+    } else {
+        CU_CHECK(ctx, cudaMemsetAsync(ctx->ctrl.p, 0, sizeof(Ctrl), st));
+    }
     CUtensorMap tm;
     memset(&tm, 0, sizeof tm);
     if (P.use_tma && !make_tmap(&tm, d_frames, ctx->W, ctx->H, nslabs * C, C))
         return fail(ctx, DCT3D_E_CUDA, "cuTensorMapEncodeTiled failed (set option tma=0 to use plain loads)");
-    if (C == 8) rc = emit_q ? launch_encode<8, true>(ctx, P, tm, st) : launch_encode<8, false>(ctx, P, tm, st);
-    else rc = emit_q ? launch_encode<4, true>(ctx, P, tm, st) : launch_encode<4, false>(ctx, P, tm, st);
-    if (rc) return rc;
-    if (end_bit || emit_q) {
+    if (emit_q) {
+        rc = C == 8 ? launch_encode<8, MODE_NAT>(ctx, P, tm, st) : launch_encode<4, MODE_NAT>(ctx, P, tm, st);
+        if (rc) return rc;
         if ((rc = fetch_ctrl(ctx, st))) return rc;
         if (ctx->h_ctrl->err & 16u) return fail(ctx, DCT3D_E_CUDA, "TMA tile load timed out");
-        if (ctx->h_ctrl->err & 8u) return fail(ctx, DCT3D_E_CUDA, "tile look-back timed out");
-        if (ctx->h_ctrl->err & 1u) return fail(ctx, DCT3D_E_OVERFLOW, "stream buffer of %zu bytes is too small", cap);
-        if (end_bit) *end_bit = ctx->h_ctrl->end_bit;
+        return DCT3D_OK;
     }
-    return DCT3D_OK;
+    // the control block is zeroed here (before kernel 1, which may flag a TMA time-out in it) and
+    // again only partially by run_pack: keep one reset, done by run_pack, and run kernel 1 after it
+    const long long ptiles = (P.L.ncubes + kPackThreads - 1) / kPackThreads;
+    if ((rc = reset_ctrl(ctx, ptiles, st))) return rc;
+    rc = C == 8 ? launch_encode<8, MODE_ZZ>(ctx, P, tm, st) : launch_encode<4, MODE_ZZ>(ctx, P, tm, st);
+    if (rc) return rc;
+    return run_pack_noreset(ctx, P, d_stream, cap, start_bit, end_bit, st);
 }
 
 int dct3d_encode_u8_dev(dct3d_ctx *ctx, const void *d_frames, int nframes, void *d_stream, size_t cap,
@@ -454,31 +498,22 @@ int dct3d_eg_encode_i16_dev(dct3d_ctx *ctx, const void *d_qcubes, size_t ncubes,
     if ((rc = zero_stream(ctx, d_stream, cap, start_bit, st))) return rc;
     if (ncubes == 0) { if (end_bit) *end_bit = start_bit; return DCT3D_OK; }
     if (!d_qcubes) return fail(ctx, DCT3D_E_INVALID, "null cube pointer");
+    const int C = ctx->C;
     EncParams P;
     memset(&P, 0, sizeof P);
-    P.L = make_layout(ctx->W, ctx->H, ctx->C, 0);
+    P.L = make_layout(ctx->W, ctx->H, C, 0);
     P.L.ncubes = (long long)ncubes;
-    P.L.ntiles = ((long long)ncubes + kTileCubes - 1) / kTileCubes;
-    if ((rc = reset_ctrl(ctx, P.L.ntiles, st))) return rc;
-    Ctrl *dc = (Ctrl *)ctx->ctrl.p;
+    CU_CHECK(ctx, ctx->zz.reserve(ncubes * C * C * C * sizeof(int16_t)));
+    CU_CHECK(ctx, ctx->cmask.reserve(ncubes * 4));
+    P.zzg = (int16_t *)ctx->zz.p;
+    P.cmask = (uint32_t *)ctx->cmask.p;
     P.qcubes_in = (const int16_t *)d_qcubes;
-    P.out_words = (uint32_t *)d_stream;
-    P.cap_bits = (unsigned long long)(cap / 4) * 32;
-    P.start_bit = start_bit;
-    P.tile_status = (unsigned long long *)ctx->status.p;
-    P.ticket = &dc->ticket; P.err = &dc->err; P.end_bit = &dc->end_bit;
-    const long long grid = std::min<long long>(P.L.ntiles, (long long)ctx->num_sms * 4);
-    if (ctx->C == 8) eg_encode_kernel<8><<<(unsigned)grid, kThreads, 0, st>>>(P);
-    else eg_encode_kernel<4><<<(unsigned)grid, kThreads, 0, st>>>(P);
+    const long long grid = std::min<long long>(((long long)ncubes + kWarps - 1) / kWarps, (long long)ctx->num_sms * 16);
+    if (C == 8) zz_gather_kernel<8><<<(unsigned)grid, kThreads, 0, st>>>(P);
+    else zz_gather_kernel<4><<<(unsigned)grid, kThreads, 0, st>>>(P);
     ctx->launches++;
     CU_CHECK(ctx, cudaGetLastError());
-    if (end_bit) {
-        if ((rc = fetch_ctrl(ctx, st))) return rc;
-        if (ctx->h_ctrl->err & 8u) return fail(ctx, DCT3D_E_CUDA, "tile look-back timed out");
-        if (ctx->h_ctrl->err & 1u) return fail(ctx, DCT3D_E_OVERFLOW, "stream buffer of %zu bytes is too small", cap);
-        *end_bit = ctx->h_ctrl->end_bit;
-    }
-    return DCT3D_OK;
+    return run_pack(ctx, P, d_stream, cap, start_bit, end_bit, st);
 }
 
 // Index discovery + parse: stream -> natural-order int16 cubes in ctx->q (or d_qcubes).

@@ -29,7 +29,6 @@
 
 namespace dct3d {
 
-constexpr int kTileCubes = 32;   // cubes per tile = lanes of the entropy warp
 constexpr int kBoxW = 128;       // pixels (bytes) per TMA box row
 constexpr int kWarps = 4;        // transform warps per CTA
 constexpr int kThreads = kWarps * 32;
@@ -39,11 +38,8 @@ struct Geo {
     static constexpr int CS = C * C * C;
     static constexpr int CPW = 32 / C;                       // cubes per warp pass
     static constexpr int CUBES_PER_BOX = kBoxW / C;          // 16 (C=8) / 32 (C=4)
-    static constexpr int BOXES_PER_TILE = kTileCubes / CUBES_PER_BOX;
     static constexpr int ROW_BYTES = kBoxW * C;              // one TMA op: C frames of one row
     static constexpr int BOX_BYTES = ROW_BYTES * C;
-    static constexpr int IN_BYTES = BOX_BYTES * BOXES_PER_TILE;
-    static constexpr int PASSES = kTileCubes / (kWarps * CPW);
     static constexpr int ZZ_STRIDE = CS + 8;                 // int16 units; odd multiple of 16 B
     static constexpr int NDIAG = 2 * C - 1;
     static constexpr int CHUNKS = CS / 16;                   // 16-coefficient chunks per cube
@@ -68,9 +64,12 @@ struct EncParams {
     unsigned int *ticket;             // zeroed
     unsigned int *err;                // zeroed; bit0 = overflow
     unsigned long long *end_bit;      // out: start_bit + total bits
-    int16_t *qcubes;                  // EMIT_Q: natural-order int16 cubes out
+    int16_t *zzg;                     // zig-zag chunk scratch [cube][CS] (sparsely touched)
+    uint32_t *cmask;                  // [cube] mask of non-zero 16-coefficient chunks
+    int16_t *qcubes;                  // MODE_NAT: natural-order int16 cubes out
     const int16_t *qcubes_in;         // EG-only kernel: natural-order int16 cubes in
     int use_tma;
+    int debug;                        // reserved for profiling experiments
 };
 
 // ------------------------------------------------------------------------------------------
@@ -289,53 +288,32 @@ __device__ __forceinline__ unsigned long long tile_lookback(unsigned long long *
     return excl;
 }
 
-// Warp 0: lane = cube slot of the tile.  zz/cmask in shared memory.
-template <int C>
-__device__ __forceinline__ void entropy_stage(const EncParams &P, long long tile, const int16_t *s_zz,
-                                              const uint32_t *s_cmask, uint32_t validmask, int lane)
-{
-    using G = Geo<C>;
-    const bool valid = (validmask >> lane) & 1u;
-    const int16_t *zz = s_zz + lane * G::ZZ_STRIDE;
-    const uint32_t cm = valid ? s_cmask[lane] : 0u;
-    const uint32_t nb = valid ? eg_count_cube<G::CS>(zz, cm) : 0u;
-    uint32_t incl = nb;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += o;
-    }
-    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-    const unsigned long long tile_off = tile_lookback(P.tile_status, tile, total, P.start_bit, lane, P.err);
-    if (tile == P.L.ntiles - 1 && lane == 0) *P.end_bit = tile_off + total;
-    if (valid) {
-        const unsigned long long off = tile_off + (incl - nb);
-        if (off + nb + 64 > P.cap_bits) {
-            atomicOr(P.err, 1u);
-        } else {
-            GlobalSink sink{P.out_words};
-            eg_write_cube<G::CS>(zz, cm, off, sink);
-        }
-    }
-}
+// ------------------------------------------------------------------------------------------
+// Encoder kernel 1: u8 frames -> quantised coefficients.
+//   MODE_ZZ : zig-zag ordered int16 cubes in a dense-addressed, SPARSELY TOUCHED scratch
+//             [cube][CS] plus one chunk mask per cube; only the 32-byte chunks (16 coefficients)
+//             that hold a non-zero value are ever written (3.3 of 32 on natural content), and
+//             kernel 2 only reads those.  This is the one place a coefficient is written.
+//   MODE_NAT: natural-order int16 cubes (the dct3d_quantize_u8 stage entry point).
+// One tile = one TMA box = 128 px x C rows x C frames = kWarps*CPW cubes; tiles are double
+// buffered so the next box lands while the current one is transformed.
+// ------------------------------------------------------------------------------------------
+constexpr int MODE_ZZ = 0, MODE_NAT = 1;
 
-// ------------------------------------------------------------------------------------------
-// Fused encoder: u8 frames -> Exp-Golomb stream (EMIT_Q = false) or -> int16 cubes (true).
-// Persistent CTAs take tiles from an atomic ticket, in stream order.
-// ------------------------------------------------------------------------------------------
 template <int C>
 struct EncSmem {
     using G = Geo<C>;
-    static constexpr int IN_OFF = 0;
-    static constexpr int XCH_OFF = IN_OFF + G::IN_BYTES;
+    static constexpr int TILE = G::CUBES_PER_BOX;
+    static constexpr int IN_OFF = 0;                                              // 2 x BOX_BYTES (1024-aligned)
+    static constexpr int XCH_OFF = IN_OFF + 2 * G::BOX_BYTES;
     static constexpr int ZZ_OFF = XCH_OFF + kWarps * Xch<C, float>::WARP_BYTES;
-    static constexpr int CM_OFF = ZZ_OFF + kTileCubes * G::ZZ_STRIDE * 2;
-    static constexpr int BAR_OFF = CM_OFF + kTileCubes * 4;
-    static constexpr int TOTAL = BAR_OFF + 32;
+    static constexpr int ZZ_BYTES = TILE * G::ZZ_STRIDE * 2;
+    static constexpr int BAR_OFF = ZZ_OFF + ZZ_BYTES;
+    static constexpr int TOTAL = BAR_OFF + 16;
 };
 
-template <int C, bool EMIT_Q>
-__global__ void __launch_bounds__(kThreads, 3)
+template <int C, int MODE>
+__global__ void __launch_bounds__(kThreads, 4)
 encode_kernel(const __grid_constant__ CUtensorMap tmap, const EncParams P)
 {
     using G = Geo<C>;
@@ -344,17 +322,12 @@ encode_kernel(const __grid_constant__ CUtensorMap tmap, const EncParams P)
     uint8_t *s_in = smem + S::IN_OFF;
     uint8_t *s_xch = smem + S::XCH_OFF;
     int16_t *s_zz = reinterpret_cast<int16_t *>(smem + S::ZZ_OFF);
-    uint32_t *s_cmask = reinterpret_cast<uint32_t *>(smem + S::CM_OFF);
     uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem + S::BAR_OFF);
-    long long *s_tile = reinterpret_cast<long long *>(smem + S::BAR_OFF + 8);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int cl = lane / C, r = lane % C;   // cube within the warp pass; t (stage 1) or k1 (stage 2)
+    const int cl = lane / C, r = lane % C;   // cube within the warp; t (stage 1) or k1 (stage 2)
     const Layout &L = P.L;
 
-    if (tid == 0 && P.use_tma) mbar_init(s_bar, 1);
-
-    // per-lane constants: reciprocal quantiser and zig-zag run bases for k1 = r
     float rq[G::NDIAG];
     uint32_t zb[G::NDIAG];
 #pragma unroll
@@ -362,193 +335,231 @@ encode_kernel(const __grid_constant__ CUtensorMap tmap, const EncParams P)
         rq[s] = 1.0f / (float)quant_divisor(s + r);
         zb[s] = zz_base<C>(r, s);
     }
-    uint32_t parity = 0;
-    __syncthreads();
-
-    for (;;) {
-        if (tid == 0) {
-            const long long tile = (long long)atomicAdd(P.ticket, 1u);
-            *s_tile = tile;
-            if (P.use_tma && tile < L.ntiles) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                mbar_expect_tx(s_bar, G::IN_BYTES);
+    auto issue_tma = [&](long long tile, int h) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(&s_bar[h], G::BOX_BYTES);
+        const BoxPos bp = box_pos<C>(L, tile);
 #pragma unroll 1
-                for (int bi = 0; bi < G::BOXES_PER_TILE; bi++) {
-                    const long long b = tile * G::BOXES_PER_TILE + bi;
-                    // a box past the end of the clip is loaded from coordinates outside the tensor: zero fill
-                    const BoxPos bp = b < L.nboxes ? box_pos<C>(L, b) : BoxPos{L.nslabs, 0, 0, 0, 0};
-#pragma unroll 1
-                    for (int y = 0; y < C; y++)
-                        tma_load_3d(s_in + bi * G::BOX_BYTES + y * G::ROW_BYTES, &tmap, bp.bxb * kBoxW, bp.byi * C + y,
-                                    bp.slab * C, s_bar);
-                }
-            }
-        }
-        __syncthreads();
-        const long long tile = *s_tile;
-        if (tile >= L.ntiles) break;
+        for (int y = 0; y < C; y++)
+            tma_load_3d(s_in + h * G::BOX_BYTES + y * G::ROW_BYTES, &tmap, bp.bxb * kBoxW, bp.byi * C + y, bp.slab * C, &s_bar[h]);
+    };
+    if (tid == 0 && P.use_tma) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        if ((long long)blockIdx.x < L.ntiles) issue_tma(blockIdx.x, 0);
+    }
 
-        uint32_t validmask = 0;
-#pragma unroll
-        for (int bi = 0; bi < G::BOXES_PER_TILE; bi++) {
-            const long long b = tile * G::BOXES_PER_TILE + bi;
-            if (b < L.nboxes) {
-                const int nv = box_pos<C>(L, b).nvalid;
-                validmask |= (nv >= 32 ? 0xffffffffu : ((1u << nv) - 1u)) << (bi * G::CUBES_PER_BOX);
-            }
-        }
-
+    int it = 0;
+    for (long long tile = blockIdx.x; tile < L.ntiles; tile += gridDim.x, it++) {
+        const int h = it & 1;
+        __syncthreads();                       // iteration it-1 is done with in[h^1]; barrier init visible
+        if (tid == 0 && P.use_tma && tile + gridDim.x < L.ntiles) issue_tma(tile + gridDim.x, h ^ 1);
+        const BoxPos bp = box_pos<C>(L, tile);
+        uint8_t *box = s_in + h * G::BOX_BYTES;
         if (!P.use_tma) {
             // plain loader: C-byte pieces (always aligned since W % C == 0), same swizzled layout
-            constexpr int PIECES = G::IN_BYTES / C;
+            constexpr int PIECES = G::BOX_BYTES / C;
             for (int i = tid; i < PIECES; i += kThreads) {
-                const int bi = i / (G::BOX_BYTES / C);
-                const int rem = i - bi * (G::BOX_BYTES / C);
-                const int row = rem / (kBoxW / C);          // y*C + t
-                const int cb = rem - row * (kBoxW / C);     // cube in box
+                const int row = i / (kBoxW / C);            // y*C + t
+                const int cb = i - row * (kBoxW / C);       // cube in box
                 const int y = row / C, t = row - y * C;
-                const long long b = tile * G::BOXES_PER_TILE + bi;
                 uint32_t lo = 0, hi = 0;
-                if (b < L.nboxes) {
-                    const BoxPos bp = box_pos<C>(L, b);
-                    if (cb < bp.nvalid) {
-                        const uint8_t *src = P.frames + ((size_t)(bp.slab * C + t) * L.H + (bp.byi * C + y)) * L.W +
-                                             bp.bxb * kBoxW + cb * C;
-                        if (C == 8) { const uint2 v = *reinterpret_cast<const uint2 *>(src); lo = v.x; hi = v.y; }
-                        else lo = *reinterpret_cast<const uint32_t *>(src);
-                    }
+                if (cb < bp.nvalid) {
+                    const uint8_t *src = P.frames + ((size_t)(bp.slab * C + t) * L.H + (bp.byi * C + y)) * L.W +
+                                         bp.bxb * kBoxW + cb * C;
+                    if (C == 8) { const uint2 v = *reinterpret_cast<const uint2 *>(src); lo = v.x; hi = v.y; }
+                    else lo = *reinterpret_cast<const uint32_t *>(src);
                 }
-                uint8_t *dst = s_in + bi * G::BOX_BYTES + in_offset<C>(y, t, cb * C);
+                uint8_t *dst = box + in_offset<C>(y, t, cb * C);
                 if (C == 8) *reinterpret_cast<uint2 *>(dst) = make_uint2(lo, hi);
                 else *reinterpret_cast<uint32_t *>(dst) = lo;
             }
             __syncthreads();
         } else {
+            const uint32_t parity = (uint32_t)(it >> 1) & 1u;
             unsigned spins = 0;
-            while (!mbar_try_wait(s_bar, parity)) {
+            while (!mbar_try_wait(&s_bar[h], parity)) {
                 if (++spins > (1u << 22)) { if (tid == 0) atomicOr(P.err, 16u); break; }   // never hang the GPU
             }
-            parity ^= 1;
         }
 
-        // ---- transform passes -----------------------------------------------------------
-#pragma unroll 1
-        for (int p = 0; p < G::PASSES; p++) {
-            const int slot = p * (kWarps * G::CPW) + warp * G::CPW + cl;
-            const int bi = slot / G::CUBES_PER_BOX, cb = slot % G::CUBES_PER_BOX;
-            float a[C][C], bq[C][C];
-            const uint8_t *box = s_in + bi * G::BOX_BYTES;
+        // ---- transform: one cube per C threads ---------------------------------------------
+        const int slot = warp * G::CPW + cl;     // cube in the tile
+        float a[C][C], bq[C][C];
 #pragma unroll
-            for (int y = 0; y < C; y++) {
-                const uint8_t *src = box + in_offset<C>(y, r, cb * C);
-                if (C == 8) {
-                    const uint2 v = *reinterpret_cast<const uint2 *>(src);
+        for (int y = 0; y < C; y++) {
+            const uint8_t *src = box + in_offset<C>(y, r, slot * C);
+            if (C == 8) {
+                const uint2 v = *reinterpret_cast<const uint2 *>(src);
 #pragma unroll
-                    for (int x = 0; x < 4; x++) { a[y][x] = byte_to_float(v.x, x); a[y][(x + 4) % C] = byte_to_float(v.y, x); }
-                } else {
-                    const uint32_t v = *reinterpret_cast<const uint32_t *>(src);
-#pragma unroll
-                    for (int x = 0; x < 4; x++) a[y][x % C] = byte_to_float(v, x);
-                }
-            }
-            fwd_xy<C, float>(a);
-            Xch<C, float>::transpose(s_xch + warp * Xch<C, float>::WARP_BYTES, cl, r, a, bq);
-            fwd_t<C, float>(bq);
-            // bq[k0][k2] is coefficient (k0, k1 = r, k2)
-            if (EMIT_Q) {
-                if ((validmask >> slot) & 1u) {
-                    const BoxPos bp = box_pos<C>(L, tile * G::BOXES_PER_TILE + bi);
-                    int16_t *dst = P.qcubes + (size_t)(bp.cube0 + cb) * G::CS + r * C;
-#pragma unroll
-                    for (int k0 = 0; k0 < C; k0++) {
-                        uint32_t w[C / 2];
-#pragma unroll
-                        for (int k2 = 0; k2 < C; k2 += 2) {
-                            const uint32_t q0 = (uint32_t)quantize_f32(bq[k0][k2], rq[k0 + k2]) & 0xffffu;
-                            const uint32_t q1 = (uint32_t)quantize_f32(bq[k0][k2 + 1], rq[k0 + k2 + 1]) & 0xffffu;
-                            w[k2 / 2] = q0 | (q1 << 16);
-                        }
-                        if (C == 8) *reinterpret_cast<uint4 *>(dst + k0 * C * C) = make_uint4(w[0], w[1], w[2 % (C / 2)], w[3 % (C / 2)]);
-                        else *reinterpret_cast<uint2 *>(dst + k0 * C * C) = make_uint2(w[0], w[1]);
-                    }
-                }
+                for (int x = 0; x < 4; x++) { a[y][x] = byte_to_float(v.x, x); a[y][(x + 4) % C] = byte_to_float(v.y, x); }
             } else {
-                int16_t *zz = s_zz + slot * G::ZZ_STRIDE;
+                const uint32_t v = *reinterpret_cast<const uint32_t *>(src);
 #pragma unroll
-                for (int k0 = 0; k0 < C; k0++) {
-#pragma unroll
-                    for (int k2 = 0; k2 < C; k2++) {
-                        const int s = k0 + k2;
-                        const int k0min = s > C - 1 ? s - (C - 1) : 0;
-                        zz[zb[s] + (k0 - k0min)] = (int16_t)quantize_f32(bq[k0][k2], rq[s]);
-                    }
-                }
-                __syncwarp();
-                // 16-coefficient chunk masks of this pass's cubes
-                constexpr int ITER = (G::CPW * G::CHUNKS) / 32;   // 4 (C=8) / 1 (C=4)
-                const int slot0 = p * (kWarps * G::CPW) + warp * G::CPW;
-#pragma unroll
-                for (int it = 0; it < ITER; it++) {
-                    const int ci = it * 32 + lane;
-                    const int cube = ci / G::CHUNKS, chunk = ci % G::CHUNKS;
-                    const uint4 *q = reinterpret_cast<const uint4 *>(s_zz + (slot0 + cube) * G::ZZ_STRIDE + chunk * 16);
-                    const uint4 v0 = q[0], v1 = q[1];
-                    const uint32_t any = v0.x | v0.y | v0.z | v0.w | v1.x | v1.y | v1.z | v1.w;
-                    const uint32_t bal = __ballot_sync(0xffffffffu, any != 0);
-                    if (G::CHUNKS == 32) { if (lane == 0) s_cmask[slot0 + it] = bal; }
-                    else { if (lane < 32 / G::CHUNKS) s_cmask[slot0 + lane] = (bal >> (lane * G::CHUNKS)) & ((1u << (G::CHUNKS & 31)) - 1u); }
-                }
+                for (int x = 0; x < 4; x++) a[y][x % C] = byte_to_float(v, x);
             }
         }
-        __syncthreads();
-        if (!EMIT_Q && warp == 0) entropy_stage<C>(P, tile, s_zz, s_cmask, validmask, lane);
+        fwd_xy<C, float>(a);
+        Xch<C, float>::transpose(s_xch + warp * Xch<C, float>::WARP_BYTES, cl, r, a, bq);
+        fwd_t<C, float>(bq);
+        // bq[k0][k2] is coefficient (k0, k1 = r, k2)
+        if (MODE == MODE_NAT) {
+            if (slot < bp.nvalid) {
+                int16_t *dst = P.qcubes + (size_t)(bp.cube0 + slot) * G::CS + r * C;
+#pragma unroll
+                for (int k0 = 0; k0 < C; k0++) {
+                    uint32_t w[C / 2];
+#pragma unroll
+                    for (int k2 = 0; k2 < C; k2 += 2) {
+                        const uint32_t q0 = (uint32_t)quantize_f32(bq[k0][k2], rq[k0 + k2]) & 0xffffu;
+                        const uint32_t q1 = (uint32_t)quantize_f32(bq[k0][k2 + 1], rq[k0 + k2 + 1]) & 0xffffu;
+                        w[k2 / 2] = q0 | (q1 << 16);
+                    }
+                    if (C == 8) *reinterpret_cast<uint4 *>(dst + k0 * C * C) = make_uint4(w[0], w[1], w[2 % (C / 2)], w[3 % (C / 2)]);
+                    else *reinterpret_cast<uint2 *>(dst + k0 * C * C) = make_uint2(w[0], w[1]);
+                }
+            }
+            continue;
+        }
+        // zig-zag scatter into this warp's private cubes (runs of a diagonal are contiguous)
+        int16_t *zz = s_zz + slot * G::ZZ_STRIDE;
+#pragma unroll
+        for (int k0 = 0; k0 < C; k0++) {
+#pragma unroll
+            for (int k2 = 0; k2 < C; k2++) {
+                const int s = k0 + k2;
+                const int k0min = s > C - 1 ? s - (C - 1) : 0;
+                zz[zb[s] + (k0 - k0min)] = (int16_t)quantize_f32(bq[k0][k2], rq[s]);
+            }
+        }
+        __syncwarp();
+        // chunk masks + sparse store: lane <-> 16-coefficient chunk
+        constexpr int ITER = (G::CPW * G::CHUNKS) / 32;   // 4 (C=8) / 1 (C=4)
+        const int slot0 = warp * G::CPW;
+#pragma unroll
+        for (int k = 0; k < ITER; k++) {
+            const int ci = k * 32 + lane;
+            const int cube = ci / G::CHUNKS, chunk = ci % G::CHUNKS;
+            const uint4 *q = reinterpret_cast<const uint4 *>(s_zz + (slot0 + cube) * G::ZZ_STRIDE + chunk * 16);
+            const uint4 v0 = q[0], v1 = q[1];
+            const uint32_t any = v0.x | v0.y | v0.z | v0.w | v1.x | v1.y | v1.z | v1.w;
+            const bool ok = slot0 + cube < bp.nvalid;
+            const uint32_t bal = __ballot_sync(0xffffffffu, any != 0);
+            const long long gc = bp.cube0 + slot0 + cube;
+            if (ok && any != 0) {
+                uint4 *dst = reinterpret_cast<uint4 *>(P.zzg + (size_t)gc * G::CS + chunk * 16);
+                dst[0] = v0;
+                dst[1] = v1;
+            }
+            if (G::CHUNKS == 32) { if (lane == 0 && ok) P.cmask[gc] = bal; }
+            else { if (chunk == 0 && ok) P.cmask[gc] = (bal >> (cube * G::CHUNKS)) & ((1u << (G::CHUNKS & 31)) - 1u); }
+        }
+        __syncwarp();                           // zz is rewritten by the next tile
+    }
+}
+
+// Natural-order int16 cubes -> the same zig-zag chunk scratch + masks (dct3d_eg_encode_i16).
+// One warp per cube, lane <-> chunk.
+template <int C>
+__global__ void __launch_bounds__(kThreads)
+zz_gather_kernel(const EncParams P)
+{
+    using G = Geo<C>;
+    const int lane = threadIdx.x & 31;
+    const long long wid = (long long)blockIdx.x * kWarps + (threadIdx.x >> 5);
+    const long long nw = (long long)gridDim.x * kWarps;
+    const uint16_t *lin = zz_lin<C>();
+    for (long long cube = wid; cube < P.L.ncubes; cube += nw) {
+        const int16_t *src = P.qcubes_in + (size_t)cube * G::CS;
+        uint32_t mask = 0;
+        for (int c0 = 0; c0 < G::CHUNKS; c0 += 32) {
+            const int chunk = c0 + lane;
+            uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            uint32_t any = 0;
+            if (chunk < G::CHUNKS) {
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    const uint32_t v = (uint16_t)src[lin[chunk * 16 + i]];
+                    w[i >> 1] |= v << ((i & 1) * 16);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; i++) any |= w[i];
+                if (any) {
+                    uint4 *dst = reinterpret_cast<uint4 *>(P.zzg + (size_t)cube * G::CS + chunk * 16);
+                    dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+                    dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+                }
+            }
+            mask |= __ballot_sync(0xffffffffu, any != 0);
+        }
+        if (lane == 0) P.cmask[cube] = mask;
     }
 }
 
 // ------------------------------------------------------------------------------------------
-// Exp-Golomb encoder for int16 cubes already in global memory (natural order): gathers the
-// cubes of a tile into the zig-zag buffer, then the same entropy stage.
+// Encoder kernel 2: Exp-Golomb bit packing, one thread per cube, 256 cubes per CTA tile.
+//   count pass (only the non-zero chunks) -> block scan -> decoupled look-back across tiles
+//   (tiles taken from a ticket, in stream order) -> write pass straight into the stream.
+// The serial bit append per thread is latency-bound; it runs at full occupancy so that other
+// warps cover it.
 // ------------------------------------------------------------------------------------------
+constexpr int kPackThreads = 256;
+
 template <int C>
-__global__ void __launch_bounds__(kThreads)
-eg_encode_kernel(const EncParams P)
+__global__ void __launch_bounds__(kPackThreads)
+eg_pack_kernel(const EncParams P)
 {
     using G = Geo<C>;
-    __shared__ __align__(16) int16_t s_zz[kTileCubes * G::ZZ_STRIDE];
-    __shared__ uint32_t s_cmask[kTileCubes];
+    __shared__ uint32_t s_wsum[kPackThreads / 32];
+    __shared__ unsigned long long s_off;
     __shared__ long long s_tile;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint16_t *lin = zz_lin<C>();
+    const long long ntiles = (P.L.ncubes + kPackThreads - 1) / kPackThreads;
     for (;;) {
         if (tid == 0) s_tile = (long long)atomicAdd(P.ticket, 1u);
         __syncthreads();
         const long long tile = s_tile;
-        if (tile >= P.L.ntiles) break;
-        const long long cube0 = tile * kTileCubes;
-        const int nv = (int)min((long long)kTileCubes, P.L.ncubes - cube0);
-        for (int i = tid; i < nv * G::CS; i += kThreads) {
-            const int cube = i / G::CS, pos = i % G::CS;
-            s_zz[cube * G::ZZ_STRIDE + pos] = P.qcubes_in[(size_t)(cube0 + cube) * G::CS + lin[pos]];
+        if (tile >= ntiles) break;
+        const long long cube = tile * kPackThreads + tid;
+        const bool valid = cube < P.L.ncubes;
+        const int16_t *zz = P.zzg + (size_t)(valid ? cube : 0) * G::CS;
+        const uint32_t cm = valid ? P.cmask[cube] : 0u;
+        const uint32_t nb = valid ? eg_count_cube<G::CS>(zz, cm) : 0u;
+        uint32_t incl = nb;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += o;
         }
+        if (lane == 31) s_wsum[warp] = incl;
         __syncthreads();
-        // chunk masks: one warp per 8 cubes
-        for (int cube = warp; cube < nv; cube += kWarps) {
-            uint32_t m = 0;
-            for (int c0 = 0; c0 < G::CHUNKS; c0 += 32) {
-                const int chunk = c0 + lane;
-                uint32_t any = 0;
-                if (chunk < G::CHUNKS) {
-                    const uint4 *q = reinterpret_cast<const uint4 *>(s_zz + cube * G::ZZ_STRIDE + chunk * 16);
-                    const uint4 v0 = q[0], v1 = q[1];
-                    any = v0.x | v0.y | v0.z | v0.w | v1.x | v1.y | v1.z | v1.w;
-                }
-                m |= __ballot_sync(0xffffffffu, any != 0);
+        if (warp == 0) {
+            const uint32_t w = lane < kPackThreads / 32 ? s_wsum[lane] : 0u;
+            uint32_t wi = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xffffffffu, wi, d);
+                if (lane >= d) wi += o;
             }
-            if (lane == 0) s_cmask[cube] = m;
+            if (lane < kPackThreads / 32) s_wsum[lane] = wi - w;          // exclusive warp offsets
+            const uint32_t total = __shfl_sync(0xffffffffu, wi, 31);
+            const unsigned long long off = tile_lookback(P.tile_status, tile, total, P.start_bit, lane, P.err);
+            if (lane == 0) {
+                s_off = off;
+                if (tile == ntiles - 1) *P.end_bit = off + total;
+            }
         }
         __syncthreads();
-        if (warp == 0) entropy_stage<C>(P, tile, s_zz, s_cmask, nv >= 32 ? 0xffffffffu : ((1u << nv) - 1u), lane);
-        __syncthreads();
+        if (valid) {
+            const unsigned long long off = s_off + s_wsum[warp] + (incl - nb);
+            if (off + nb + 64 > P.cap_bits) {
+                atomicOr(P.err, 1u);
+            } else {
+                GlobalSink sink{P.out_words};
+                eg_write_cube<G::CS>(zz, cm, off, sink);
+            }
+        }
+        __syncthreads();                        // s_tile / s_wsum / s_off are reused
     }
 }
 

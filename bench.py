@@ -164,7 +164,11 @@ def run_ours(args):
     cap = N // 2 + 4096
     d_stream = torch.zeros(cap, dtype=torch.uint8, device=dev)
     d_out = torch.empty_like(frames)
-    st = torch.cuda.current_stream().cuda_stream
+    # a real (non-NULL) stream: NULL would mean "the context's own stream" to libdct3d, invisible to torch events
+    tstream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(tstream)
+    st = tstream.cuda_stream
+    assert st != 0
 
     def step():
         end = c.encode_u8_dev(frames, F, d_stream, cap, 0, st)
