@@ -53,7 +53,7 @@ struct dct3d_ctx {
     long launches = 0;
     cudaStream_t stream = nullptr;
     std::string err;
-    DevBuf frames, bits, q, status, ctrl, seg, cubeoff, fa, fb, zz, cmask;
+    DevBuf frames, bits, q, status, ctrl, seg, fa, fb, zz, cmask;
     Ctrl *h_ctrl = nullptr;          // pinned
     unsigned long long *h_u64 = nullptr;  // pinned scratch (4 entries)
     // streaming state
@@ -237,6 +237,22 @@ int zero_stream(dct3d_ctx *ctx, void *d_stream, size_t cap, uint64_t start_bit, 
 
 
 template <int C>
+static int launch_reconstruct_zz(dct3d_ctx *ctx, const Layout &L, void *d_frames, cudaStream_t st)
+{
+    auto kern = reconstruct_zz_kernel<C>;
+    const int smem = RecSmem<C>::TOTAL;
+    CU_CHECK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int occ = 0;
+    CU_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem));
+    const long long groups = (L.ncubes + Geo<C>::CPW - 1) / Geo<C>::CPW;
+    const long long grid = std::min<long long>((groups + kWarps - 1) / kWarps, (long long)ctx->num_sms * std::max(occ, 1));
+    kern<<<(unsigned)grid, kThreads, smem, st>>>(L, (const int16_t *)ctx->zz.p, (const uint32_t *)ctx->cmask.p, (uint8_t *)d_frames);
+    ctx->launches++;
+    CU_CHECK(ctx, cudaGetLastError());
+    return DCT3D_OK;
+}
+
+template <int C>
 static int launch_reconstruct(dct3d_ctx *ctx, const Layout &L, const void *d_q, void *d_frames, cudaStream_t st)
 {
     const int smem = kWarps * Xch<C, float>::WARP_BYTES;
@@ -352,7 +368,7 @@ void dct3d_destroy(dct3d_ctx *ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    for (DevBuf *b : {&ctx->frames, &ctx->bits, &ctx->q, &ctx->status, &ctx->ctrl, &ctx->seg, &ctx->cubeoff, &ctx->fa, &ctx->fb, &ctx->zz, &ctx->cmask}) b->release();
+    for (DevBuf *b : {&ctx->frames, &ctx->bits, &ctx->q, &ctx->status, &ctx->ctrl, &ctx->seg, &ctx->fa, &ctx->fb, &ctx->zz, &ctx->cmask}) b->release();
     if (ctx->h_ctrl) cudaFreeHost(ctx->h_ctrl);
     if (ctx->h_u64) cudaFreeHost(ctx->h_u64);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -516,9 +532,9 @@ int dct3d_eg_encode_i16_dev(dct3d_ctx *ctx, const void *d_qcubes, size_t ncubes,
     return run_pack(ctx, P, d_stream, cap, start_bit, end_bit, st);
 }
 
-// Index discovery + parse: stream -> natural-order int16 cubes in ctx->q (or d_qcubes).
+// Index discovery + parse: stream -> zig-zag chunk scratch (ctx->zz, ctx->cmask).
 static int parse_common(dct3d_ctx *ctx, const void *d_stream, size_t nbytes, uint64_t start_bit, size_t ncubes,
-                        void *d_qcubes, uint64_t *end_bit, cudaStream_t st)
+                        uint64_t *end_bit, cudaStream_t st)
 {
     int rc;
     const int C = ctx->C, CS = C * C * C;
@@ -532,26 +548,26 @@ static int parse_common(dct3d_ctx *ctx, const void *d_stream, size_t nbytes, uin
     P.nwords = ((unsigned long long)nbytes + 3) / 4;
     P.nbits_total = (unsigned long long)nbytes * 8;
     P.start_bit = start_bit;
-    P.seg_bits = 4096;
+    P.seg_bits = 1024;
     P.nseg = (P.nbits_total - start_bit + P.seg_bits - 1) / P.seg_bits;
     // seg arrays: count[nseg] over[nseg+1] used[nseg] (u32) first[nseg+1] (u64)
     const size_t n = (size_t)P.nseg;
     const size_t off_first = ((3 * n + 1) * 4 + 7) & ~(size_t)7;
     CU_CHECK(ctx, ctx->seg.reserve(off_first + (n + 1) * 8));
-    CU_CHECK(ctx, ctx->cubeoff.reserve((ncubes + 1) * 8));
     CU_CHECK(ctx, ctx->ctrl.reserve(sizeof(Ctrl)));
+    CU_CHECK(ctx, ctx->zz.reserve(ncubes * CS * sizeof(int16_t)));
+    CU_CHECK(ctx, ctx->cmask.reserve(ncubes * 4));
     P.seg_count = (unsigned int *)ctx->seg.p;
     P.seg_over = P.seg_count + n;
     P.seg_used = P.seg_over + n + 1;
     P.seg_first = (unsigned long long *)((uint8_t *)ctx->seg.p + off_first);
     Ctrl *dc = (Ctrl *)ctx->ctrl.p;
-    P.changed = &dc->changed; P.err = &dc->err;
-    P.cube_off = (unsigned long long *)ctx->cubeoff.p;
-    P.qcubes = (int16_t *)d_qcubes;
+    P.changed = &dc->changed; P.err = &dc->err; P.end_bit = &dc->end_bit;
+    P.zzg = (int16_t *)ctx->zz.p;
+    P.cmask = (uint32_t *)ctx->cmask.p;
     CU_CHECK(ctx, cudaMemsetAsync(ctx->ctrl.p, 0, sizeof(Ctrl), st));
     CU_CHECK(ctx, cudaMemsetAsync(P.seg_over, 0, (n + 1) * 4, st));
-    CU_CHECK(ctx, cudaMemsetAsync(P.cube_off, 0xff, (ncubes + 1) * 8, st));
-    CU_CHECK(ctx, cudaMemsetAsync(d_qcubes, 0, ncubes * CS * sizeof(int16_t), st));
+    CU_CHECK(ctx, cudaMemsetAsync(P.cmask, 0, ncubes * 4, st));
     const unsigned sb = 128, sg = (unsigned)((P.nseg + sb - 1) / sb);
     seg_scan_kernel<<<sg, sb, 0, st>>>(P, 1);
     ctx->launches++;
@@ -563,25 +579,29 @@ static int parse_common(dct3d_ctx *ctx, const void *d_stream, size_t nbytes, uin
         if ((rc = fetch_ctrl(ctx, st))) return rc;
         if (!ctx->h_ctrl->changed) break;
     }
-    seg_prefix_kernel<<<1, 1024, 0, st>>>(P);
-    ctx->launches++;
+    {
+        const long long stiles = (long long)((P.nseg + kScanThreads * kScanItems - 1) / (kScanThreads * kScanItems));
+        CU_CHECK(ctx, ctx->status.reserve((size_t)stiles * 8));
+        CU_CHECK(ctx, cudaMemsetAsync(ctx->status.p, 0, (size_t)stiles * 8, st));
+        CU_CHECK(ctx, cudaMemsetAsync(&dc->ticket, 0, 4, st));
+        const long long grid = std::min<long long>(stiles, (long long)ctx->num_sms * 8);
+        seg_prefix_kernel<<<(unsigned)grid, kScanThreads, 0, st>>>(P, (unsigned long long *)ctx->status.p, &dc->ticket);
+        ctx->launches++;
+    }
     CU_CHECK(ctx, cudaMemcpyAsync(ctx->h_u64, P.seg_first + n, 8, cudaMemcpyDeviceToHost, st));
     if ((rc = fetch_ctrl(ctx, st))) return rc;
     if (ctx->h_ctrl->err & 2u) return fail(ctx, DCT3D_E_STREAM, "malformed Exp-Golomb code in stream");
     if (ctx->h_u64[0] < (unsigned long long)ncubes * CS)
         return fail(ctx, DCT3D_E_NEED_MORE, "stream holds %llu codes, %llu needed", ctx->h_u64[0], (unsigned long long)ncubes * CS);
-    if (C == 8) cube_index_kernel<512><<<sg, sb, 0, st>>>(P); else cube_index_kernel<64><<<sg, sb, 0, st>>>(P);
-    ctx->launches++;
-    const unsigned pb = 128, pg = (unsigned)((ncubes + pb - 1) / pb);
-    if (C == 8) cube_parse_kernel<8><<<pg, pb, 0, st>>>(P); else cube_parse_kernel<4><<<pg, pb, 0, st>>>(P);
+    const unsigned pg = (unsigned)((P.nseg + kParseThreads - 1) / kParseThreads);
+    if (C == 8) seg_parse_kernel<8><<<pg, kParseThreads, 0, st>>>(P); else seg_parse_kernel<4><<<pg, kParseThreads, 0, st>>>(P);
     ctx->launches++;
     CU_CHECK(ctx, cudaGetLastError());
     if (end_bit) {
-        CU_CHECK(ctx, cudaMemcpyAsync(ctx->h_u64, P.cube_off + ncubes, 8, cudaMemcpyDeviceToHost, st));
         if ((rc = fetch_ctrl(ctx, st))) return rc;
         if (ctx->h_ctrl->err & 2u) return fail(ctx, DCT3D_E_STREAM, "malformed Exp-Golomb code in stream");
         if (ctx->h_ctrl->err & 4u) return fail(ctx, DCT3D_E_STREAM, "Exp-Golomb stream truncated");
-        *end_bit = ctx->h_u64[0];
+        *end_bit = ctx->h_ctrl->end_bit;
     }
     return DCT3D_OK;
 }
@@ -593,7 +613,21 @@ int dct3d_eg_decode_i16_dev(dct3d_ctx *ctx, const void *d_stream, size_t nbytes,
     if (rc) return rc;
     if (ncubes == 0) { if (end_bit) *end_bit = start_bit; return DCT3D_OK; }
     if (!d_qcubes) return fail(ctx, DCT3D_E_INVALID, "null cube pointer");
-    return parse_common(ctx, d_stream, nbytes, start_bit, ncubes, d_qcubes, end_bit, pick(ctx, cuda_stream));
+    cudaStream_t st = pick(ctx, cuda_stream);
+    if ((rc = parse_common(ctx, d_stream, nbytes, start_bit, ncubes, end_bit, st))) return rc;
+    DecParams P;
+    memset(&P, 0, sizeof P);
+    P.L = make_layout(ctx->W, ctx->H, ctx->C, 0);
+    P.L.ncubes = (long long)ncubes;
+    P.zzg = (int16_t *)ctx->zz.p;
+    P.cmask = (uint32_t *)ctx->cmask.p;
+    P.qcubes = (int16_t *)d_qcubes;
+    const long long grid = std::min<long long>(((long long)ncubes + kWarps - 1) / kWarps, (long long)ctx->num_sms * 16);
+    if (ctx->C == 8) zz_scatter_kernel<8><<<(unsigned)grid, kThreads, 0, st>>>(P);
+    else zz_scatter_kernel<4><<<(unsigned)grid, kThreads, 0, st>>>(P);
+    ctx->launches++;
+    CU_CHECK(ctx, cudaGetLastError());
+    return DCT3D_OK;
 }
 
 int dct3d_reconstruct_i16_dev(dct3d_ctx *ctx, const void *d_qcubes, int nframes, void *d_frames, void *cuda_stream)
@@ -620,11 +654,10 @@ int dct3d_decode_u8_dev(dct3d_ctx *ctx, const void *d_stream, size_t nbytes, uin
     if (!d_frames) return fail(ctx, DCT3D_E_INVALID, "null frame pointer");
     const Layout L = make_layout(ctx->W, ctx->H, C, nslabs);
     cudaStream_t st = pick(ctx, cuda_stream);
-    CU_CHECK(ctx, ctx->q.reserve((size_t)L.ncubes * C * C * C * sizeof(int16_t)));
     uint64_t end = 0;
-    if ((rc = parse_common(ctx, d_stream, nbytes, start_bit, (size_t)L.ncubes, ctx->q.p, &end, st))) return rc;
+    if ((rc = parse_common(ctx, d_stream, nbytes, start_bit, (size_t)L.ncubes, &end, st))) return rc;
     if (end_bit) *end_bit = end;
-    return C == 8 ? launch_reconstruct<8>(ctx, L, ctx->q.p, d_frames, st) : launch_reconstruct<4>(ctx, L, ctx->q.p, d_frames, st);
+    return C == 8 ? launch_reconstruct_zz<8>(ctx, L, d_frames, st) : launch_reconstruct_zz<4>(ctx, L, d_frames, st);
 }
 
 int dct3d_forward_f32_dev(dct3d_ctx *c, const void *i, void *o, int n, void *s) { return transform_dev<float, true, false>(c, i, o, n, s); }

@@ -582,9 +582,11 @@ struct DecParams {
     unsigned int *seg_used;             // [nseg] entry overhang used for the current count
     unsigned long long *seg_first;      // [nseg+1] exclusive prefix of seg_count
     unsigned int *changed;              // fix-up flag
-    unsigned long long *cube_off;       // [ncubes+1] absolute bit offset of every cube
     unsigned int *err;                  // bit1 = malformed, bit2 = truncated
-    int16_t *qcubes;                    // natural-order cubes
+    unsigned long long *end_bit;        // out: first bit after the last code
+    int16_t *zzg;                       // zig-zag chunk scratch [cube][CS]
+    uint32_t *cmask;                    // [cube], zeroed before seg_parse_kernel
+    int16_t *qcubes;                    // natural-order cubes (zz_scatter_kernel)
     uint8_t *frames;
 };
 
@@ -611,99 +613,249 @@ __global__ void seg_scan_kernel(const DecParams P, int first_pass)
     if (first_pass || P.seg_over[k + 1] != over) { P.seg_over[k + 1] = over; if (!first_pass) *P.changed = 1u; }
 }
 
-// Exclusive prefix sum of seg_count (single CTA, 1024 threads, sequential over chunks).
-__global__ void seg_prefix_kernel(const DecParams P)
+// Exclusive prefix sum of seg_count over all segments: 1024 segments per CTA tile, block scan,
+// decoupled look-back across tiles (same machinery as the bit packer).  seg_first[nseg] = total.
+constexpr int kScanThreads = 256, kScanItems = 4;
+
+__global__ void __launch_bounds__(kScanThreads)
+seg_prefix_kernel(const DecParams P, unsigned long long *tile_status, unsigned int *ticket)
 {
-    __shared__ unsigned long long s_warp[32];
-    __shared__ unsigned long long s_carry;
+    __shared__ unsigned long long s_wsum[kScanThreads / 32];
+    __shared__ unsigned long long s_off;
+    __shared__ long long s_tile;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_carry = 0;
-    __syncthreads();
-    for (unsigned long long base = 0; base < P.nseg; base += 1024) {
-        const unsigned long long k = base + tid;
-        unsigned long long v = k < P.nseg ? P.seg_count[k] : 0ull;
-        if (v & 0x80000000ull) { atomicOr(P.err, 2u); v &= 0x7fffffffull; }
-        unsigned long long incl = v;
+    constexpr int TILE = kScanThreads * kScanItems;
+    const long long ntiles = (long long)((P.nseg + TILE - 1) / TILE);
+    for (;;) {
+        if (tid == 0) s_tile = (long long)atomicAdd(ticket, 1u);
+        __syncthreads();
+        const long long tile = s_tile;
+        if (tile >= ntiles) break;
+        const unsigned long long k0 = (unsigned long long)tile * TILE + (unsigned long long)tid * kScanItems;
+        unsigned long long v[kScanItems], sum = 0;
+#pragma unroll
+        for (int i = 0; i < kScanItems; i++) {
+            unsigned long long x = k0 + i < P.nseg ? P.seg_count[k0 + i] : 0ull;
+            if (x & 0x80000000ull) { atomicOr(P.err, 2u); x &= 0x7fffffffull; }   // still malformed after convergence
+            v[i] = x;
+            sum += x;
+        }
+        unsigned long long incl = sum;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { const unsigned long long o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
-        if (lane == 31) s_warp[warp] = incl;
+        if (lane == 31) s_wsum[warp] = incl;
         __syncthreads();
         if (warp == 0) {
-            unsigned long long w = s_warp[lane], wi = w;
+            const unsigned long long w = lane < kScanThreads / 32 ? s_wsum[lane] : 0ull;
+            unsigned long long wi = w;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) { const unsigned long long o = __shfl_up_sync(0xffffffffu, wi, d); if (lane >= d) wi += o; }
-            s_warp[lane] = wi - w;
+            if (lane < kScanThreads / 32) s_wsum[lane] = wi - w;
+            const unsigned long long total = __shfl_sync(0xffffffffu, wi, 31);
+            const unsigned long long off = tile_lookback(tile_status, tile, total, 0ull, lane, P.err);
+            if (lane == 0) {
+                s_off = off;
+                if (tile == ntiles - 1) P.seg_first[P.nseg] = off + total;
+            }
         }
         __syncthreads();
-        const unsigned long long carry = s_carry;
-        if (k < P.nseg) P.seg_first[k] = carry + s_warp[warp] + incl - v;
-        __syncthreads();
-        if (tid == 1023) s_carry = carry + s_warp[warp] + incl;
+        unsigned long long run = s_off + s_wsum[warp] + incl - sum;
+#pragma unroll
+        for (int i = 0; i < kScanItems; i++) {
+            if (k0 + i < P.nseg) P.seg_first[k0 + i] = run;
+            run += v[i];
+        }
         __syncthreads();
     }
-    if (tid == 0) P.seg_first[P.nseg] = s_carry;
 }
 
-// Every thread re-walks its segment and records the bit offset of each cube boundary in it.
-template <int CS>
-__global__ void cube_index_kernel(const DecParams P)
+// Every thread re-walks its segment, now knowing the index of its first code, and writes the
+// non-zero coefficients into the zig-zag chunk scratch (same format the encoder's kernel 1
+// produces): a thread owns the 16-coefficient chunks that START among its codes, so it skips up to
+// 15 leading codes (owned by its predecessor) and runs up to 15 codes past its segment.  Chunks are
+// assembled in a per-thread shared-memory slot and stored whole (32 B); cmask (zeroed beforehand)
+// collects the non-zero chunks of every cube.
+constexpr int kParseThreads = 128;
+constexpr int kStageWords = 10;   // 40-byte stride: 32 B of data + padding against bank conflicts
+
+template <int C>
+__global__ void __launch_bounds__(kParseThreads)
+seg_parse_kernel(const DecParams P)
 {
+    using G = Geo<C>;
+    __shared__ __align__(8) uint32_t s_stage[kParseThreads * kStageWords];
     const unsigned long long k = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
     if (k >= P.nseg) return;
-    unsigned long long idx = P.seg_first[k];                      // index of the first code starting here
+    const unsigned long long ncodes = (unsigned long long)P.L.ncubes * G::CS;
+    unsigned long long cur = P.seg_first[k];
     const unsigned long long nxt = P.seg_first[k + 1];
-    const unsigned long long ncodes = (unsigned long long)P.L.ncubes * CS;
-    if (idx >= nxt) return;
-    // first cube boundary at or after idx
-    unsigned long long target = ((idx + CS - 1) / CS) * CS;
-    if (target > ncodes || target >= nxt) return;
-    const unsigned long long seg0 = P.start_bit + k * (unsigned long long)P.seg_bits;
+    const unsigned long long lo = (cur + 15) & ~15ull;
+    unsigned long long hi = (nxt + 15) & ~15ull;
+    if (hi > ncodes) hi = ncodes;
+    if (lo >= hi) return;
+    uint32_t *stage = s_stage + threadIdx.x * kStageWords;
+    int16_t *stage16 = reinterpret_cast<int16_t *>(stage);
+#pragma unroll
+    for (int i = 0; i < 8; i++) stage[i] = 0;
+    bool dirty = false;
+    auto flush = [&](unsigned long long chunk) {
+        uint2 *dst = reinterpret_cast<uint2 *>(P.zzg + chunk * 16);
+        const uint2 *src = reinterpret_cast<const uint2 *>(stage);
+#pragma unroll
+        for (int i = 0; i < 4; i++) { dst[i] = src[i]; }
+#pragma unroll
+        for (int i = 0; i < 8; i++) stage[i] = 0;
+        atomicOr(P.cmask + chunk / G::CHUNKS, 1u << (unsigned)(chunk % G::CHUNKS));
+        dirty = false;
+    };
     StreamSource src{P.words, P.nwords};
-    BitReader<StreamSource> br(src, seg0 + P.seg_over[k]);
-    while (idx < nxt) {
-        if (idx == target) {
-            P.cube_off[target / CS] = br.pos;
-            target += CS;
-            if (target > ncodes || target >= nxt) return;
-        }
+    BitReader<StreamSource> br(src, P.start_bit + k * (unsigned long long)P.seg_bits + P.seg_over[k]);
+    while (cur < hi) {
         br.refill();
         const uint64_t inv = ~br.buf;
         int ones = inv ? clz64(inv) : 64;
         if (ones > br.navail) ones = br.navail;
         if (ones > 0) {
-            const unsigned long long room = target - idx;
+            const unsigned long long room = hi - cur;
             if ((unsigned long long)ones > room) ones = (int)room;
-            idx += ones;
+            const unsigned long long nc = cur + (unsigned)ones;
+            if (dirty && (nc >> 4) != (cur >> 4)) flush(cur >> 4);
+            cur = nc;
             br.skip(ones);
             continue;
         }
         const int z = clz64(br.buf);
-        if (z > 16) return;
-        idx++;
-        br.skip(2 * z + 1);
+        if (z > 16) { atomicOr(P.err, br.pos + (uint64_t)z >= P.nbits_total ? 4u : 2u); return; }
+        const int len = 2 * z + 1;
+        if (cur >= lo) {
+            stage16[cur & 15] = (int16_t)eg_unmap((uint32_t)(br.buf >> (64 - len)));
+            dirty = true;
+        }
+        br.skip(len);
+        cur++;
+        if (dirty && (cur & 15) == 0) flush((cur - 1) >> 4);
+    }
+    if (hi == ncodes) *P.end_bit = br.pos;
+}
+
+// zig-zag chunk scratch -> dense natural-order int16 cubes (dct3d_eg_decode_i16).  Warp per cube.
+template <int C>
+__global__ void __launch_bounds__(kThreads)
+zz_scatter_kernel(const DecParams P)
+{
+    using G = Geo<C>;
+    const int lane = threadIdx.x & 31;
+    const long long wid = (long long)blockIdx.x * kWarps + (threadIdx.x >> 5);
+    const long long nw = (long long)gridDim.x * kWarps;
+    const uint16_t *lin = zz_lin<C>();
+    for (long long cube = wid; cube < P.L.ncubes; cube += nw) {
+        const uint32_t cm = P.cmask[cube];
+        for (int pos = lane; pos < G::CS; pos += 32) {
+            const int16_t v = ((cm >> (pos >> 4)) & 1u) ? P.zzg[(size_t)cube * G::CS + pos] : (int16_t)0;
+            P.qcubes[(size_t)cube * G::CS + lin[pos]] = v;
+        }
     }
 }
 
-struct CubeOut {
-    int16_t *o;
-    __device__ __forceinline__ void put(int idx, int16_t v) { o[idx] = v; }
+// Inverse tail shared by both reconstruct kernels: b[k0][k2] holds the dequantised coefficients of
+// row-frequency k1 = r.  Inverse butterflies along t, exchange, along y and x, clamp to [0,255],
+// truncate (Decoder.java:112, decoder.c:29), store the thread's frame plane.
+template <int C>
+__device__ __forceinline__ void idct_store(float (&b)[C][C], uint8_t *xbuf, int cl, int r, bool valid, const Layout &L,
+                                           long long cube, uint8_t *__restrict__ frames)
+{
+    float a[C][C];
+    inv_t<C, float>(b);
+    Xch<C, float>::transpose(xbuf, cl, r, b, a);   // the exchange is its own inverse
+    inv_yx<C, float>(a);
+    if (!valid) return;
+    const int per_slab = L.by * L.bx;
+    const int slab = (int)(cube / per_slab);
+    const int rem = (int)(cube - (long long)slab * per_slab);
+    const int byi = rem / L.bx, bxi = rem - byi * L.bx;
+    uint8_t *dst = frames + ((size_t)(slab * C + r) * L.H + byi * C) * L.W + bxi * C;
+#pragma unroll
+    for (int y = 0; y < C; y++) {
+        uint32_t w[2] = {0, 0};
+#pragma unroll
+        for (int x = 0; x < C; x++) {
+            // clamp, then add 2^23 rounding toward zero: floor(v) lands in the low mantissa byte
+            const float v = fminf(fmaxf(a[y][x], 0.0f), 255.0f);
+            const uint32_t bits = __float_as_uint(__fadd_rz(v, 8388608.0f)) & 0xffu;
+            w[x / 4] |= bits << ((x & 3) * 8);
+        }
+        if (C == 8) *reinterpret_cast<uint2 *>(dst + (size_t)y * L.W) = make_uint2(w[0], w[1]);
+        else *reinterpret_cast<uint32_t *>(dst + (size_t)y * L.W) = w[0];
+    }
+}
+
+// zig-zag chunk scratch + masks -> u8 frames.  Per warp: zero CPW cube buffers in shared memory,
+// copy in the non-zero chunks (lane <-> chunk), gather each thread's 64 coefficients through the
+// same per-lane run bases the encoder scatters with, dequantise, inverse transform.
+template <int C>
+struct RecSmem {
+    using G = Geo<C>;
+    static constexpr int ZZ_WARP = G::CPW * G::ZZ_STRIDE * 2;     // bytes
+    static constexpr int WARP_BYTES = ZZ_WARP + Xch<C, float>::WARP_BYTES;
+    static constexpr int TOTAL = kWarps * WARP_BYTES;
 };
 
-// One thread per cube: parse 512 (64) codes, scatter the non-zero ones (qcubes pre-zeroed).
 template <int C>
-__global__ void cube_parse_kernel(const DecParams P)
+__global__ void __launch_bounds__(kThreads, 4)
+reconstruct_zz_kernel(const Layout L, const int16_t *__restrict__ zzg, const uint32_t *__restrict__ cmask,
+                      uint8_t *__restrict__ frames)
 {
     using G = Geo<C>;
-    const long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (c >= P.L.ncubes) return;
-    StreamSource src{P.words, P.nwords};
-    CubeOut out{P.qcubes + (size_t)c * G::CS};
-    const unsigned long long start = P.cube_off[c];
-    if (start == ~0ull) { atomicOr(P.err, 4u); return; }   // the stream holds fewer codes than the clip needs
-    const uint64_t end = eg_parse_cube<G::CS>(src, start, zz_lin<C>(), out);
-    if (end == ~0ull) atomicOr(P.err, 2u);
-    else if (end > P.nbits_total) atomicOr(P.err, 4u);
-    else if (c == P.L.ncubes - 1) P.cube_off[P.L.ncubes] = end;
+    using S = RecSmem<C>;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int cl = lane / C, r = lane % C;
+    int16_t *wz = reinterpret_cast<int16_t *>(smem + warp * S::WARP_BYTES);
+    uint8_t *xbuf = smem + warp * S::WARP_BYTES + S::ZZ_WARP;
+    float dq[G::NDIAG];
+    uint32_t zb[G::NDIAG];
+#pragma unroll
+    for (int s = 0; s < G::NDIAG; s++) {
+        dq[s] = (float)quant_divisor(s + r);
+        zb[s] = zz_base<C>(r, s);
+    }
+    const long long ngroups = (L.ncubes + G::CPW - 1) / G::CPW;
+    for (long long g = (long long)blockIdx.x * kWarps + warp; g < ngroups; g += (long long)gridDim.x * kWarps) {
+        // zero the warp's cube buffers
+        constexpr int NV = S::ZZ_WARP / 16;
+        for (int i = lane; i < NV; i += 32) reinterpret_cast<uint4 *>(wz)[i] = make_uint4(0, 0, 0, 0);
+        __syncwarp();
+        // non-zero chunks: lane <-> chunk
+        constexpr int ITER = (G::CPW * G::CHUNKS) / 32;   // 4 (C=8) / 1 (C=4)
+#pragma unroll
+        for (int k = 0; k < ITER; k++) {
+            const int ci = k * 32 + lane;
+            const int c = ci / G::CHUNKS, chunk = ci % G::CHUNKS;
+            const long long gc = g * G::CPW + c;
+            if (gc < L.ncubes && ((__ldg(cmask + gc) >> chunk) & 1u)) {
+                const uint4 *src = reinterpret_cast<const uint4 *>(zzg + (size_t)gc * G::CS + chunk * 16);
+                uint4 *dst = reinterpret_cast<uint4 *>(wz + c * G::ZZ_STRIDE + chunk * 16);
+                const uint4 v0 = __ldg(src), v1 = __ldg(src + 1);
+                dst[0] = v0;
+                dst[1] = v1;
+            }
+        }
+        __syncwarp();
+        const long long cube = g * G::CPW + cl;
+        const int16_t *zz = wz + cl * G::ZZ_STRIDE;
+        float b[C][C];
+#pragma unroll
+        for (int k0 = 0; k0 < C; k0++) {
+#pragma unroll
+            for (int k2 = 0; k2 < C; k2++) {
+                const int s = k0 + k2;
+                const int k0min = s > C - 1 ? s - (C - 1) : 0;
+                b[k0][k2] = (float)(int)zz[zb[s] + (k0 - k0min)] * dq[s];
+            }
+        }
+        __syncwarp();
+        idct_store<C>(b, xbuf, cl, r, cube < L.ncubes, L, cube, frames);
+    }
 }
 
 // int16 natural-order cubes -> u8 frames: dequantise, inverse butterflies, clamp, truncate.
@@ -723,7 +875,7 @@ reconstruct_kernel(const Layout L, const int16_t *__restrict__ qcubes, uint8_t *
     for (long long g = (long long)blockIdx.x * kWarps + warp; g < ngroups; g += (long long)gridDim.x * kWarps) {
         const long long cube = g * G::CPW + cl;
         const bool valid = cube < L.ncubes;
-        float b[C][C], a[C][C];
+        float b[C][C];
         // thread = k1 = r: rows (k0, k1) of the cube, C int16 each
         const int16_t *src = qcubes + (size_t)(valid ? cube : 0) * G::CS + r * C;
 #pragma unroll
@@ -739,30 +891,7 @@ reconstruct_kernel(const Layout L, const int16_t *__restrict__ qcubes, uint8_t *
                 b[k0][k2] = (float)q * dq[k0 + k2];
             }
         }
-        inv_t<C, float>(b);
-        // b[t][k2] (thread = k1) -> a[k1][k2] (thread = t): the exchange is its own inverse
-        Xch<C, float>::transpose(smem + warp * Xch<C, float>::WARP_BYTES, cl, r, b, a);
-        inv_yx<C, float>(a);
-        if (valid) {
-            const int per_slab = L.by * L.bx;
-            const int slab = (int)(cube / per_slab);
-            const int rem = (int)(cube - (long long)slab * per_slab);
-            const int byi = rem / L.bx, bxi = rem - byi * L.bx;
-            uint8_t *dst = frames + ((size_t)(slab * C + r) * L.H + byi * C) * L.W + bxi * C;
-#pragma unroll
-            for (int y = 0; y < C; y++) {
-                uint32_t w[2] = {0, 0};
-#pragma unroll
-                for (int x = 0; x < C; x++) {
-                    // clamp to [0,255], truncate: add 2^23 rounding toward zero, byte lands in the mantissa
-                    const float v = fminf(fmaxf(a[y][x], 0.0f), 255.0f);
-                    const uint32_t bits = __float_as_uint(__fadd_rz(v, 8388608.0f)) & 0xffu;
-                    w[x / 4] |= bits << ((x & 3) * 8);
-                }
-                if (C == 8) *reinterpret_cast<uint2 *>(dst + (size_t)y * L.W) = make_uint2(w[0], w[1]);
-                else *reinterpret_cast<uint32_t *>(dst + (size_t)y * L.W) = w[0];
-            }
-        }
+        idct_store<C>(b, smem + warp * Xch<C, float>::WARP_BYTES, cl, r, valid, L, cube, frames);
     }
 }
 
