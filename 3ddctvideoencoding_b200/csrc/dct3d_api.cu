@@ -548,7 +548,7 @@ static int parse_common(dct3d_ctx *ctx, const void *d_stream, size_t nbytes, uin
     P.nwords = ((unsigned long long)nbytes + 3) / 4;
     P.nbits_total = (unsigned long long)nbytes * 8;
     P.start_bit = start_bit;
-    P.seg_bits = 1024;
+    P.seg_bits = kSegWords * 32;
     P.nseg = (P.nbits_total - start_bit + P.seg_bits - 1) / P.seg_bits;
     // seg arrays: count[nseg] over[nseg+1] used[nseg] (u32) first[nseg+1] (u64)
     const size_t n = (size_t)P.nseg;
@@ -568,7 +568,7 @@ static int parse_common(dct3d_ctx *ctx, const void *d_stream, size_t nbytes, uin
     CU_CHECK(ctx, cudaMemsetAsync(ctx->ctrl.p, 0, sizeof(Ctrl), st));
     CU_CHECK(ctx, cudaMemsetAsync(P.seg_over, 0, (n + 1) * 4, st));
     CU_CHECK(ctx, cudaMemsetAsync(P.cmask, 0, ncubes * 4, st));
-    const unsigned sb = 128, sg = (unsigned)((P.nseg + sb - 1) / sb);
+    const unsigned sb = kSegThreads, sg = (unsigned)((P.nseg + sb - 1) / sb);
     seg_scan_kernel<<<sg, sb, 0, st>>>(P, 1);
     ctx->launches++;
     // fix-up rounds: re-scan segments whose entry overhang differs from the one assumed

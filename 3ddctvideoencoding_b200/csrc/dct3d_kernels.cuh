@@ -348,6 +348,9 @@ encode_kernel(const __grid_constant__ CUtensorMap tmap, const EncParams P)
         mbar_init(&s_bar[1], 1);
         if ((long long)blockIdx.x < L.ntiles) issue_tma(blockIdx.x, 0);
     }
+    // The zig-zag buffer is kept all-zero between tiles: only non-zero coefficients are scattered
+    // into it (97% are zero), and the lanes that find a non-zero chunk wipe it after storing it.
+    for (int i = tid; i < S::ZZ_BYTES / 16; i += kThreads) reinterpret_cast<uint4 *>(s_zz)[i] = make_uint4(0, 0, 0, 0);
 
     int it = 0;
     for (long long tile = blockIdx.x; tile < L.ntiles; tile += gridDim.x, it++) {
@@ -429,7 +432,9 @@ encode_kernel(const __grid_constant__ CUtensorMap tmap, const EncParams P)
             for (int k2 = 0; k2 < C; k2++) {
                 const int s = k0 + k2;
                 const int k0min = s > C - 1 ? s - (C - 1) : 0;
-                zz[zb[s] + (k0 - k0min)] = (int16_t)quantize_f32(bq[k0][k2], rq[s]);
+                // one FFMA quantises (magic rounding); a zero result is exactly the magic constant
+                const int bits = __float_as_int(fmaf(bq[k0][k2], rq[s], DCT_MAGIC));
+                if (bits != 0x4B400000) zz[zb[s] + (k0 - k0min)] = (int16_t)bits;
             }
         }
         __syncwarp();
@@ -440,16 +445,23 @@ encode_kernel(const __grid_constant__ CUtensorMap tmap, const EncParams P)
         for (int k = 0; k < ITER; k++) {
             const int ci = k * 32 + lane;
             const int cube = ci / G::CHUNKS, chunk = ci % G::CHUNKS;
-            const uint4 *q = reinterpret_cast<const uint4 *>(s_zz + (slot0 + cube) * G::ZZ_STRIDE + chunk * 16);
-            const uint4 v0 = q[0], v1 = q[1];
-            const uint32_t any = v0.x | v0.y | v0.z | v0.w | v1.x | v1.y | v1.z | v1.w;
+            uint4 *q = reinterpret_cast<uint4 *>(s_zz + (slot0 + cube) * G::ZZ_STRIDE + chunk * 16);
+            // lanes 4..7 of every 8 read their two 16-byte halves in the other order: the quarter
+            // warp then touches 8 distinct bank groups instead of 4 twice
+            const int hsel = (lane >> 2) & 1;
+            const uint4 va = q[hsel], vb = q[hsel ^ 1];
+            const uint32_t any = va.x | va.y | va.z | va.w | vb.x | vb.y | vb.z | vb.w;
             const bool ok = slot0 + cube < bp.nvalid;
             const uint32_t bal = __ballot_sync(0xffffffffu, any != 0);
             const long long gc = bp.cube0 + slot0 + cube;
-            if (ok && any != 0) {
-                uint4 *dst = reinterpret_cast<uint4 *>(P.zzg + (size_t)gc * G::CS + chunk * 16);
-                dst[0] = v0;
-                dst[1] = v1;
+            if (any != 0) {
+                if (ok) {
+                    uint4 *dst = reinterpret_cast<uint4 *>(P.zzg + (size_t)gc * G::CS + chunk * 16);
+                    dst[hsel] = va;
+                    dst[hsel ^ 1] = vb;
+                }
+                q[0] = make_uint4(0, 0, 0, 0);      // leave the buffer clean for the next tile
+                q[1] = make_uint4(0, 0, 0, 0);
             }
             if (G::CHUNKS == 32) { if (lane == 0 && ok) P.cmask[gc] = bal; }
             else { if (chunk == 0 && ok) P.cmask[gc] = (bal >> (cube * G::CHUNKS)) & ((1u << (G::CHUNKS & 31)) - 1u); }
@@ -568,8 +580,47 @@ eg_pack_kernel(const EncParams P)
 // ------------------------------------------------------------------------------------------
 struct StreamSource {
     const uint32_t *words; unsigned long long nwords;
-    __device__ __forceinline__ uint32_t word(uint64_t i) const { return i < nwords ? bswap32(__ldg(words + i)) : 0u; }
+    __device__ __forceinline__ uint32_t word(uint32_t i) const { return i < nwords ? bswap32(__ldg(words + i)) : 0u; }
 };
+
+// The segment kernels give every thread 1024 consecutive stream bits.  Read word by word from
+// global memory that is 32 different cache lines per warp load (8x over-fetch out of L2), so the
+// CTA first stages its contiguous part of the stream in shared memory with coalesced loads,
+// byte-swapped, one padding word per 32 so that threads 32 words apart hit different banks.
+constexpr int kSegWords = 32;                       // 1024-bit segments
+constexpr int kSegThreads = 128;
+constexpr int kStageN = kSegThreads * kSegWords + 32;   // + margin for codes running past the last segment
+constexpr int kStageSmem = kStageN + kStageN / 32 + 1;
+
+struct StagedSource {
+    const uint32_t *s; unsigned long long w0;
+    const uint32_t *words; unsigned long long nwords;
+    // word j relative to w0; bit positions handed to BitReader are relative to bit 32*w0
+    __device__ __forceinline__ uint32_t word(uint32_t j) const
+    {
+        if (j < (uint32_t)kStageN) return s[j + (j >> 5)];
+        const unsigned long long i = w0 + j;
+        return i < nwords ? bswap32(__ldg(words + i)) : 0u;   // beyond the staged window (rare)
+    }
+    __device__ __forceinline__ uint32_t rel(unsigned long long abs_bit) const
+    {
+        const unsigned long long base = w0 * 32ull;
+        const unsigned long long d = abs_bit > base ? abs_bit - base : 0ull;
+        return d > 0xffffffffull ? 0xffffffffu : (uint32_t)d;
+    }
+};
+
+__device__ __forceinline__ StagedSource stage_stream(uint32_t *s_words, const uint32_t *words, unsigned long long nwords,
+                                                     unsigned long long start_bit, unsigned long long first_seg)
+{
+    const unsigned long long w0 = (start_bit >> 5) + first_seg * kSegWords;
+    for (int j = threadIdx.x; j < kStageN; j += blockDim.x) {
+        const unsigned long long i = w0 + j;
+        s_words[j + (j >> 5)] = i < nwords ? bswap32(__ldg(words + i)) : 0u;
+    }
+    __syncthreads();
+    return StagedSource{s_words, w0, words, nwords};
+}
 
 struct DecParams {
     Layout L;
@@ -591,25 +642,31 @@ struct DecParams {
 };
 
 // Pass 1 / fix-up: every thread scans one segment from its current entry overhang.
-__global__ void seg_scan_kernel(const DecParams P, int first_pass)
+// In the fix-up rounds a CTA whose segments all kept their entry point exits before staging.
+__global__ void __launch_bounds__(kSegThreads)
+seg_scan_kernel(const DecParams P, int first_pass)
 {
-    const unsigned long long k = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
-    if (k >= P.nseg) return;
-    const unsigned int entry = first_pass ? (k == 0 ? 0u : 0u) : P.seg_over[k];
-    if (!first_pass && entry == P.seg_used[k]) return;
-    const unsigned long long seg0 = P.start_bit + k * (unsigned long long)P.seg_bits;
-    unsigned long long lim = seg0 + P.seg_bits;
-    if (lim > P.nbits_total) lim = P.nbits_total;
-    StreamSource src{P.words, P.nwords};
-    uint32_t n = 0; uint64_t next = 0;
+    __shared__ uint32_t s_words[kStageSmem];
+    const unsigned long long k = blockIdx.x * (unsigned long long)kSegThreads + threadIdx.x;
+    const bool in_range = k < P.nseg;
+    const unsigned int entry = (first_pass || !in_range) ? 0u : P.seg_over[k];
+    const bool work = in_range && (first_pass || entry != P.seg_used[k]);
+    if (!__syncthreads_or(work)) return;
+    const StagedSource src = stage_stream(s_words, P.words, P.nwords, P.start_bit, blockIdx.x * (unsigned long long)kSegThreads);
+    if (!work) return;
+    const uint32_t seg0 = src.rel(P.start_bit + k * (unsigned long long)P.seg_bits);
+    const uint32_t eos = src.rel(P.nbits_total);
+    uint32_t lim = seg0 + P.seg_bits;
+    if (lim > eos) lim = eos;
+    uint32_t n = 0, next = 0;
     // A scan from a wrongly assumed entry point may run into an impossible code; that is only an
     // error if it is still there once the entry points have converged, so it is recorded per segment.
     unsigned int bad = 0;
     if (seg0 + entry >= lim) { n = 0; next = seg0 + entry; }
-    else if (!eg_scan_segment(src, seg0 + entry, lim, P.nbits_total, n, next)) { bad = 0x80000000u; n = 0; next = lim; }
+    else if (!eg_scan_segment(src, seg0 + entry, lim, eos, n, next)) { bad = 0x80000000u; n = 0; next = lim; }
     P.seg_count[k] = n | bad;
     P.seg_used[k] = entry;
-    const unsigned int over = (unsigned int)(next > lim ? next - lim : 0);
+    const unsigned int over = next > lim ? next - lim : 0u;
     if (first_pass || P.seg_over[k + 1] != over) { P.seg_over[k + 1] = over; if (!first_pass) *P.changed = 1u; }
 }
 
@@ -675,7 +732,7 @@ seg_prefix_kernel(const DecParams P, unsigned long long *tile_status, unsigned i
 // 15 leading codes (owned by its predecessor) and runs up to 15 codes past its segment.  Chunks are
 // assembled in a per-thread shared-memory slot and stored whole (32 B); cmask (zeroed beforehand)
 // collects the non-zero chunks of every cube.
-constexpr int kParseThreads = 128;
+constexpr int kParseThreads = kSegThreads;
 constexpr int kStageWords = 10;   // 40-byte stride: 32 B of data + padding against bank conflicts
 
 template <int C>
@@ -684,7 +741,9 @@ seg_parse_kernel(const DecParams P)
 {
     using G = Geo<C>;
     __shared__ __align__(8) uint32_t s_stage[kParseThreads * kStageWords];
+    __shared__ uint32_t s_words[kStageSmem];
     const unsigned long long k = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    const StagedSource src = stage_stream(s_words, P.words, P.nwords, P.start_bit, blockIdx.x * (unsigned long long)kParseThreads);
     if (k >= P.nseg) return;
     const unsigned long long ncodes = (unsigned long long)P.L.ncubes * G::CS;
     unsigned long long cur = P.seg_first[k];
@@ -708,13 +767,10 @@ seg_parse_kernel(const DecParams P)
         atomicOr(P.cmask + chunk / G::CHUNKS, 1u << (unsigned)(chunk % G::CHUNKS));
         dirty = false;
     };
-    StreamSource src{P.words, P.nwords};
-    BitReader<StreamSource> br(src, P.start_bit + k * (unsigned long long)P.seg_bits + P.seg_over[k]);
+    BitReader<StagedSource> br(src, src.rel(P.start_bit + k * (unsigned long long)P.seg_bits) + P.seg_over[k]);
     while (cur < hi) {
         br.refill();
-        const uint64_t inv = ~br.buf;
-        int ones = inv ? clz64(inv) : 64;
-        if (ones > br.navail) ones = br.navail;
+        int ones = clz32(~br.hi);
         if (ones > 0) {
             const unsigned long long room = hi - cur;
             if ((unsigned long long)ones > room) ones = (int)room;
@@ -724,18 +780,17 @@ seg_parse_kernel(const DecParams P)
             br.skip(ones);
             continue;
         }
-        const int z = clz64(br.buf);
-        if (z > 16) { atomicOr(P.err, br.pos + (uint64_t)z >= P.nbits_total ? 4u : 2u); return; }
-        const int len = 2 * z + 1;
+        uint32_t m;
+        const uint32_t at = br.pos;
+        if (!br.take_code(m)) { atomicOr(P.err, at + 17u >= src.rel(P.nbits_total) ? 4u : 2u); return; }
         if (cur >= lo) {
-            stage16[cur & 15] = (int16_t)eg_unmap((uint32_t)(br.buf >> (64 - len)));
+            stage16[cur & 15] = (int16_t)eg_unmap(m);
             dirty = true;
         }
-        br.skip(len);
         cur++;
         if (dirty && (cur & 15) == 0) flush((cur - 1) >> 4);
     }
-    if (hi == ncodes) *P.end_bit = br.pos;
+    if (hi == ncodes) *P.end_bit = src.w0 * 32ull + br.pos;
 }
 
 // zig-zag chunk scratch -> dense natural-order int16 cubes (dct3d_eg_decode_i16).  Warp per cube.
@@ -812,27 +867,31 @@ reconstruct_zz_kernel(const Layout L, const int16_t *__restrict__ zzg, const uin
     const int cl = lane / C, r = lane % C;
     int16_t *wz = reinterpret_cast<int16_t *>(smem + warp * S::WARP_BYTES);
     uint8_t *xbuf = smem + warp * S::WARP_BYTES + S::ZZ_WARP;
-    float dq[G::NDIAG];
-    uint32_t zb[G::NDIAG];
+    // per-lane run bases and, per diagonal, the mask of the (at most two) chunks the run lies in
+    uint32_t zb[G::NDIAG], rm[G::NDIAG];
 #pragma unroll
     for (int s = 0; s < G::NDIAG; s++) {
-        dq[s] = (float)quant_divisor(s + r);
         zb[s] = zz_base<C>(r, s);
+        const int len = s < C ? s + 1 : 2 * C - 1 - s;
+        rm[s] = (1u << (zb[s] >> 4)) | (1u << ((zb[s] + len - 1) >> 4));
     }
+    const float r5 = 5.0f * (float)r;
+    // the warp's cube buffers stay all-zero between groups: lanes wipe the chunks they copied in
+    constexpr int NV = S::ZZ_WARP / 16;
+    for (int i = lane; i < NV; i += 32) reinterpret_cast<uint4 *>(wz)[i] = make_uint4(0, 0, 0, 0);
+    __syncwarp();
     const long long ngroups = (L.ncubes + G::CPW - 1) / G::CPW;
     for (long long g = (long long)blockIdx.x * kWarps + warp; g < ngroups; g += (long long)gridDim.x * kWarps) {
-        // zero the warp's cube buffers
-        constexpr int NV = S::ZZ_WARP / 16;
-        for (int i = lane; i < NV; i += 32) reinterpret_cast<uint4 *>(wz)[i] = make_uint4(0, 0, 0, 0);
-        __syncwarp();
         // non-zero chunks: lane <-> chunk
         constexpr int ITER = (G::CPW * G::CHUNKS) / 32;   // 4 (C=8) / 1 (C=4)
+        bool mine[ITER];
 #pragma unroll
         for (int k = 0; k < ITER; k++) {
             const int ci = k * 32 + lane;
             const int c = ci / G::CHUNKS, chunk = ci % G::CHUNKS;
             const long long gc = g * G::CPW + c;
-            if (gc < L.ncubes && ((__ldg(cmask + gc) >> chunk) & 1u)) {
+            mine[k] = gc < L.ncubes && ((__ldg(cmask + gc) >> chunk) & 1u);
+            if (mine[k]) {
                 const uint4 *src = reinterpret_cast<const uint4 *>(zzg + (size_t)gc * G::CS + chunk * 16);
                 uint4 *dst = reinterpret_cast<uint4 *>(wz + c * G::ZZ_STRIDE + chunk * 16);
                 const uint4 v0 = __ldg(src), v1 = __ldg(src + 1);
@@ -842,6 +901,7 @@ reconstruct_zz_kernel(const Layout L, const int16_t *__restrict__ zzg, const uin
         }
         __syncwarp();
         const long long cube = g * G::CPW + cl;
+        const uint32_t cm = cube < L.ncubes ? __ldg(cmask + cube) : 0u;
         const int16_t *zz = wz + cl * G::ZZ_STRIDE;
         float b[C][C];
 #pragma unroll
@@ -850,7 +910,20 @@ reconstruct_zz_kernel(const Layout L, const int16_t *__restrict__ zzg, const uin
             for (int k2 = 0; k2 < C; k2++) {
                 const int s = k0 + k2;
                 const int k0min = s > C - 1 ? s - (C - 1) : 0;
-                b[k0][k2] = (float)(int)zz[zb[s] + (k0 - k0min)] * dq[s];
+                // only runs that touch a non-zero chunk are read (everything else is zero)
+                float v = 0.0f;
+                if (cm & rm[s]) v = (float)(int)zz[zb[s] + (k0 - k0min)] * fmaxf(1.0f, r5 + 5.0f * (float)s);
+                b[k0][k2] = v;
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < ITER; k++) {
+            if (mine[k]) {
+                const int ci = k * 32 + lane;
+                uint4 *dst = reinterpret_cast<uint4 *>(wz + (ci / G::CHUNKS) * G::ZZ_STRIDE + (ci % G::CHUNKS) * 16);
+                dst[0] = make_uint4(0, 0, 0, 0);
+                dst[1] = make_uint4(0, 0, 0, 0);
             }
         }
         __syncwarp();

@@ -54,6 +54,32 @@ EG_HD uint32_t bswap32(uint32_t x)
 #endif
 }
 
+// 32-bit funnel helpers (shift counts 0..32, clamped): one SHF each on the device.
+EG_HD uint32_t fsl(uint32_t hi, uint32_t lo, int n)      // high word of (hi:lo) << n
+{
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_lc(lo, hi, n);
+#else
+    return n <= 0 ? hi : n >= 32 ? lo : (hi << n) | (lo >> (32 - n));
+#endif
+}
+EG_HD uint32_t shl32c(uint32_t x, int n)                 // x << n, 0 when n == 32
+{
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_lc(0u, x, n);
+#else
+    return n >= 32 ? 0u : x << n;
+#endif
+}
+EG_HD uint32_t shr32c(uint32_t x, int n)                 // x >> n, 0 when n == 32
+{
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_rc(x, 0u, n);
+#else
+    return n >= 32 ? 0u : x >> n;
+#endif
+}
+
 // 16-byte vector: one LDS.128 / LDG.128 on the device.
 struct alignas(16) Vec16 { uint32_t x, y, z, w; };
 // the 16 int16 coefficients of chunk c of a zig-zag cube (32-byte aligned rows of 16 B)
@@ -116,39 +142,47 @@ EG_HD uint32_t eg_count_cube(const int16_t *zz, uint32_t chunkmask)
 template <typename Sink>
 struct BitWriter {
     Sink &sink;
-    uint64_t acc;   // pending bits, left-aligned
+    uint32_t acc;   // pending bits, left-aligned
     int nacc;       // number of pending bits (< 32 between calls)
-    uint64_t widx;  // index of the word the pending bits start in
+    uint64_t widx;  // index of the word the pending bits belong to
     bool first;
 
     EG_HD BitWriter(Sink &s, uint64_t start_bit) : sink(s), acc(0), nacc((int)(start_bit & 31)), widx(start_bit >> 5), first(true) {}
 
-    // append the low `len` bits of m (1 <= len <= 33, nacc + len <= 64)
-    EG_HD void put(uint64_t m, int len)
+    // append the low `len` bits of m, 1 <= len <= 32
+    EG_HD void put(uint32_t m, int len)
     {
-        acc |= m << (64 - nacc - len);
+        const uint32_t ml = m << (32 - len);
+        acc |= ml >> nacc;
+        const uint32_t spill = shl32c(ml, 32 - nacc);   // bits that do not fit the current word
         nacc += len;
-        while (nacc >= 32) {  // at most twice (31 pending + a 33-bit code)
-            sink.put(widx, bswap32((uint32_t)(acc >> 32)), first);
+        if (nacc >= 32) {
+            sink.put(widx, bswap32(acc), first);
             first = false;
             widx++;
-            acc <<= 32;
+            acc = spill;
             nacc -= 32;
         }
     }
     EG_HD void put_code(int v)
     {
         const uint32_t m = eg_map(v);
-        put(m, 2 * (32 - clz32(m)) - 1);
+        const int L = 32 - clz32(m);
+        if (L <= 16) {
+            put(m, 2 * L - 1);
+        } else {              // 33-bit code (v = -32768): 16 zeros, then m in 17 bits
+            put(0u, 16);
+            put(m, 17);
+        }
     }
     EG_HD void put_ones(int k)
     {
-        while (k >= 32) { put(0xffffffffull, 32); k -= 32; }
-        if (k > 0) put((1ull << k) - 1, k);
+        while (k >= 32) { put(0xffffffffu, 32); k -= 32; }
+        if (k > 0) put(0xffffffffu >> (32 - k), k);
     }
     EG_HD void flush()
     {
-        if (nacc > 0) sink.put(widx, bswap32((uint32_t)(acc >> 32)), true);
+        if (nacc > 0) sink.put(widx, bswap32(acc), true);
     }
 };
 
@@ -175,95 +209,112 @@ EG_HD void eg_write_cube(const int16_t *zz, uint32_t chunkmask, uint64_t start_b
 }
 
 // ---------------------------------------------------------------------------------------
-// Reading.  Source is a policy with  uint32_t word(uint64_t word_index)  returning the
-// byte-swapped (numeric MSB-first) word, zero past the end of the stream.
+// Reading.  Source is a policy with  uint32_t word(uint32_t j)  returning word j (relative to the
+// source's own base) byte-swapped to numeric MSB-first order, zero past the end of the stream.
+// Positions are 32-bit bit offsets relative to that base.
 // ---------------------------------------------------------------------------------------
 template <typename Source>
 struct BitReader {
     const Source &src;
-    uint64_t buf;    // next bits, left-aligned
-    int navail;      // valid bits in buf
-    uint64_t wnext;  // next word to load
-    uint64_t pos;    // absolute position of the first bit in buf
+    uint32_t hi, lo;  // next bits, left-aligned in hi:lo
+    int navail;       // valid bits in hi:lo (>= 33 after refill)
+    uint32_t wnext;   // next word to load
+    uint32_t pos;     // position of the first bit in hi
 
-    EG_HD BitReader(const Source &s, uint64_t start_bit) : src(s), pos(start_bit)
+    EG_HD BitReader(const Source &s, uint32_t start_bit) : src(s), pos(start_bit)
     {
         wnext = start_bit >> 5;
         const int sh = (int)(start_bit & 31);
-        buf = (uint64_t)src.word(wnext++) << 32;
-        buf |= (uint64_t)src.word(wnext++);
-        buf <<= sh;
+        const uint32_t w0 = src.word(wnext++), w1 = src.word(wnext++);
+        hi = fsl(w0, w1, sh);
+        lo = w1 << sh;
         navail = 64 - sh;
     }
     EG_HD void refill()
     {
-        if (navail <= 32) {
-            buf |= (uint64_t)src.word(wnext++) << (32 - navail);
+        while (navail <= 32) {            // lo is empty here
+            const uint32_t w = src.word(wnext++);
+            hi |= shr32c(w, navail);
+            lo = shl32c(w, 32 - navail);
             navail += 32;
         }
     }
-    EG_HD void skip(int n) { buf = n >= 64 ? 0ull : buf << n; navail -= n; pos += (uint64_t)n; }
+    EG_HD void skip(int n)                // 0 <= n <= 32
+    {
+        hi = fsl(hi, lo, n);
+        lo = shl32c(lo, n);
+        navail -= n;
+        pos += (uint32_t)n;
+    }
+    // Decode the code at the head (its first bit is 0).  Returns false for more than 16 leading zeros.
+    EG_HD bool take_code(uint32_t &m)
+    {
+        const int z = clz32(hi);
+        if (z > 16) return false;
+        if (z < 16) {
+            const int len = 2 * z + 1;
+            m = hi >> (32 - len);
+            skip(len);
+        } else {                          // 33 bits: 16 zeros, a one, 16 more bits
+            m = (hi << 1) | (lo >> 31);
+            skip(32);
+            skip(1);
+        }
+        return true;
+    }
 };
 
-// Decode one cube (CS codes) starting at absolute bit `start`, scattering non-zero values to
-// out[izz[i]] (out must be zero-filled).  Returns the end bit, or ~0 for a malformed code
+// Decode one cube (CS codes) starting at bit `start`, scattering non-zero values to
+// out[izz[i]] (out must be zero-filled).  Returns the end bit, or ~0u for a malformed code
 // (more than 16 leading zeros: the value would not fit the codec's int16 range).
 template <int CS, typename Source, typename Out>
-EG_HD uint64_t eg_parse_cube(const Source &src, uint64_t start, const uint16_t *izz, Out &out)
+EG_HD uint32_t eg_parse_cube(const Source &src, uint32_t start, const uint16_t *izz, Out &out)
 {
     BitReader<Source> br(src, start);
     int i = 0;
     while (i < CS) {
         br.refill();
-        const uint64_t inv = ~br.buf;
-        int ones = inv ? clz64(inv) : 64;
-        if (ones > br.navail) ones = br.navail;
+        int ones = clz32(~br.hi);
         if (ones > 0) {
             if (ones > CS - i) ones = CS - i;
             i += ones;
             br.skip(ones);
             continue;
         }
-        const int z = clz64(br.buf);  // leading bit is 0 here, so z >= 1
-        if (z > 16) return ~0ull;
-        const int len = 2 * z + 1;    // <= 33 <= navail
-        const uint32_t m = (uint32_t)(br.buf >> (64 - len));
+        uint32_t m;
+        if (!br.take_code(m)) return ~0u;
         out.put(izz[i], (int16_t)eg_unmap(m));
         i++;
-        br.skip(len);
     }
     return br.pos;
 }
 
 // Count the codes that START in [start, limit) and report where the first code at or after
-// `limit` starts (stream segments for index discovery).  Stops early at `maxcodes`.
-// Returns false on a malformed code.
+// `limit` starts (stream segments for index discovery).  Returns false on a malformed code
+// (zero padding after the last code of the stream is not an error).
 template <typename Source>
-EG_HD bool eg_scan_segment(const Source &src, uint64_t start, uint64_t limit, uint64_t end_of_stream,
-                           uint32_t &ncodes, uint64_t &next_start)
+EG_HD bool eg_scan_segment(const Source &src, uint32_t start, uint32_t limit, uint32_t end_of_stream,
+                           uint32_t &ncodes, uint32_t &next_start)
 {
     BitReader<Source> br(src, start);
     uint32_t n = 0;
     while (br.pos < limit) {
         br.refill();
-        const uint64_t inv = ~br.buf;
-        int ones = inv ? clz64(inv) : 64;
-        if (ones > br.navail) ones = br.navail;
+        int ones = clz32(~br.hi);
         if (ones > 0) {
-            const uint64_t room = limit - br.pos;
-            if ((uint64_t)ones > room) ones = (int)room;
+            const uint32_t room = limit - br.pos;
+            if ((uint32_t)ones > room) ones = (int)room;
             n += (uint32_t)ones;
             br.skip(ones);
             continue;
         }
-        const int z = clz64(br.buf);
-        if (z > 16) {
-            // zero padding after the last code of the stream is not an error
-            if (br.pos + (uint64_t)z >= end_of_stream) { br.pos = limit > br.pos ? limit : br.pos; break; }
+        uint32_t m;
+        const uint32_t at = br.pos;
+        if (!br.take_code(m)) {
+            if (at + 17 >= end_of_stream || clz32(br.hi) + at >= end_of_stream) { br.pos = limit > at ? limit : at; break; }
             return false;
         }
         n++;
-        br.skip(2 * z + 1);
     }
     ncodes = n;
     next_start = br.pos;

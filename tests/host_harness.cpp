@@ -47,7 +47,7 @@ struct VecSink {
 };
 struct VecSource {
     const uint32_t *w; uint64_t n;
-    uint32_t word(uint64_t i) const { return i < n ? bswap32(w[i]) : 0u; }
+    uint32_t word(uint32_t i) const { return i < n ? bswap32(w[i]) : 0u; }
 };
 struct ArrOut { int16_t *o; void put(int idx, int16_t v) { o[idx] = v; } };
 
@@ -85,11 +85,11 @@ uint64_t hh_eg_parse(const uint8_t *buf, size_t nbytes, uint64_t start, int ncub
     std::vector<uint32_t> words((nbytes + 3) / 4 + 1, 0);
     memcpy(words.data(), buf, nbytes);
     VecSource src{words.data(), (uint64_t)words.size()};
-    uint64_t pos = start;
+    uint32_t pos = (uint32_t)start;
     for (int c = 0; c < ncubes; c++) {
         ArrOut o{out + (size_t)c * cs};
         pos = cs == 512 ? eg_parse_cube<512>(src, pos, izz, o) : eg_parse_cube<64>(src, pos, izz, o);
-        if (pos == ~0ull) return pos;
+        if (pos == ~0u) return ~0ull;
     }
     return pos;
 }
@@ -99,6 +99,9 @@ int hh_eg_scan(const uint8_t *buf, size_t nbytes, uint64_t start, uint64_t limit
     std::vector<uint32_t> words((nbytes + 3) / 4 + 1, 0);
     memcpy(words.data(), buf, nbytes);
     VecSource src{words.data(), (uint64_t)words.size()};
-    return eg_scan_segment(src, start, limit, (uint64_t)nbytes * 8, *ncodes, *next) ? 0 : -1;
+    uint32_t nx = 0;
+    const bool ok = eg_scan_segment(src, (uint32_t)start, (uint32_t)limit, (uint32_t)(nbytes * 8), *ncodes, nx);
+    *next = nx;
+    return ok ? 0 : -1;
 }
 }
