@@ -39,7 +39,7 @@ struct Ctrl {               // small device control block, zeroed before every l
     unsigned int ticket;
     unsigned int err;
     unsigned int changed;
-    unsigned int pad;
+    unsigned int nwork;
     unsigned long long end_bit;
 };
 
@@ -550,9 +550,9 @@ static int parse_common(dct3d_ctx *ctx, const void *d_stream, size_t nbytes, uin
     P.start_bit = start_bit;
     P.seg_bits = kSegWords * 32;
     P.nseg = (P.nbits_total - start_bit + P.seg_bits - 1) / P.seg_bits;
-    // seg arrays: count[nseg] over[nseg+1] used[nseg] (u32) first[nseg+1] (u64)
+    // seg arrays: count[nseg] over[nseg+1] used[nseg] work[nseg] (u32) first[nseg+1] (u64)
     const size_t n = (size_t)P.nseg;
-    const size_t off_first = ((3 * n + 1) * 4 + 7) & ~(size_t)7;
+    const size_t off_first = ((4 * n + 1) * 4 + 7) & ~(size_t)7;
     CU_CHECK(ctx, ctx->seg.reserve(off_first + (n + 1) * 8));
     CU_CHECK(ctx, ctx->ctrl.reserve(sizeof(Ctrl)));
     CU_CHECK(ctx, ctx->zz.reserve(ncubes * CS * sizeof(int16_t)));
@@ -560,22 +560,24 @@ static int parse_common(dct3d_ctx *ctx, const void *d_stream, size_t nbytes, uin
     P.seg_count = (unsigned int *)ctx->seg.p;
     P.seg_over = P.seg_count + n;
     P.seg_used = P.seg_over + n + 1;
+    P.seg_work = P.seg_used + n;
     P.seg_first = (unsigned long long *)((uint8_t *)ctx->seg.p + off_first);
     Ctrl *dc = (Ctrl *)ctx->ctrl.p;
-    P.changed = &dc->changed; P.err = &dc->err; P.end_bit = &dc->end_bit;
+    P.changed = &dc->changed; P.err = &dc->err; P.end_bit = &dc->end_bit; P.nwork = &dc->nwork;
     P.zzg = (int16_t *)ctx->zz.p;
     P.cmask = (uint32_t *)ctx->cmask.p;
     CU_CHECK(ctx, cudaMemsetAsync(ctx->ctrl.p, 0, sizeof(Ctrl), st));
-    CU_CHECK(ctx, cudaMemsetAsync(P.seg_over, 0, (n + 1) * 4, st));
+    CU_CHECK(ctx, cudaMemsetAsync(P.seg_over, 0, 4, st));
     CU_CHECK(ctx, cudaMemsetAsync(P.cmask, 0, ncubes * 4, st));
     const unsigned sb = kSegThreads, sg = (unsigned)((P.nseg + sb - 1) / sb);
-    seg_scan_kernel<<<sg, sb, 0, st>>>(P, 1);
+    seg_scan_kernel<<<sg, sb, 0, st>>>(P);
     ctx->launches++;
-    // fix-up rounds: re-scan segments whose entry overhang differs from the one assumed
+    // fix-up rounds: re-scan only the segments whose entry overhang differs from the one assumed
     for (unsigned long long round = 0; round <= P.nseg; round++) {
-        CU_CHECK(ctx, cudaMemsetAsync(&dc->changed, 0, 4, st));
-        seg_scan_kernel<<<sg, sb, 0, st>>>(P, 0);
-        ctx->launches++;
+        CU_CHECK(ctx, cudaMemsetAsync(&dc->changed, 0, 8, st));   // changed + nwork
+        seg_check_kernel<<<(unsigned)((P.nseg + 255) / 256), 256, 0, st>>>(P);
+        seg_fix_kernel<<<(unsigned)std::min<unsigned long long>((P.nseg + 127) / 128, (unsigned long long)ctx->num_sms * 16), 128, 0, st>>>(P);
+        ctx->launches += 2;
         if ((rc = fetch_ctrl(ctx, st))) return rc;
         if (!ctx->h_ctrl->changed) break;
     }

@@ -578,11 +578,6 @@ eg_pack_kernel(const EncParams P)
 // ------------------------------------------------------------------------------------------
 // Decode side
 // ------------------------------------------------------------------------------------------
-struct StreamSource {
-    const uint32_t *words; unsigned long long nwords;
-    __device__ __forceinline__ uint32_t word(uint32_t i) const { return i < nwords ? bswap32(__ldg(words + i)) : 0u; }
-};
-
 // The segment kernels give every thread 1024 consecutive stream bits.  Read word by word from
 // global memory that is 32 different cache lines per warp load (8x over-fetch out of L2), so the
 // CTA first stages its contiguous part of the stream in shared memory with coalesced loads,
@@ -592,21 +587,36 @@ constexpr int kSegThreads = 128;
 constexpr int kStageN = kSegThreads * kSegWords + 32;   // + margin for codes running past the last segment
 constexpr int kStageSmem = kStageN + kStageN / 32 + 1;
 
-struct StagedSource {
-    const uint32_t *s; unsigned long long w0;
-    const uint32_t *words; unsigned long long nwords;
-    // word j relative to w0; bit positions handed to BitReader are relative to bit 32*w0
-    __device__ __forceinline__ uint32_t word(uint32_t j) const
-    {
-        if (j < (uint32_t)kStageN) return s[j + (j >> 5)];
-        const unsigned long long i = w0 + j;
-        return i < nwords ? bswap32(__ldg(words + i)) : 0u;   // beyond the staged window (rare)
-    }
+// Relative addressing shared by both word sources: word j / bit positions are relative to word w0.
+struct WordBase {
+    unsigned long long w0;
     __device__ __forceinline__ uint32_t rel(unsigned long long abs_bit) const
     {
         const unsigned long long base = w0 * 32ull;
         const unsigned long long d = abs_bit > base ? abs_bit - base : 0ull;
         return d > 0xffffffffull ? 0xffffffffu : (uint32_t)d;
+    }
+};
+
+// The CTA's staged window.  A thread reads at most its own 32 words, a 33-bit entry overhang, 15
+// more codes (seg_parse_kernel) and the reader's two-word look-ahead: always inside the window's
+// 32-word margin.  The index is clamped so that even a corrupt stream cannot read outside it.
+struct StagedSource : WordBase {
+    const uint32_t *s;
+    __device__ __forceinline__ uint32_t word(uint32_t j) const
+    {
+        j = min(j, (uint32_t)kStageN - 1u);
+        return s[j + (j >> 5)];
+    }
+};
+
+// Plain global reads (fix-up kernel: scattered segments).
+struct GlobalSource : WordBase {
+    const uint32_t *words; unsigned long long nwords;
+    __device__ __forceinline__ uint32_t word(uint32_t j) const
+    {
+        const unsigned long long i = w0 + j;
+        return i < nwords ? bswap32(__ldg(words + i)) : 0u;
     }
 };
 
@@ -619,7 +629,10 @@ __device__ __forceinline__ StagedSource stage_stream(uint32_t *s_words, const ui
         s_words[j + (j >> 5)] = i < nwords ? bswap32(__ldg(words + i)) : 0u;
     }
     __syncthreads();
-    return StagedSource{s_words, w0, words, nwords};
+    StagedSource src;
+    src.w0 = w0;
+    src.s = s_words;
+    return src;
 }
 
 struct DecParams {
@@ -631,6 +644,8 @@ struct DecParams {
     unsigned int *seg_count;            // [nseg] codes starting in the segment
     unsigned int *seg_over;             // [nseg+1] overhang INTO segment k (seg_over[0] = 0)
     unsigned int *seg_used;             // [nseg] entry overhang used for the current count
+    unsigned int *seg_work;             // [nseg] worklist of segments to re-scan
+    unsigned int *nwork;
     unsigned long long *seg_first;      // [nseg+1] exclusive prefix of seg_count
     unsigned int *changed;              // fix-up flag
     unsigned int *err;                  // bit1 = malformed, bit2 = truncated
@@ -641,19 +656,15 @@ struct DecParams {
     uint8_t *frames;
 };
 
-// Pass 1 / fix-up: every thread scans one segment from its current entry overhang.
-// In the fix-up rounds a CTA whose segments all kept their entry point exits before staging.
+// Pass 1: every thread scans one segment assuming that a code starts at its first bit, and
+// records how far its last code runs into the next segment (seg_over[k+1]).
 __global__ void __launch_bounds__(kSegThreads)
-seg_scan_kernel(const DecParams P, int first_pass)
+seg_scan_kernel(const DecParams P)
 {
     __shared__ uint32_t s_words[kStageSmem];
     const unsigned long long k = blockIdx.x * (unsigned long long)kSegThreads + threadIdx.x;
-    const bool in_range = k < P.nseg;
-    const unsigned int entry = (first_pass || !in_range) ? 0u : P.seg_over[k];
-    const bool work = in_range && (first_pass || entry != P.seg_used[k]);
-    if (!__syncthreads_or(work)) return;
     const StagedSource src = stage_stream(s_words, P.words, P.nwords, P.start_bit, blockIdx.x * (unsigned long long)kSegThreads);
-    if (!work) return;
+    if (k >= P.nseg) return;
     const uint32_t seg0 = src.rel(P.start_bit + k * (unsigned long long)P.seg_bits);
     const uint32_t eos = src.rel(P.nbits_total);
     uint32_t lim = seg0 + P.seg_bits;
@@ -662,12 +673,45 @@ seg_scan_kernel(const DecParams P, int first_pass)
     // A scan from a wrongly assumed entry point may run into an impossible code; that is only an
     // error if it is still there once the entry points have converged, so it is recorded per segment.
     unsigned int bad = 0;
-    if (seg0 + entry >= lim) { n = 0; next = seg0 + entry; }
-    else if (!eg_scan_segment(src, seg0 + entry, lim, eos, n, next)) { bad = 0x80000000u; n = 0; next = lim; }
+    if (seg0 >= lim) { n = 0; next = seg0; }
+    else if (!eg_scan_segment(src, seg0, lim, eos, n, next)) { bad = 0x80000000u; n = 0; next = lim; }
     P.seg_count[k] = n | bad;
-    P.seg_used[k] = entry;
-    const unsigned int over = next > lim ? next - lim : 0u;
-    if (first_pass || P.seg_over[k + 1] != over) { P.seg_over[k + 1] = over; if (!first_pass) *P.changed = 1u; }
+    P.seg_used[k] = 0u;
+    P.seg_over[k + 1] = next > lim ? next - lim : 0u;
+}
+
+// Fix-up rounds: list the segments whose true entry point (the predecessor's overhang) differs from
+// the one they were scanned with, then re-scan only those (about one in seven on the first round,
+// almost none afterwards), until nothing changes.
+__global__ void seg_check_kernel(const DecParams P)
+{
+    const unsigned long long k = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    if (k >= P.nseg) return;
+    if (P.seg_over[k] != P.seg_used[k]) P.seg_work[atomicAdd(P.nwork, 1u)] = (unsigned int)k;
+}
+
+__global__ void seg_fix_kernel(const DecParams P)
+{
+    const unsigned int nwork = *P.nwork;
+    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < nwork; i += gridDim.x * blockDim.x) {
+        const unsigned long long k = P.seg_work[i];
+        const unsigned long long w0 = (P.start_bit >> 5) + k * kSegWords;
+        GlobalSource src;                                      // scattered segments: plain global reads
+        src.w0 = w0; src.words = P.words; src.nwords = P.nwords;
+        const unsigned int entry = P.seg_over[k];
+        const uint32_t seg0 = src.rel(P.start_bit + k * (unsigned long long)P.seg_bits);
+        const uint32_t eos = src.rel(P.nbits_total);
+        uint32_t lim = seg0 + P.seg_bits;
+        if (lim > eos) lim = eos;
+        uint32_t n = 0, next = 0;
+        unsigned int bad = 0;
+        if (seg0 + entry >= lim) { n = 0; next = seg0 + entry; }
+        else if (!eg_scan_segment(src, seg0 + entry, lim, eos, n, next)) { bad = 0x80000000u; n = 0; next = lim; }
+        P.seg_count[k] = n | bad;
+        P.seg_used[k] = entry;
+        const unsigned int over = next > lim ? next - lim : 0u;
+        if (P.seg_over[k + 1] != over) { P.seg_over[k + 1] = over; *P.changed = 1u; }
+    }
 }
 
 // Exclusive prefix sum of seg_count over all segments: 1024 segments per CTA tile, block scan,
@@ -769,17 +813,18 @@ seg_parse_kernel(const DecParams P)
     };
     BitReader<StagedSource> br(src, src.rel(P.start_bit + k * (unsigned long long)P.seg_bits) + P.seg_over[k]);
     while (cur < hi) {
+        // one iteration = a run of one-bits (zero coefficients) followed by one longer code
         br.refill();
-        int ones = clz32(~br.hi);
-        if (ones > 0) {
-            const unsigned long long room = hi - cur;
-            if ((unsigned long long)ones > room) ones = (int)room;
-            const unsigned long long nc = cur + (unsigned)ones;
-            if (dirty && (nc >> 4) != (cur >> 4)) flush(cur >> 4);
-            cur = nc;
-            br.skip(ones);
-            continue;
-        }
+        unsigned long long ones = (unsigned)clz32(~br.hi);
+        const unsigned long long room = hi - cur;
+        if (ones > room) ones = room;
+        const unsigned long long nc = cur + ones;
+        if (dirty && (nc >> 4) != (cur >> 4)) flush(cur >> 4);
+        cur = nc;
+        br.skip((int)ones);
+        if (cur >= hi) break;
+        br.refill();
+        if (br.hi >> 31) continue;
         uint32_t m;
         const uint32_t at = br.pos;
         if (!br.take_code(m)) { atomicOr(P.err, at + 17u >= src.rel(P.nbits_total) ? 4u : 2u); return; }
@@ -844,16 +889,24 @@ __device__ __forceinline__ void idct_store(float (&b)[C][C], uint8_t *xbuf, int 
     }
 }
 
-// zig-zag chunk scratch + masks -> u8 frames.  Per warp: zero CPW cube buffers in shared memory,
-// copy in the non-zero chunks (lane <-> chunk), gather each thread's 64 coefficients through the
-// same per-lane run bases the encoder scatters with, dequantise, inverse transform.
+// zig-zag chunk scratch + masks -> u8 frames.  Per warp and group of CPW cubes: the non-zero
+// chunks are copied global -> shared with cp.async (lane <-> chunk) one group AHEAD into the other
+// half of a double buffer, the chunk masks two groups ahead, so neither latency is exposed.  Each
+// thread then gathers its 64 coefficients through the same per-lane run bases the encoder
+// scatters with -- only the runs that touch a non-zero chunk -- dequantises and runs the inverse
+// transform.  The buffers are kept all-zero: a lane wipes the chunks it copied in.
 template <int C>
 struct RecSmem {
     using G = Geo<C>;
-    static constexpr int ZZ_WARP = G::CPW * G::ZZ_STRIDE * 2;     // bytes
-    static constexpr int WARP_BYTES = ZZ_WARP + Xch<C, float>::WARP_BYTES;
+    static constexpr int ZZ_GROUP = G::CPW * G::ZZ_STRIDE * 2;     // bytes, one group of cubes
+    static constexpr int WARP_BYTES = 2 * ZZ_GROUP + Xch<C, float>::WARP_BYTES;
     static constexpr int TOTAL = kWarps * WARP_BYTES;
 };
+
+__device__ __forceinline__ void cp_async16(void *dst, const void *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
 
 template <int C>
 __global__ void __launch_bounds__(kThreads, 4)
@@ -865,8 +918,8 @@ reconstruct_zz_kernel(const Layout L, const int16_t *__restrict__ zzg, const uin
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int cl = lane / C, r = lane % C;
-    int16_t *wz = reinterpret_cast<int16_t *>(smem + warp * S::WARP_BYTES);
-    uint8_t *xbuf = smem + warp * S::WARP_BYTES + S::ZZ_WARP;
+    uint8_t *wbase = smem + warp * S::WARP_BYTES;
+    uint8_t *xbuf = wbase + 2 * S::ZZ_GROUP;
     // per-lane run bases and, per diagonal, the mask of the (at most two) chunks the run lies in
     uint32_t zb[G::NDIAG], rm[G::NDIAG];
 #pragma unroll
@@ -876,33 +929,56 @@ reconstruct_zz_kernel(const Layout L, const int16_t *__restrict__ zzg, const uin
         rm[s] = (1u << (zb[s] >> 4)) | (1u << ((zb[s] + len - 1) >> 4));
     }
     const float r5 = 5.0f * (float)r;
-    // the warp's cube buffers stay all-zero between groups: lanes wipe the chunks they copied in
-    constexpr int NV = S::ZZ_WARP / 16;
-    for (int i = lane; i < NV; i += 32) reinterpret_cast<uint4 *>(wz)[i] = make_uint4(0, 0, 0, 0);
+    constexpr int ITER = (G::CPW * G::CHUNKS) / 32;   // chunk <-> lane rounds per group: 4 (C=8) / 1 (C=4)
+    for (int i = lane; i < 2 * S::ZZ_GROUP / 16; i += 32) reinterpret_cast<uint4 *>(wbase)[i] = make_uint4(0, 0, 0, 0);
     __syncwarp();
+
     const long long ngroups = (L.ncubes + G::CPW - 1) / G::CPW;
-    for (long long g = (long long)blockIdx.x * kWarps + warp; g < ngroups; g += (long long)gridDim.x * kWarps) {
-        // non-zero chunks: lane <-> chunk
-        constexpr int ITER = (G::CPW * G::CHUNKS) / 32;   // 4 (C=8) / 1 (C=4)
-        bool mine[ITER];
+    const long long stride = (long long)gridDim.x * kWarps;
+    long long g = (long long)blockIdx.x * kWarps + warp;
+    // masks of the cubes of a group, as the chunk-copy rounds need them: lane's cube in round k
+    auto load_masks = [&](long long grp, uint32_t (&m)[ITER]) {
+#pragma unroll
+        for (int k = 0; k < ITER; k++) {
+            const long long gc = grp * G::CPW + (k * 32 + lane) / G::CHUNKS;
+            m[k] = (grp < ngroups && gc < L.ncubes) ? __ldg(cmask + gc) : 0u;
+        }
+    };
+    auto issue_copy = [&](long long grp, const uint32_t (&m)[ITER], int buf) {
 #pragma unroll
         for (int k = 0; k < ITER; k++) {
             const int ci = k * 32 + lane;
             const int c = ci / G::CHUNKS, chunk = ci % G::CHUNKS;
-            const long long gc = g * G::CPW + c;
-            mine[k] = gc < L.ncubes && ((__ldg(cmask + gc) >> chunk) & 1u);
-            if (mine[k]) {
-                const uint4 *src = reinterpret_cast<const uint4 *>(zzg + (size_t)gc * G::CS + chunk * 16);
-                uint4 *dst = reinterpret_cast<uint4 *>(wz + c * G::ZZ_STRIDE + chunk * 16);
-                const uint4 v0 = __ldg(src), v1 = __ldg(src + 1);
-                dst[0] = v0;
-                dst[1] = v1;
+            if ((m[k] >> chunk) & 1u) {
+                const int16_t *src = zzg + (size_t)(grp * G::CPW + c) * G::CS + chunk * 16;
+                int16_t *dst = reinterpret_cast<int16_t *>(wbase + buf * S::ZZ_GROUP) + c * G::ZZ_STRIDE + chunk * 16;
+                cp_async16(dst, src);
+                cp_async16(dst + 8, src + 8);
             }
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    uint32_t m0[ITER], m1[ITER], m2[ITER];
+    load_masks(g, m0);
+    load_masks(g + stride, m1);
+    issue_copy(g, m0, 0);
+    int buf = 0;
+    for (; g < ngroups; g += stride, buf ^= 1) {
+        load_masks(g + 2 * stride, m2);                 // consumed two iterations from now
+        issue_copy(g + stride, m1, buf ^ 1);            // lands while this group is transformed
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
         __syncwarp();
         const long long cube = g * G::CPW + cl;
-        const uint32_t cm = cube < L.ncubes ? __ldg(cmask + cube) : 0u;
-        const int16_t *zz = wz + cl * G::ZZ_STRIDE;
+        // this thread's cube mask: round (cl * CHUNKS) / 32 of m0 (all lanes of that round hold it)
+        uint32_t cm;
+        if (G::CHUNKS == 32) {
+            cm = m0[0];
+#pragma unroll
+            for (int k = 1; k < ITER; k++) cm = cl == k ? m0[k] : cm;
+        } else {
+            cm = __shfl_sync(0xffffffffu, m0[0], cl * G::CHUNKS);
+        }
+        const int16_t *zz = reinterpret_cast<const int16_t *>(wbase + buf * S::ZZ_GROUP) + cl * G::ZZ_STRIDE;
         float b[C][C];
 #pragma unroll
         for (int k0 = 0; k0 < C; k0++) {
@@ -919,16 +995,20 @@ reconstruct_zz_kernel(const Layout L, const int16_t *__restrict__ zzg, const uin
         __syncwarp();
 #pragma unroll
         for (int k = 0; k < ITER; k++) {
-            if (mine[k]) {
-                const int ci = k * 32 + lane;
-                uint4 *dst = reinterpret_cast<uint4 *>(wz + (ci / G::CHUNKS) * G::ZZ_STRIDE + (ci % G::CHUNKS) * 16);
+            const int ci = k * 32 + lane;
+            const int chunk = ci % G::CHUNKS;
+            if ((m0[k] >> chunk) & 1u) {
+                uint4 *dst = reinterpret_cast<uint4 *>(reinterpret_cast<int16_t *>(wbase + buf * S::ZZ_GROUP) +
+                                                       (ci / G::CHUNKS) * G::ZZ_STRIDE + chunk * 16);
                 dst[0] = make_uint4(0, 0, 0, 0);
                 dst[1] = make_uint4(0, 0, 0, 0);
             }
         }
-        __syncwarp();
         idct_store<C>(b, xbuf, cl, r, cube < L.ncubes, L, cube, frames);
+#pragma unroll
+        for (int k = 0; k < ITER; k++) { m0[k] = m1[k]; m1[k] = m2[k]; }
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 // int16 natural-order cubes -> u8 frames: dequantise, inverse butterflies, clamp, truncate.

@@ -230,9 +230,9 @@ struct BitReader {
         lo = w1 << sh;
         navail = 64 - sh;
     }
-    EG_HD void refill()
+    EG_HD void refill()                   // afterwards the 32 bits of hi are all valid
     {
-        while (navail <= 32) {            // lo is empty here
+        if (navail <= 32) {               // lo is empty here
             const uint32_t w = src.word(wnext++);
             hi |= shr32c(w, navail);
             lo = shl32c(w, 32 - navail);
@@ -256,6 +256,7 @@ struct BitReader {
             m = hi >> (32 - len);
             skip(len);
         } else {                          // 33 bits: 16 zeros, a one, 16 more bits
+            refill();                     // navail may be exactly 32 here
             m = (hi << 1) | (lo >> 31);
             skip(32);
             skip(1);
@@ -273,14 +274,15 @@ EG_HD uint32_t eg_parse_cube(const Source &src, uint32_t start, const uint16_t *
     BitReader<Source> br(src, start);
     int i = 0;
     while (i < CS) {
+        // one iteration = a run of one-bits (zero coefficients) followed by one longer code
         br.refill();
         int ones = clz32(~br.hi);
-        if (ones > 0) {
-            if (ones > CS - i) ones = CS - i;
-            i += ones;
-            br.skip(ones);
-            continue;
-        }
+        if (ones > CS - i) ones = CS - i;
+        i += ones;
+        br.skip(ones);
+        if (i >= CS) break;
+        br.refill();
+        if (br.hi >> 31) continue;        // the run of ones goes on
         uint32_t m;
         if (!br.take_code(m)) return ~0u;
         out.put(izz[i], (int16_t)eg_unmap(m));
@@ -300,14 +302,14 @@ EG_HD bool eg_scan_segment(const Source &src, uint32_t start, uint32_t limit, ui
     uint32_t n = 0;
     while (br.pos < limit) {
         br.refill();
-        int ones = clz32(~br.hi);
-        if (ones > 0) {
-            const uint32_t room = limit - br.pos;
-            if ((uint32_t)ones > room) ones = (int)room;
-            n += (uint32_t)ones;
-            br.skip(ones);
-            continue;
-        }
+        uint32_t ones = (uint32_t)clz32(~br.hi);
+        const uint32_t room = limit - br.pos;
+        if (ones > room) ones = room;
+        n += ones;
+        br.skip((int)ones);
+        if (br.pos >= limit) break;
+        br.refill();
+        if (br.hi >> 31) continue;
         uint32_t m;
         const uint32_t at = br.pos;
         if (!br.take_code(m)) {
