@@ -1,0 +1,82 @@
+/* decoder.c -- the C codec's decode flow over libdct3d.so.
+ *
+ * Same flow as the reference's 3d-DCT-video-encoding-OpenCL/decoder.c:85-314: read and inflate until
+ * one slab's worth of codes is buffered, decode it, write DCT_BLOCK_DEPTH frames, drop the consumed
+ * bytes and keep the bit position of the partial byte (expGolomb_freeBuffer(..., 0),
+ * ExpGolomb.c:123-129).  expGolomb_readValue + reorderDctCoeffs + applyDequantization + the cl*
+ * sequence + writeCubes (:229-295) are ONE call, dct3d_stream_decode, which reports
+ * DCT3D_E_NEED_MORE while the buffered input does not yet hold the whole slab.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <zlib.h>
+
+#include "../include/dct3d.h"
+#include "codec.h"
+
+int decode(char *inputFileName, char *outputFileName, int width, int height, int framesToDecode, int platformIndex)
+{
+    const size_t bufferSize = (size_t)width * height * DCT_BLOCK_DEPTH;
+    FILE *inputFile = fopen(inputFileName, "rb");
+    FILE *outputFile = fopen(outputFileName, "wb");
+    if (!inputFile || !outputFile) { printf("Error opening files\n"); return 1; }
+    unsigned char *zlibCompressedData = (unsigned char *)malloc(bufferSize);
+    size_t cap = 2 * bufferSize + 64, have = 0;                  /* inflated, not yet consumed */
+    unsigned char *expGolombCodedData = (unsigned char *)malloc(cap);
+    unsigned char *frames = (unsigned char *)malloc(bufferSize);
+
+    z_stream zlibStream;
+    memset(&zlibStream, 0, sizeof zlibStream);
+    inflateInit(&zlibStream);
+
+    printf("Getting device id\n");
+    dct3d_ctx *ctx = NULL;
+    if (dct3d_create(&ctx, platformIndex - 1, width, height, DCT_BLOCK_WIDTH) != DCT3D_OK) {
+        printf("Error creating dct3d context: %s\n", dct3d_last_error(NULL));
+        return 1;
+    }
+
+    printf("Starting decoding process\n");
+    int framesRead = 0, eof = 0, inflated_all = 0;
+    uint64_t bitpos = 0;
+    while (framesRead < framesToDecode) {
+        int rc = have ? dct3d_stream_decode(ctx, expGolombCodedData, have, &bitpos, DCT_BLOCK_DEPTH, frames) : DCT3D_E_NEED_MORE;
+        if (rc == DCT3D_E_NEED_MORE) {
+            if (inflated_all) { printf("Input ended before all frames were decoded\n"); return 1; }
+            /* Reading data from file and applying the inflate algorithm */
+            if (zlibStream.avail_in == 0 && !eof) {
+                size_t got = fread(zlibCompressedData, 1, bufferSize, inputFile);
+                if (got == 0) eof = 1;
+                zlibStream.next_in = zlibCompressedData;
+                zlibStream.avail_in = (uInt)got;
+            }
+            if (cap - have < bufferSize) { cap *= 2; expGolombCodedData = (unsigned char *)realloc(expGolombCodedData, cap); }
+            zlibStream.next_out = expGolombCodedData + have;
+            zlibStream.avail_out = (uInt)(cap - have);
+            int zr = inflate(&zlibStream, Z_NO_FLUSH);
+            have = cap - zlibStream.avail_out;
+            if (zr == Z_STREAM_END || (eof && zlibStream.avail_in == 0)) inflated_all = (zr == Z_STREAM_END) || eof;
+            if (zr != Z_OK && zr != Z_STREAM_END && zr != Z_BUF_ERROR) { printf("Error inflating input: %d\n", zr); return 1; }
+            continue;
+        }
+        if (rc != DCT3D_OK) { printf("Error decoding slab: %s\n", dct3d_last_error(ctx)); return 1; }
+        /* Writing the resulting pixels to the output file */
+        fwrite(frames, 1, bufferSize, outputFile);
+        framesRead += DCT_BLOCK_DEPTH;
+        /* drop the consumed bytes, keep the partial byte's bit position */
+        const size_t consumed = (size_t)(bitpos / 8);
+        memmove(expGolombCodedData, expGolombCodedData + consumed, have - consumed);
+        have -= consumed;
+        bitpos %= 8;
+        printf("Frames processed: %d\n", framesRead);
+    }
+    inflateEnd(&zlibStream);
+    fflush(outputFile);
+    fclose(outputFile);
+    fclose(inputFile);
+    dct3d_destroy(ctx);
+    free(zlibCompressedData); free(expGolombCodedData); free(frames);
+    printf("Decoding process completed");
+    return 0;
+}

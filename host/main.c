@@ -1,0 +1,38 @@
+/* main.c -- the C codec's command line, same shape as the reference's
+ * 3d-DCT-video-encoding-OpenCL/main.c:5-49:
+ *   codec list_platforms
+ *   codec encode|decode <input file> <output file> <width> <height> <nr of frames> [device_index]
+ * list_platforms lists CUDA devices (dct3d_list_devices) instead of OpenCL platforms. */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../include/dct3d.h"
+#include "codec.h"
+
+static void printUsage(void)
+{
+    printf("Usage\n\n");
+    printf("codec list_platforms -> List available CUDA devices\n");
+    printf("codec encode|decode <input file> <output file> <width> <height> <nr of frames to encode/decode> "
+           "<device_index (optional)> -> Encode/Decode given file");
+}
+
+int main(int argc, char *argv[])
+{
+    if (argc < 2) { printUsage(); exit(0); }
+    if (!strcmp(argv[1], "list_platforms")) {
+        char buf[4096];
+        if (dct3d_list_devices(buf, sizeof buf) < 0) { printf("%s\n", dct3d_last_error(NULL)); return 1; }
+        printf("%s", buf);
+    } else if (argc >= 7) {
+        int width = atoi(argv[4]), height = atoi(argv[5]), framesToProcess = atoi(argv[6]);
+        int platformIndex = argc > 7 ? atoi(argv[7]) : 1;
+        if (!strcmp(argv[1], "encode")) return encode(argv[2], argv[3], width, height, framesToProcess, platformIndex);
+        else if (!strcmp(argv[1], "decode")) return decode(argv[2], argv[3], width, height, framesToProcess, platformIndex);
+        else printUsage();
+    } else {
+        printUsage();
+    }
+    return 0;
+}

@@ -263,3 +263,73 @@ def test_full_hd_slabs_properties(codec_mod, oracle, synth):
         c.set_option("tma", 0)
         s2, b2 = c.encode_u8(clip)
         assert b2 == nbits and s2.tobytes() == stream.tobytes()
+
+
+def test_c_cli_interoperates_with_reference_cli(codec_mod, oracle, synth, tmp_path):
+    """Files written by our C codec (host/codec, the reference's encoder.c/decoder.c flow over libdct3d)
+    decode with the reference's own CLI (oracle/_ref/codec_ref: unmodified reference C + CPU OpenCL shim)
+    and vice versa; the Python mirrors of the Java/C command lines read and write the same files."""
+    import os, subprocess, zlib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ours = os.path.join(root, "host", "codec")
+    ref = os.path.join(root, "oracle", "_ref", "codec_ref")
+    if not os.path.exists(ours):
+        subprocess.check_call(["make", "-C", os.path.join(root, "host"), "CC=gcc"])
+    W, H, F = 64, 48, 24
+    clip = synth.natural(W, H, F, 1)
+    raw = tmp_path / "in.raw"
+    clip.tofile(raw)
+    args = [str(W), str(H), str(F)]
+    run = lambda exe, *a: subprocess.run([exe, *a], check=True, stdout=subprocess.DEVNULL)
+    run(ours, "encode", str(raw), str(tmp_path / "ours.enc"), *args)
+    stream = np.frombuffer(zlib.decompress(open(tmp_path / "ours.enc", "rb").read()), np.uint8)
+    with make(codec_mod, W, H, 8) as c:
+        one, nbits = c.encode_u8(clip)
+    assert stream.tobytes() == one.tobytes()                       # slab loop + carried partial byte == one shot
+    run(ours, "decode", str(tmp_path / "ours.enc"), str(tmp_path / "ours.dec"), *args)
+    mine = np.fromfile(tmp_path / "ours.dec", np.uint8).reshape(F, H, W)
+    assert np.abs(mine.astype(int) - oracle.decode_u8(stream, W, H, F).astype(int)).max() <= 1
+    # Python mirrors of the Java command lines and of the C command line
+    assert codec_mod.Encoder.main([str(raw), str(tmp_path / "j.enc"), *args]) == 0
+    assert zlib.decompress(open(tmp_path / "j.enc", "rb").read()) == one.tobytes()
+    assert codec_mod.Decoder.main([str(tmp_path / "ours.enc"), str(tmp_path / "j.dec"), *args]) == 0
+    assert (np.fromfile(tmp_path / "j.dec", np.uint8).reshape(F, H, W) == mine).all()
+    assert codec_mod.codec_main(["codec", "decode", str(tmp_path / "j.enc"), str(tmp_path / "p.dec"), *args]) == 0
+    assert (np.fromfile(tmp_path / "p.dec", np.uint8).reshape(F, H, W) == mine).all()
+    if os.path.exists(ref):
+        run(ref, "decode", str(tmp_path / "ours.enc"), str(tmp_path / "ref.dec"), *args)      # reference reads our file
+        theirs = np.fromfile(tmp_path / "ref.dec", np.uint8).reshape(F, H, W)
+        assert np.abs(theirs.astype(int) - mine.astype(int)).max() <= 1                          # rule (4)
+        run(ref, "encode", str(raw), str(tmp_path / "ref.enc"), *args)                          # we read the reference's file
+        run(ours, "decode", str(tmp_path / "ref.enc"), str(tmp_path / "x.dec"), *args)
+        run(ref, "decode", str(tmp_path / "ref.enc"), str(tmp_path / "y.dec"), *args)
+        a = np.fromfile(tmp_path / "x.dec", np.uint8).astype(int)
+        b = np.fromfile(tmp_path / "y.dec", np.uint8).astype(int)
+        assert np.abs(a - b).max() <= 1
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_ranges_equal_one_shot(codec_mod, synth, world):
+    """The multi-GPU path, emulated on one GPU: every 'rank' codes its slab range from bit 0 of its own
+    buffer; prefix-summed bit counts + shifted concatenation give the one-shot stream bit for bit, and
+    every range decodes from its start bit."""
+    sh = pkg("sharding")
+    W, H, F = 128, 64, 64
+    clip = synth.natural(W, H, F, 3)
+    with make(codec_mod, W, H, 8) as c:
+        one, bits = c.encode_u8(clip)
+        parts, nb = [], []
+        for g in range(world):
+            lo, hi = sh.slab_range(F // 8, g, world)
+            s, b = c.encode_u8(clip[lo * 8:hi * 8])
+            parts.append(s)
+            nb.append(b)
+        cat, total = sh.concatenate(parts, nb)
+        assert total == bits and cat.tobytes() == one.tobytes()
+        offs = sh.bit_offsets(nb)
+        assert any(o % 8 for o in offs[1:-1])          # ranges do not start on byte boundaries
+        full = c.decode_u8(one, F)
+        for g in range(world):
+            lo, hi = sh.slab_range(F // 8, g, world)
+            fr, end = c.stream_decode(one, offs[g], (hi - lo) * 8)
+            assert end == offs[g + 1] and (fr == full[lo * 8:hi * 8]).all()
