@@ -54,6 +54,8 @@ struct dct3d_ctx {
     cudaStream_t stream = nullptr;
     std::string err;
     DevBuf frames, bits, q, status, ctrl, seg, fa, fb, zz, cmask;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // around encode_kernel / reconstruct_zz_kernel
+    bool ev_valid[2] = {false, false};
     Ctrl *h_ctrl = nullptr;          // pinned
     unsigned long long *h_u64 = nullptr;  // pinned scratch (4 entries)
     // streaming state
@@ -196,7 +198,9 @@ int launch_encode(dct3d_ctx *ctx, const EncParams &P, const CUtensorMap &tm, cud
     CU_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem));
     if (occ < 1) return fail(ctx, DCT3D_E_CUDA, "encode kernel does not fit on an SM");
     const long long grid = std::min<long long>(P.L.ntiles, (long long)ctx->num_sms * occ);
+    if (MODE == MODE_ZZ) cudaEventRecord(ctx->ev[0], st);
     kern<<<(unsigned)grid, kThreads, smem, st>>>(tm, P);
+    if (MODE == MODE_ZZ) { cudaEventRecord(ctx->ev[1], st); ctx->ev_valid[0] = true; }
     ctx->launches++;
     CU_CHECK(ctx, cudaGetLastError());
     return DCT3D_OK;
@@ -246,7 +250,10 @@ static int launch_reconstruct_zz(dct3d_ctx *ctx, const Layout &L, void *d_frames
     CU_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem));
     const long long groups = (L.ncubes + Geo<C>::CPW - 1) / Geo<C>::CPW;
     const long long grid = std::min<long long>((groups + kWarps - 1) / kWarps, (long long)ctx->num_sms * std::max(occ, 1));
+    cudaEventRecord(ctx->ev[2], st);
     kern<<<(unsigned)grid, kThreads, smem, st>>>(L, (const int16_t *)ctx->zz.p, (const uint32_t *)ctx->cmask.p, (uint8_t *)d_frames);
+    cudaEventRecord(ctx->ev[3], st);
+    ctx->ev_valid[1] = true;
     ctx->launches++;
     CU_CHECK(ctx, cudaGetLastError());
     return DCT3D_OK;
@@ -354,6 +361,7 @@ int dct3d_create(dct3d_ctx **out, int device, int width, int height, int cube)
     if (rc == DCT3D_OK) {
         cudaError_t e = cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device);
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+        for (int i = 0; i < 4 && e == cudaSuccess; i++) e = cudaEventCreate(&ctx->ev[i]);
         if (e == cudaSuccess) e = cudaMallocHost((void **)&ctx->h_ctrl, sizeof(Ctrl));
         if (e == cudaSuccess) e = cudaMallocHost((void **)&ctx->h_u64, 4 * sizeof(unsigned long long));
         if (e != cudaSuccess) rc = fail(ctx, DCT3D_E_CUDA, "context setup failed: %s", cudaGetErrorString(e));
@@ -369,6 +377,7 @@ void dct3d_destroy(dct3d_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     for (DevBuf *b : {&ctx->frames, &ctx->bits, &ctx->q, &ctx->status, &ctx->ctrl, &ctx->seg, &ctx->fa, &ctx->fb, &ctx->zz, &ctx->cmask}) b->release();
+    for (int i = 0; i < 4; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->h_ctrl) cudaFreeHost(ctx->h_ctrl);
     if (ctx->h_u64) cudaFreeHost(ctx->h_u64);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -396,6 +405,17 @@ long dct3d_get_stat(const dct3d_ctx *ctx, const char *key)
     if (!strcmp(key, "launches")) return ctx->launches;
     if (!strcmp(key, "tma")) return ctx->use_tma;
     if (!strcmp(key, "num_sms")) return ctx->num_sms;
+    // device time of the last encode_kernel / reconstruct_zz_kernel launch, nanoseconds (CUDA events on
+    // the launching stream; waits for that launch to finish)
+    for (int k = 0; k < 2; k++) {
+        if (!strcmp(key, k == 0 ? "ns_encode_kernel" : "ns_reconstruct_kernel")) {
+            if (!ctx->ev_valid[k]) return -1;
+            float ms = 0.f;
+            if (cudaEventSynchronize(ctx->ev[2 * k + 1]) != cudaSuccess) return -1;
+            if (cudaEventElapsedTime(&ms, ctx->ev[2 * k], ctx->ev[2 * k + 1]) != cudaSuccess) return -1;
+            return (long)(ms * 1e6f);
+        }
+    }
     return -1;
 }
 

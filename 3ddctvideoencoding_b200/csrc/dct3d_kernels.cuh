@@ -203,6 +203,46 @@ __device__ __forceinline__ void inv_yx(T (&a)[C][C])
 #pragma unroll
     for (int y = 0; y < C; y++) Dct1D<C, T>::template inv<1>(&a[y][0]);
 }
+// Scaled pipeline of the fused kernels (dct_math.h): x and y butterflies normalised, the t butterfly
+// carries S[k2] in its constants, S[k1] (k1 = lane) lives in the quantiser / dequantiser tables.
+template <int C, typename T>
+__device__ __forceinline__ void fwd_xy_n(T (&a)[C][C])
+{
+#pragma unroll
+    for (int y = 0; y < C; y++) Dct1D<C, T>::template fwd_n<1>(&a[y][0]);
+#pragma unroll
+    for (int x = 0; x < C; x++) Dct1D<C, T>::template fwd_n<C>(&a[0][x]);
+}
+template <int C, typename T>
+__device__ __forceinline__ void inv_yx_n(T (&a)[C][C])
+{
+#pragma unroll
+    for (int x = 0; x < C; x++) Dct1D<C, T>::template inv_n<C>(&a[0][x]);
+#pragma unroll
+    for (int y = 0; y < C; y++) Dct1D<C, T>::template inv_n<1>(&a[y][0]);
+}
+template <int C, typename T>
+__device__ __forceinline__ void fwd_t_g(T (&b)[C][C])
+{
+#pragma unroll
+    for (int x = 0; x < C; x++) Dct1D<C, T>::template fwd_g<C>(&b[0][x], Dct1D<C, T>::scale(x));
+}
+template <int C, typename T>
+__device__ __forceinline__ void inv_t_g(T (&b)[C][C])
+{
+#pragma unroll
+    for (int x = 0; x < C; x++) Dct1D<C, T>::template inv_g<C>(&b[0][x], Dct1D<C, T>::scale(x));
+}
+// S[k1] for a run-time k1 (the lane)
+template <int C>
+__device__ __forceinline__ float lane_scale(int k1)
+{
+    float v = Dct1D<C, float>::scale(0);
+#pragma unroll
+    for (int k = 1; k < C; k++) v = k1 == k ? Dct1D<C, float>::scale(k) : v;
+    return v;
+}
+
 template <int C, typename T>
 __device__ __forceinline__ void fwd_t(T (&b)[C][C])
 {
@@ -214,6 +254,14 @@ __device__ __forceinline__ void inv_t(T (&b)[C][C])
 {
 #pragma unroll
     for (int x = 0; x < C; x++) Dct1D<C, T>::template inv<C>(&b[0][x]);
+}
+
+// clamp to [0,255] + truncate toward zero (Decoder.java:74-80,112; decoder.c:29; 3dDCT.cl:255-262)
+__device__ __forceinline__ uint32_t f2u8_sat(float v)
+{
+    uint32_t r;
+    asm("cvt.rzi.sat.u8.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return r;
 }
 
 // u8 -> f32 without the conversion pipe: PRMT the byte into the mantissa of 2^23, subtract.
@@ -332,7 +380,7 @@ encode_kernel(const __grid_constant__ CUtensorMap tmap, const EncParams P)
     uint32_t zb[G::NDIAG];
 #pragma unroll
     for (int s = 0; s < G::NDIAG; s++) {
-        rq[s] = 1.0f / (float)quant_divisor(s + r);
+        rq[s] = lane_scale<C>(r) / (float)quant_divisor(s + r);   // S[k1] of the scaled butterflies folded in
         zb[s] = zz_base<C>(r, s);
     }
     auto issue_tma = [&](long long tile, int h) {
@@ -402,9 +450,9 @@ encode_kernel(const __grid_constant__ CUtensorMap tmap, const EncParams P)
                 for (int x = 0; x < 4; x++) a[y][x % C] = byte_to_float(v, x);
             }
         }
-        fwd_xy<C, float>(a);
+        fwd_xy_n<C, float>(a);
         Xch<C, float>::transpose(s_xch + warp * Xch<C, float>::WARP_BYTES, cl, r, a, bq);
-        fwd_t<C, float>(bq);
+        fwd_t_g<C, float>(bq);
         // bq[k0][k2] is coefficient (k0, k1 = r, k2)
         if (MODE == MODE_NAT) {
             if (slot < bp.nvalid) {
@@ -865,9 +913,9 @@ __device__ __forceinline__ void idct_store(float (&b)[C][C], uint8_t *xbuf, int 
                                            long long cube, uint8_t *__restrict__ frames)
 {
     float a[C][C];
-    inv_t<C, float>(b);
+    inv_t_g<C, float>(b);
     Xch<C, float>::transpose(xbuf, cl, r, b, a);   // the exchange is its own inverse
-    inv_yx<C, float>(a);
+    inv_yx_n<C, float>(a);
     if (!valid) return;
     const int per_slab = L.by * L.bx;
     const int slab = (int)(cube / per_slab);
@@ -878,11 +926,12 @@ __device__ __forceinline__ void idct_store(float (&b)[C][C], uint8_t *xbuf, int 
     for (int y = 0; y < C; y++) {
         uint32_t w[2] = {0, 0};
 #pragma unroll
-        for (int x = 0; x < C; x++) {
-            // clamp, then add 2^23 rounding toward zero: floor(v) lands in the low mantissa byte
-            const float v = fminf(fmaxf(a[y][x], 0.0f), 255.0f);
-            const uint32_t bits = __float_as_uint(__fadd_rz(v, 8388608.0f)) & 0xffu;
-            w[x / 4] |= bits << ((x & 3) * 8);
+        for (int x = 0; x < C; x += 4) {
+            // clamp to [0,255] and truncate in one saturating conversion each (the otherwise idle
+            // conversion pipe), then PRMT the four bytes together
+            const uint32_t b0 = f2u8_sat(a[y][x]), b1 = f2u8_sat(a[y][x + 1]);
+            const uint32_t b2 = f2u8_sat(a[y][x + 2]), b3 = f2u8_sat(a[y][x + 3]);
+            w[x / 4] = __byte_perm(__byte_perm(b0, b1, 0x0040), __byte_perm(b2, b3, 0x0040), 0x5410);
         }
         if (C == 8) *reinterpret_cast<uint2 *>(dst + (size_t)y * L.W) = make_uint2(w[0], w[1]);
         else *reinterpret_cast<uint32_t *>(dst + (size_t)y * L.W) = w[0];
@@ -929,6 +978,7 @@ reconstruct_zz_kernel(const Layout L, const int16_t *__restrict__ zzg, const uin
         rm[s] = (1u << (zb[s] >> 4)) | (1u << ((zb[s] + len - 1) >> 4));
     }
     const float r5 = 5.0f * (float)r;
+    const float sj = lane_scale<C>(r);       // S[k1] expected by the scaled inverse butterflies
     constexpr int ITER = (G::CPW * G::CHUNKS) / 32;   // chunk <-> lane rounds per group: 4 (C=8) / 1 (C=4)
     for (int i = lane; i < 2 * S::ZZ_GROUP / 16; i += 32) reinterpret_cast<uint4 *>(wbase)[i] = make_uint4(0, 0, 0, 0);
     __syncwarp();
@@ -988,7 +1038,7 @@ reconstruct_zz_kernel(const Layout L, const int16_t *__restrict__ zzg, const uin
                 const int k0min = s > C - 1 ? s - (C - 1) : 0;
                 // only runs that touch a non-zero chunk are read (everything else is zero)
                 float v = 0.0f;
-                if (cm & rm[s]) v = (float)(int)zz[zb[s] + (k0 - k0min)] * fmaxf(1.0f, r5 + 5.0f * (float)s);
+                if (cm & rm[s]) v = (float)(int)zz[zb[s] + (k0 - k0min)] * (fmaxf(1.0f, r5 + 5.0f * (float)s) * sj);
                 b[k0][k2] = v;
             }
         }
@@ -1023,7 +1073,7 @@ reconstruct_kernel(const Layout L, const int16_t *__restrict__ qcubes, uint8_t *
     const int cl = lane / C, r = lane % C;
     float dq[G::NDIAG];
 #pragma unroll
-    for (int s = 0; s < G::NDIAG; s++) dq[s] = (float)quant_divisor(s + r);
+    for (int s = 0; s < G::NDIAG; s++) dq[s] = (float)quant_divisor(s + r) * lane_scale<C>(r);
     const long long ngroups = (L.ncubes + G::CPW - 1) / G::CPW;
     for (long long g = (long long)blockIdx.x * kWarps + warp; g < ngroups; g += (long long)gridDim.x * kWarps) {
         const long long cube = g * G::CPW + cl;

@@ -36,6 +36,27 @@ static void cube_transform(const T *in, T *out, bool inverse)
     memcpy(out, a, sizeof(a));
 }
 
+// the scaled pipeline the fused kernels use: x and y normalised, t with constants times S[k2],
+// S[k1] applied at the end (the kernels fold it into the quantiser table)
+template <int N, typename T>
+static void cube_transform_scaled(const T *in, T *out, bool inverse)
+{
+    T a[N][N][N];   // [t][y][x]
+    memcpy(a, in, sizeof(a));
+    if (!inverse) {
+        for (int t = 0; t < N; t++) for (int y = 0; y < N; y++) Dct1D<N, T>::template fwd_n<1>(&a[t][y][0]);
+        for (int t = 0; t < N; t++) for (int x = 0; x < N; x++) Dct1D<N, T>::template fwd_n<N>(&a[t][0][x]);
+        for (int y = 0; y < N; y++) for (int x = 0; x < N; x++) Dct1D<N, T>::template fwd_g<N * N>(&a[0][y][x], Dct1D<N, T>::scale(x));
+        for (int t = 0; t < N; t++) for (int y = 0; y < N; y++) for (int x = 0; x < N; x++) a[t][y][x] *= Dct1D<N, T>::scale(y);
+    } else {
+        for (int t = 0; t < N; t++) for (int y = 0; y < N; y++) for (int x = 0; x < N; x++) a[t][y][x] *= Dct1D<N, T>::scale(y);
+        for (int y = 0; y < N; y++) for (int x = 0; x < N; x++) Dct1D<N, T>::template inv_g<N * N>(&a[0][y][x], Dct1D<N, T>::scale(x));
+        for (int t = 0; t < N; t++) for (int x = 0; x < N; x++) Dct1D<N, T>::template inv_n<N>(&a[t][0][x]);
+        for (int t = 0; t < N; t++) for (int y = 0; y < N; y++) Dct1D<N, T>::template inv_n<1>(&a[t][y][0]);
+    }
+    memcpy(out, a, sizeof(a));
+}
+
 struct VecSink {
     std::vector<uint32_t> &w;
     explicit VecSink(std::vector<uint32_t> &v) : w(v) {}
@@ -57,6 +78,10 @@ void hh_cube_f32(const float *in, float *out, int n, int inverse)
 { if (n == 8) cube_transform<8, float>(in, out, inverse); else cube_transform<4, float>(in, out, inverse); }
 void hh_cube_f64(const double *in, double *out, int n, int inverse)
 { if (n == 8) cube_transform<8, double>(in, out, inverse); else cube_transform<4, double>(in, out, inverse); }
+void hh_cube_scaled_f32(const float *in, float *out, int n, int inverse)
+{ if (n == 8) cube_transform_scaled<8, float>(in, out, inverse); else cube_transform_scaled<4, float>(in, out, inverse); }
+void hh_cube_scaled_f64(const double *in, double *out, int n, int inverse)
+{ if (n == 8) cube_transform_scaled<8, double>(in, out, inverse); else cube_transform_scaled<4, double>(in, out, inverse); }
 int hh_quantize(float coef, int ksum) { return quantize_f32(coef, 1.0f / (float)quant_divisor(ksum)); }
 
 // zz: ncubes x cs int16 in zig-zag order.  Writes the stream into out (cap bytes, zeroed by the

@@ -27,6 +27,8 @@ def hh():
     u16 = np.ctypeslib.ndpointer(np.uint16, flags="C")
     L.hh_cube_f32.argtypes = [f32, f32, C.c_int, C.c_int]
     L.hh_cube_f64.argtypes = [f64, f64, C.c_int, C.c_int]
+    L.hh_cube_scaled_f32.argtypes = [f32, f32, C.c_int, C.c_int]
+    L.hh_cube_scaled_f64.argtypes = [f64, f64, C.c_int, C.c_int]
     L.hh_quantize.argtypes = [C.c_float, C.c_int]
     L.hh_quantize.restype = C.c_int
     L.hh_eg_write.argtypes = [i16, C.c_int, C.c_int, C.c_uint64, u8, C.c_size_t]
@@ -57,6 +59,28 @@ def test_butterfly_matches_fp64_oracle(hh, oracle, n):
         assert np.abs(back - px).max() < 1e-9
         back32 = np.zeros((n, n, n), np.float32)
         hh.hh_cube_f32(out32, back32, n, 1)
+        assert np.abs(back32 - px).max() < 1e-3
+
+
+@pytest.mark.parametrize("n", [8, 4])
+def test_scaled_butterflies_match_fp64_oracle(hh, oracle, n):
+    """The normalised x/y butterflies + scaled t butterfly + S[k1] factor equal the plain transform."""
+    rng = np.random.default_rng(4)
+    for trial in range(8):
+        px = rng.integers(0, 256, size=(n, n, n)).astype(np.float64)
+        ref = oracle.dct_direct(px, n)
+        out64 = np.zeros_like(px)
+        hh.hh_cube_scaled_f64(np.ascontiguousarray(px), out64, n, 0)
+        assert np.abs(out64 - ref).max() < 1e-10
+        out32 = np.zeros((n, n, n), np.float32)
+        hh.hh_cube_scaled_f32(px.astype(np.float32), out32, n, 0)
+        assert np.abs(out32 - ref).max() <= 1e-4 * max(1.0, np.abs(ref).max())
+        assert np.abs(out32 - ref).max() < 2e-3
+        back = np.zeros_like(px)
+        hh.hh_cube_scaled_f64(out64, back, n, 1)
+        assert np.abs(back - px).max() < 1e-9
+        back32 = np.zeros((n, n, n), np.float32)
+        hh.hh_cube_scaled_f32(out32, back32, n, 1)
         assert np.abs(back32 - px).max() < 1e-3
 
 
