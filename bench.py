@@ -243,18 +243,57 @@ def run_ours(args):
     value = world * F / (ms_per_step * 1e-3)
 
     # ---- end to end through the host-buffer C ABI (pinned host memory) ---------------------------
+    # The clip is streamed the way the reference's C codec streams it (slab ranges in a loop): an
+    # encoder context on one host thread and a decoder context on another, so that the H2D copy of
+    # range i overlaps the D2H copy of range i-1 (PCIe is full duplex and is what bounds this number).
+    # Every range is a self-contained stream coded from bit 0, exactly like a multi-GPU slab range.
+    import queue
+    import threading as th
     h_frames = torch.empty((F, H, W), dtype=torch.uint8, pin_memory=True)
     h_frames.copy_(frames)
-    h_stream = torch.zeros(cap, dtype=torch.uint8, pin_memory=True)
     h_out = torch.empty((F, H, W), dtype=torch.uint8, pin_memory=True)
-    nb, ny = C.c_uint64(), C.c_size_t()
+    nchunk = 8 if F % 64 == 0 else 1
+    cf = F // nchunk                                   # frames per range
+    ccap = W * H * cf // 2 + 4096
+    h_streams = [torch.zeros(ccap, dtype=torch.uint8, pin_memory=True) for _ in range(nchunk)]
+    dec_ctx = codec.Codec(W, H, cube, device=local)
     L = c.L
+    fsz = W * H * cf
+    sizes = [0] * nchunk
 
     def e2e_step():
-        rc = L.dct3d_encode_u8(c.h, h_frames.data_ptr(), F, h_stream.data_ptr(), cap, C.byref(nb), C.byref(ny))
+        q = queue.Queue()
+        err = []
+
+        def enc():
+            nb, ny = C.c_uint64(), C.c_size_t()
+            for i in range(nchunk):
+                rc = L.dct3d_encode_u8(c.h, h_frames.data_ptr() + i * fsz, cf, h_streams[i].data_ptr(), ccap, C.byref(nb), C.byref(ny))
+                if rc != 0:
+                    err.append(L.dct3d_last_error(c.h))
+                sizes[i] = ny.value
+                q.put(i)
+
+        def dec():
+            for _ in range(nchunk):
+                i = q.get()
+                rc = L.dct3d_decode_u8(dec_ctx.h, h_streams[i].data_ptr(), sizes[i], cf, h_out.data_ptr() + i * fsz)
+                if rc != 0:
+                    err.append(L.dct3d_last_error(dec_ctx.h))
+
+        ta, tb = th.Thread(target=enc), th.Thread(target=dec)
+        ta.start(); tb.start(); ta.join(); tb.join()
+        assert not err, err
+
+    def e2e_single():
+        nb, ny = C.c_uint64(), C.c_size_t()
+        big = h_streams[0] if nchunk == 1 else torch.zeros(cap, dtype=torch.uint8, pin_memory=True)
+        t0 = time.perf_counter()
+        rc = L.dct3d_encode_u8(c.h, h_frames.data_ptr(), F, big.data_ptr(), big.numel(), C.byref(nb), C.byref(ny))
         assert rc == 0, L.dct3d_last_error(c.h)
-        rc = L.dct3d_decode_u8(c.h, h_stream.data_ptr(), ny.value, F, h_out.data_ptr())
+        rc = L.dct3d_decode_u8(c.h, big.data_ptr(), ny.value, F, h_out.data_ptr())
         assert rc == 0, L.dct3d_last_error(c.h)
+        return time.perf_counter() - t0
 
     e2e_step()
     barrier()
@@ -269,6 +308,10 @@ def run_ours(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * F / float(te.item())
     roundtrip_ok = bool((h_out.to(dev) == d_out).all().item())
+    e2e_bytes = N + sum(sizes)
+    e2e_single()
+    single_s = e2e_single()
+    dec_ctx.close()
 
     if rank == 0:
         peak, peak_src = peaks()
@@ -305,8 +348,12 @@ def run_ours(args):
                 "forward_f32": seam["forward_f32"], "inverse_f32": seam["inverse_f32"],
                 "frac": min(seam["forward_f32"], seam["inverse_f32"]) / peak},
             "cpu_baseline": cpu,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(N + S), "d2h_bytes_per_step": int(S + N),
-                    "steps": e2e_steps, "matches_device_path": roundtrip_ok},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(e2e_bytes), "d2h_bytes_per_step": int(e2e_bytes),
+                    "steps": e2e_steps, "matches_device_path": roundtrip_ok,
+                    "how": f"dct3d_encode_u8 / dct3d_decode_u8 on pinned host buffers, {nchunk} slab ranges of {cf} frames streamed "
+                           "through an encoder thread and a decoder thread (H2D of range i overlaps D2H of range i-1)",
+                    "single_call_value": world * F / single_s,
+                    "bound": "PCIe: %.2f GB each way per step" % (e2e_bytes / 1e9)},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "wall_s": t_wall,
