@@ -592,39 +592,49 @@ static int parse_common(dct3d_ctx *ctx, const void *d_stream, size_t nbytes, uin
     const unsigned sb = kSegThreads, sg = (unsigned)((P.nseg + sb - 1) / sb);
     seg_scan_kernel<<<sg, sb, 0, st>>>(P);
     ctx->launches++;
-    // fix-up rounds: re-scan only the segments whose entry overhang differs from the one assumed
-    for (unsigned long long round = 0; round <= P.nseg; round++) {
+    auto fix_round = [&]() -> int {
         CU_CHECK(ctx, cudaMemsetAsync(&dc->changed, 0, 8, st));   // changed + nwork
         seg_check_kernel<<<(unsigned)((P.nseg + 255) / 256), 256, 0, st>>>(P);
         seg_fix_kernel<<<(unsigned)std::min<unsigned long long>((P.nseg + 127) / 128, (unsigned long long)ctx->num_sms * 16), 128, 0, st>>>(P);
         ctx->launches += 2;
-        if ((rc = fetch_ctrl(ctx, st))) return rc;
-        if (!ctx->h_ctrl->changed) break;
-    }
-    {
+        return DCT3D_OK;
+    };
+    auto prefix_and_parse = [&]() -> int {
         const long long stiles = (long long)((P.nseg + kScanThreads * kScanItems - 1) / (kScanThreads * kScanItems));
         CU_CHECK(ctx, ctx->status.reserve((size_t)stiles * 8));
         CU_CHECK(ctx, cudaMemsetAsync(ctx->status.p, 0, (size_t)stiles * 8, st));
         CU_CHECK(ctx, cudaMemsetAsync(&dc->ticket, 0, 4, st));
         const long long grid = std::min<long long>(stiles, (long long)ctx->num_sms * 8);
         seg_prefix_kernel<<<(unsigned)grid, kScanThreads, 0, st>>>(P, (unsigned long long *)ctx->status.p, &dc->ticket);
-        ctx->launches++;
-    }
+        const unsigned pg = (unsigned)((P.nseg + kParseThreads - 1) / kParseThreads);
+        if (C == 8) seg_parse_kernel<8><<<pg, kParseThreads, 0, st>>>(P); else seg_parse_kernel<4><<<pg, kParseThreads, 0, st>>>(P);
+        ctx->launches += 2;
+        CU_CHECK(ctx, cudaGetLastError());
+        return DCT3D_OK;
+    };
+    // Fix-up rounds re-scan only the segments whose entry overhang differs from the one assumed.  Two
+    // rounds are enqueued without looking (the first repairs ~1 segment in 7, the second normally finds
+    // nothing), the rest of the pipeline follows, and the host checks ONCE at the end whether the second
+    // round still changed something; only then (not seen on any tested content) it iterates to
+    // convergence and redoes prefix + parse.
+    if ((rc = fix_round()) || (rc = fix_round()) || (rc = prefix_and_parse())) return rc;
     CU_CHECK(ctx, cudaMemcpyAsync(ctx->h_u64, P.seg_first + n, 8, cudaMemcpyDeviceToHost, st));
     if ((rc = fetch_ctrl(ctx, st))) return rc;
-    if (ctx->h_ctrl->err & 2u) return fail(ctx, DCT3D_E_STREAM, "malformed Exp-Golomb code in stream");
+    if (ctx->h_ctrl->changed) {
+        for (unsigned long long round = 0; round <= P.nseg && ctx->h_ctrl->changed; round++) {
+            if ((rc = fix_round()) || (rc = fetch_ctrl(ctx, st))) return rc;
+        }
+        CU_CHECK(ctx, cudaMemsetAsync(&dc->err, 0, 4, st));
+        CU_CHECK(ctx, cudaMemsetAsync(P.cmask, 0, ncubes * 4, st));
+        if ((rc = prefix_and_parse())) return rc;
+        CU_CHECK(ctx, cudaMemcpyAsync(ctx->h_u64, P.seg_first + n, 8, cudaMemcpyDeviceToHost, st));
+        if ((rc = fetch_ctrl(ctx, st))) return rc;
+    }
     if (ctx->h_u64[0] < (unsigned long long)ncubes * CS)
         return fail(ctx, DCT3D_E_NEED_MORE, "stream holds %llu codes, %llu needed", ctx->h_u64[0], (unsigned long long)ncubes * CS);
-    const unsigned pg = (unsigned)((P.nseg + kParseThreads - 1) / kParseThreads);
-    if (C == 8) seg_parse_kernel<8><<<pg, kParseThreads, 0, st>>>(P); else seg_parse_kernel<4><<<pg, kParseThreads, 0, st>>>(P);
-    ctx->launches++;
-    CU_CHECK(ctx, cudaGetLastError());
-    if (end_bit) {
-        if ((rc = fetch_ctrl(ctx, st))) return rc;
-        if (ctx->h_ctrl->err & 2u) return fail(ctx, DCT3D_E_STREAM, "malformed Exp-Golomb code in stream");
-        if (ctx->h_ctrl->err & 4u) return fail(ctx, DCT3D_E_STREAM, "Exp-Golomb stream truncated");
-        *end_bit = ctx->h_ctrl->end_bit;
-    }
+    if (ctx->h_ctrl->err & 2u) return fail(ctx, DCT3D_E_STREAM, "malformed Exp-Golomb code in stream");
+    if (ctx->h_ctrl->err & 4u) return fail(ctx, DCT3D_E_STREAM, "Exp-Golomb stream truncated");
+    if (end_bit) *end_bit = ctx->h_ctrl->end_bit;
     return DCT3D_OK;
 }
 
