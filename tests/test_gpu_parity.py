@@ -333,3 +333,69 @@ def test_sharded_ranges_equal_one_shot(codec_mod, synth, world):
             lo, hi = sh.slab_range(F // 8, g, world)
             fr, end = c.stream_decode(one, offs[g], (hi - lo) * 8)
             assert end == offs[g + 1] and (fr == full[lo * 8:hi * 8]).all()
+
+
+def _gpu_clip(W, H, F, seed):
+    import torch
+    bench = __import__("bench")
+    return bench.synth_clip_torch(W, H, F, seed, torch.device("cuda", 0))
+
+
+@pytest.mark.parametrize("W,H,F,cube", [(1920, 1080, 256, 8), (3840, 2160, 32, 8), (1920, 1080, 64, 4)])
+def test_full_size_configs_properties(codec_mod, W, H, F, cube):
+    """BASELINE configs at full frame size (config 2 in full; config 3's 4K frames and config 4's 4^3 cubes on
+    a shorter clip): size-independent properties, all device-resident.
+      * the fused stream equals the Exp-Golomb coding of the cubes the quantise entry point returns;
+      * decode(encode(x)) equals reconstruct(quantise(x));
+      * index discovery finds exactly the cubes that were coded (eg_decode == quantise);
+      * slab-range sharding (4 ranges) concatenates to the one-shot stream;
+      * the lossy round trip stays close to the source."""
+    import torch
+    sh = pkg("sharding")
+    frames = _gpu_clip(W, H, F, 5)
+    N = W * H * F
+    cap = N // 2 + 4096
+    dev = frames.device
+    with make(codec_mod, W, H, cube) as c:
+        d_stream = torch.zeros(cap, dtype=torch.uint8, device=dev)
+        end = c.encode_u8_dev(frames, F, d_stream, cap)
+        nbytes = end // 8 + 1
+        q = torch.empty(N, dtype=torch.int16, device=dev)
+        c.quantize_u8_dev(frames, F, q)
+        torch.cuda.synchronize()
+        # stage path: cubes -> stream must be the same bits
+        d2 = torch.zeros(cap, dtype=torch.uint8, device=dev)
+        e2 = C_u64()
+        c._check(c.L.dct3d_eg_encode_i16_dev(c.h, q.data_ptr(), N // cube ** 3, 0, d2.data_ptr(), cap, e2, 0))
+        torch.cuda.synchronize()
+        assert e2.value == end and torch.equal(d2[:nbytes], d_stream[:nbytes])
+        # decode side
+        out = torch.empty_like(frames)
+        dend = c.decode_u8_dev(d_stream, nbytes, F, out)
+        rec = torch.empty_like(frames)
+        c.reconstruct_i16_dev(q, F, rec)
+        q2 = torch.empty_like(q)
+        e3 = C_u64()
+        c._check(c.L.dct3d_eg_decode_i16_dev(c.h, d_stream.data_ptr(), nbytes, 0, N // cube ** 3, q2.data_ptr(), e3, 0))
+        torch.cuda.synchronize()
+        assert dend == end == e3.value
+        assert torch.equal(out, rec) and torch.equal(q, q2)
+        err = (out.to(torch.int16) - frames.to(torch.int16)).abs()
+        assert float(err.float().mean()) < 6.0 and int(err.max()) < 80
+        # sharding: 4 slab ranges from bit 0 each, concatenated on the host
+        host_one = d_stream[:nbytes].cpu().numpy()
+        parts, nb = [], []
+        nsl = F // cube
+        for g in range(4):
+            lo, hi = sh.slab_range(nsl, g, 4)
+            part = torch.zeros(cap, dtype=torch.uint8, device=dev)
+            e = c.encode_u8_dev(frames[lo * cube:hi * cube], (hi - lo) * cube, part, cap)
+            parts.append(part[: e // 8 + 1].cpu().numpy())
+            nb.append(e)
+        cat, total = sh.concatenate(parts, nb)
+        assert total == end and cat.tobytes() == host_one.tobytes()
+
+
+def C_u64():
+    import ctypes
+    return ctypes.c_uint64()
