@@ -50,6 +50,10 @@ struct dct3d_ctx {
     int num_sms = 0;
     int use_tma = 1;
     int debug = 0;
+    int reuse_zeroed = 0;            // option: see dct3d_set_option
+    const void *clean_ptr = nullptr; // stream buffer known to be zero beyond clean_dirty bytes
+    size_t clean_cap = 0, clean_dirty = 0;
+    int occ_cache[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // cached occupancy / attribute set-up per kernel variant
     long launches = 0;
     cudaStream_t stream = nullptr;
     std::string err;
@@ -193,9 +197,11 @@ int launch_encode(dct3d_ctx *ctx, const EncParams &P, const CUtensorMap &tm, cud
 {
     auto kern = encode_kernel<C, MODE>;
     const int smem = EncSmem<C>::TOTAL;
-    CU_CHECK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    int occ = 0;
-    CU_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem));
+    int &occ = ctx->occ_cache[(C == 8 ? 0 : 2) + MODE];
+    if (occ == 0) {
+        CU_CHECK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CU_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem));
+    }
     if (occ < 1) return fail(ctx, DCT3D_E_CUDA, "encode kernel does not fit on an SM");
     const long long grid = std::min<long long>(P.L.ntiles, (long long)ctx->num_sms * occ);
     if (MODE == MODE_ZZ) cudaEventRecord(ctx->ev[0], st);
@@ -223,15 +229,19 @@ int fetch_ctrl(dct3d_ctx *ctx, cudaStream_t st)
     return DCT3D_OK;
 }
 
-// zero-fill the stream from the byte after start_bit's byte (the partial byte is kept)
+// zero-fill the stream from the byte after start_bit's byte (the partial byte is kept).  With option
+// "reuse_zeroed" a buffer this context packed into before (same pointer and capacity) is only wiped up to
+// where that call wrote: everything beyond is still zero from the previous wipe.
 int zero_stream(dct3d_ctx *ctx, void *d_stream, size_t cap, uint64_t start_bit, cudaStream_t st)
 {
     const size_t first = (size_t)((start_bit + 7) / 8);
-    if (start_bit % 8 == 0) {
-        if (cap > first) CU_CHECK(ctx, cudaMemsetAsync((uint8_t *)d_stream + first, 0, cap - first, st));
-    } else if (cap > first) {
-        CU_CHECK(ctx, cudaMemsetAsync((uint8_t *)d_stream + first, 0, cap - first, st));
-    }
+    size_t upto = cap;
+    if (ctx->reuse_zeroed && d_stream == ctx->clean_ptr && cap == ctx->clean_cap && ctx->clean_dirty)
+        upto = std::min(cap, ctx->clean_dirty + 64);
+    if (upto > first) CU_CHECK(ctx, cudaMemsetAsync((uint8_t *)d_stream + first, 0, upto - first, st));
+    ctx->clean_ptr = d_stream;
+    ctx->clean_cap = cap;
+    ctx->clean_dirty = 0;            // unknown until the end bit of this call is read back
     return DCT3D_OK;
 }
 
@@ -245,9 +255,11 @@ static int launch_reconstruct_zz(dct3d_ctx *ctx, const Layout &L, void *d_frames
 {
     auto kern = reconstruct_zz_kernel<C>;
     const int smem = RecSmem<C>::TOTAL;
-    CU_CHECK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    int occ = 0;
-    CU_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem));
+    int &occ = ctx->occ_cache[5];
+    if (occ == 0) {
+        CU_CHECK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CU_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem));
+    }
     const long long groups = (L.ncubes + Geo<C>::CPW - 1) / Geo<C>::CPW;
     const long long grid = std::min<long long>((groups + kWarps - 1) / kWarps, (long long)ctx->num_sms * std::max(occ, 1));
     cudaEventRecord(ctx->ev[2], st);
@@ -314,6 +326,7 @@ static int transform_host(dct3d_ctx *ctx, const T *in, T *out, size_t count, int
     SYNC(ctx);
     return DCT3D_OK;
 }
+
 
 }  // namespace
 
@@ -396,6 +409,7 @@ int dct3d_set_option(dct3d_ctx *ctx, const char *key, long value)
         return DCT3D_OK;
     }
     if (!strcmp(key, "debug")) { ctx->debug = (int)value; return DCT3D_OK; }
+    if (!strcmp(key, "reuse_zeroed")) { ctx->reuse_zeroed = value ? 1 : 0; ctx->clean_ptr = nullptr; return DCT3D_OK; }
     return fail(ctx, DCT3D_E_INVALID, "unknown option '%s'", key);
 }
 
@@ -432,9 +446,11 @@ static int run_pack_noreset(dct3d_ctx *ctx, EncParams &P, void *d_stream, size_t
     P.start_bit = start_bit;
     P.tile_status = (unsigned long long *)ctx->status.p;
     P.ticket = &dc->ticket; P.err = &dc->err; P.end_bit = &dc->end_bit;
-    int occ = 0;
-    if (ctx->C == 8) CU_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, eg_pack_kernel<8>, kPackThreads, 0));
-    else CU_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, eg_pack_kernel<4>, kPackThreads, 0));
+    int &occ = ctx->occ_cache[4];
+    if (occ == 0) {
+        if (ctx->C == 8) CU_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, eg_pack_kernel<8>, kPackThreads, 0));
+        else CU_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, eg_pack_kernel<4>, kPackThreads, 0));
+    }
     const long long grid = std::min<long long>(ptiles, (long long)ctx->num_sms * std::max(occ, 1));
     if (ctx->C == 8) eg_pack_kernel<8><<<(unsigned)grid, kPackThreads, 0, st>>>(P);
     else eg_pack_kernel<4><<<(unsigned)grid, kPackThreads, 0, st>>>(P);
@@ -446,6 +462,7 @@ static int run_pack_noreset(dct3d_ctx *ctx, EncParams &P, void *d_stream, size_t
         if (ctx->h_ctrl->err & 8u) return fail(ctx, DCT3D_E_CUDA, "tile look-back timed out");
         if (ctx->h_ctrl->err & 1u) return fail(ctx, DCT3D_E_OVERFLOW, "stream buffer of %zu bytes is too small", cap);
         *end_bit = ctx->h_ctrl->end_bit;
+        if (d_stream == ctx->clean_ptr) ctx->clean_dirty = (size_t)(ctx->h_ctrl->end_bit / 8) + 1;
     }
     return DCT3D_OK;
 }

@@ -160,6 +160,7 @@ def run_ours(args):
     c = codec.Codec(W, H, cube, device=local)
     if args.tma is not None:
         c.set_option("tma", args.tma)
+    c.set_option("reuse_zeroed", 1)     # the stream buffer is reused every step: wipe only what the last step wrote
     frames = synth_clip_torch(W, H, F, 1 + rank, dev)
     cap = N // 2 + 4096
     d_stream = torch.zeros(cap, dtype=torch.uint8, device=dev)

@@ -58,7 +58,11 @@ void dct3d_destroy(dct3d_ctx *ctx);
 /* Last error text of the context (or of the last failed dct3d_create if ctx is NULL). */
 const char *dct3d_last_error(const dct3d_ctx *ctx);
 
-/* Options: "tma" (1 = TMA tile loads [default when width % 16 == 0], 0 = plain vector loads).
+/* Options: "tma" (1 = TMA tile loads [default when width % 16 == 0], 0 = plain vector loads);
+ * "reuse_zeroed" (default 0): the device-resident encoders zero-fill the stream buffer before packing;
+ * with 1, a buffer the context packed into on its previous call (same pointer, same capacity, end bit
+ * read back) is only wiped up to where that call wrote -- the caller promises not to have written
+ * beyond it in between.
  * Statistics (dct3d_get_stat): "launches" = kernels launched by the context so far,
  * "flips_near_tie" is reported by the tests, not here. */
 int dct3d_set_option(dct3d_ctx *ctx, const char *key, long value);
