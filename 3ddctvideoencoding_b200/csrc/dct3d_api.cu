@@ -57,7 +57,7 @@ struct dct3d_ctx {
     long launches = 0;
     cudaStream_t stream = nullptr;
     std::string err;
-    DevBuf frames, bits, q, status, ctrl, seg, fa, fb, zz, cmask;
+    DevBuf frames, bits, q, status, ctrl, seg, fa, fb, zz, cmask, coo, coocnt;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // around encode_kernel / reconstruct_zz_kernel
     bool ev_valid[2] = {false, false};
     Ctrl *h_ctrl = nullptr;          // pinned
@@ -253,8 +253,8 @@ int zero_stream(dct3d_ctx *ctx, void *d_stream, size_t cap, uint64_t start_bit, 
 template <int C>
 static int launch_reconstruct_zz(dct3d_ctx *ctx, const Layout &L, void *d_frames, cudaStream_t st)
 {
-    auto kern = reconstruct_zz_kernel<C>;
-    const int smem = RecSmem<C>::TOTAL;
+    auto kern = reconstruct_coo_kernel<C>;
+    const int smem = CooSmem<C>::TOTAL;
     int &occ = ctx->occ_cache[5];
     if (occ == 0) {
         CU_CHECK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -263,7 +263,7 @@ static int launch_reconstruct_zz(dct3d_ctx *ctx, const Layout &L, void *d_frames
     const long long groups = (L.ncubes + Geo<C>::CPW - 1) / Geo<C>::CPW;
     const long long grid = std::min<long long>((groups + kWarps - 1) / kWarps, (long long)ctx->num_sms * std::max(occ, 1));
     cudaEventRecord(ctx->ev[2], st);
-    kern<<<(unsigned)grid, kThreads, smem, st>>>(L, (const int16_t *)ctx->zz.p, (const uint32_t *)ctx->cmask.p, (uint8_t *)d_frames);
+    kern<<<(unsigned)grid, kThreads, smem, st>>>(L, (const uint32_t *)ctx->coo.p, (const uint32_t *)ctx->coocnt.p, (uint8_t *)d_frames);
     cudaEventRecord(ctx->ev[3], st);
     ctx->ev_valid[1] = true;
     ctx->launches++;
@@ -389,7 +389,7 @@ void dct3d_destroy(dct3d_ctx *ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    for (DevBuf *b : {&ctx->frames, &ctx->bits, &ctx->q, &ctx->status, &ctx->ctrl, &ctx->seg, &ctx->fa, &ctx->fb, &ctx->zz, &ctx->cmask}) b->release();
+    for (DevBuf *b : {&ctx->frames, &ctx->bits, &ctx->q, &ctx->status, &ctx->ctrl, &ctx->seg, &ctx->fa, &ctx->fb, &ctx->zz, &ctx->cmask, &ctx->coo, &ctx->coocnt}) b->release();
     for (int i = 0; i < 4; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->h_ctrl) cudaFreeHost(ctx->h_ctrl);
     if (ctx->h_u64) cudaFreeHost(ctx->h_u64);
@@ -592,8 +592,8 @@ static int parse_common(dct3d_ctx *ctx, const void *d_stream, size_t nbytes, uin
     const size_t off_first = ((4 * n + 1) * 4 + 7) & ~(size_t)7;
     CU_CHECK(ctx, ctx->seg.reserve(off_first + (n + 1) * 8));
     CU_CHECK(ctx, ctx->ctrl.reserve(sizeof(Ctrl)));
-    CU_CHECK(ctx, ctx->zz.reserve(ncubes * CS * sizeof(int16_t)));
-    CU_CHECK(ctx, ctx->cmask.reserve(ncubes * 4));
+    CU_CHECK(ctx, ctx->coo.reserve(ncubes * CS * sizeof(uint32_t)));
+    CU_CHECK(ctx, ctx->coocnt.reserve(ncubes * 4));
     P.seg_count = (unsigned int *)ctx->seg.p;
     P.seg_over = P.seg_count + n;
     P.seg_used = P.seg_over + n + 1;
@@ -601,11 +601,11 @@ static int parse_common(dct3d_ctx *ctx, const void *d_stream, size_t nbytes, uin
     P.seg_first = (unsigned long long *)((uint8_t *)ctx->seg.p + off_first);
     Ctrl *dc = (Ctrl *)ctx->ctrl.p;
     P.changed = &dc->changed; P.err = &dc->err; P.end_bit = &dc->end_bit; P.nwork = &dc->nwork;
-    P.zzg = (int16_t *)ctx->zz.p;
-    P.cmask = (uint32_t *)ctx->cmask.p;
+    P.coo = (uint32_t *)ctx->coo.p;
+    P.coo_cnt = (uint32_t *)ctx->coocnt.p;
     CU_CHECK(ctx, cudaMemsetAsync(ctx->ctrl.p, 0, sizeof(Ctrl), st));
     CU_CHECK(ctx, cudaMemsetAsync(P.seg_over, 0, 4, st));
-    CU_CHECK(ctx, cudaMemsetAsync(P.cmask, 0, ncubes * 4, st));
+    CU_CHECK(ctx, cudaMemsetAsync(P.coo_cnt, 0, ncubes * 4, st));
     const unsigned sb = kSegThreads, sg = (unsigned)((P.nseg + sb - 1) / sb);
     seg_scan_kernel<<<sg, sb, 0, st>>>(P);
     ctx->launches++;
@@ -642,7 +642,7 @@ static int parse_common(dct3d_ctx *ctx, const void *d_stream, size_t nbytes, uin
             if ((rc = fix_round()) || (rc = fetch_ctrl(ctx, st))) return rc;
         }
         CU_CHECK(ctx, cudaMemsetAsync(&dc->err, 0, 4, st));
-        CU_CHECK(ctx, cudaMemsetAsync(P.cmask, 0, ncubes * 4, st));
+        CU_CHECK(ctx, cudaMemsetAsync(P.coo_cnt, 0, ncubes * 4, st));
         if ((rc = prefix_and_parse())) return rc;
         CU_CHECK(ctx, cudaMemcpyAsync(ctx->h_u64, P.seg_first + n, 8, cudaMemcpyDeviceToHost, st));
         if ((rc = fetch_ctrl(ctx, st))) return rc;
@@ -668,12 +668,13 @@ int dct3d_eg_decode_i16_dev(dct3d_ctx *ctx, const void *d_stream, size_t nbytes,
     memset(&P, 0, sizeof P);
     P.L = make_layout(ctx->W, ctx->H, ctx->C, 0);
     P.L.ncubes = (long long)ncubes;
-    P.zzg = (int16_t *)ctx->zz.p;
-    P.cmask = (uint32_t *)ctx->cmask.p;
+    P.coo = (uint32_t *)ctx->coo.p;
+    P.coo_cnt = (uint32_t *)ctx->coocnt.p;
     P.qcubes = (int16_t *)d_qcubes;
+    CU_CHECK(ctx, cudaMemsetAsync(d_qcubes, 0, ncubes * (size_t)ctx->C * ctx->C * ctx->C * sizeof(int16_t), st));
     const long long grid = std::min<long long>(((long long)ncubes + kWarps - 1) / kWarps, (long long)ctx->num_sms * 16);
-    if (ctx->C == 8) zz_scatter_kernel<8><<<(unsigned)grid, kThreads, 0, st>>>(P);
-    else zz_scatter_kernel<4><<<(unsigned)grid, kThreads, 0, st>>>(P);
+    if (ctx->C == 8) coo_scatter_kernel<8><<<(unsigned)grid, kThreads, 0, st>>>(P);
+    else coo_scatter_kernel<4><<<(unsigned)grid, kThreads, 0, st>>>(P);
     ctx->launches++;
     CU_CHECK(ctx, cudaGetLastError());
     return DCT3D_OK;

@@ -698,8 +698,10 @@ struct DecParams {
     unsigned int *changed;              // fix-up flag
     unsigned int *err;                  // bit1 = malformed, bit2 = truncated
     unsigned long long *end_bit;        // out: first bit after the last code
-    int16_t *zzg;                       // zig-zag chunk scratch [cube][CS]
-    uint32_t *cmask;                    // [cube], zeroed before seg_parse_kernel
+    int16_t *zzg;                       // zig-zag chunk scratch [cube][CS] (zz_scatter_kernel input)
+    uint32_t *cmask;                    // [cube] chunk masks (zz_scatter_kernel input)
+    uint32_t *coo;                      // [cube][CS] non-zero list: natural index << 16 | value (sparsely touched)
+    uint32_t *coo_cnt;                  // [cube] entries in the list, zeroed before seg_parse_kernel
     int16_t *qcubes;                    // natural-order cubes (zz_scatter_kernel)
     uint8_t *frames;
 };
@@ -818,57 +820,40 @@ seg_prefix_kernel(const DecParams P, unsigned long long *tile_status, unsigned i
     }
 }
 
-// Every thread re-walks its segment, now knowing the index of its first code, and writes the
-// non-zero coefficients into the zig-zag chunk scratch (same format the encoder's kernel 1
-// produces): a thread owns the 16-coefficient chunks that START among its codes, so it skips up to
-// 15 leading codes (owned by its predecessor) and runs up to 15 codes past its segment.  Chunks are
-// assembled in a per-thread shared-memory slot and stored whole (32 B); cmask (zeroed beforehand)
-// collects the non-zero chunks of every cube.
+// Every thread re-walks its segment, now knowing the index of its first code, and appends every
+// non-zero coefficient to its cube's list: (natural index << 16 | value) at slot atomicAdd(count).
+// The lists are dense-addressed ([cube][CS] words) and sparsely touched (14 entries = two sectors per
+// cube on natural content); their order inside a cube does not matter to the inverse kernel.
 constexpr int kParseThreads = kSegThreads;
-constexpr int kStageWords = 10;   // 40-byte stride: 32 B of data + padding against bank conflicts
 
 template <int C>
 __global__ void __launch_bounds__(kParseThreads)
 seg_parse_kernel(const DecParams P)
 {
     using G = Geo<C>;
-    __shared__ __align__(8) uint32_t s_stage[kParseThreads * kStageWords];
     __shared__ uint32_t s_words[kStageSmem];
     const unsigned long long k = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
     const StagedSource src = stage_stream(s_words, P.words, P.nwords, P.start_bit, blockIdx.x * (unsigned long long)kParseThreads);
     if (k >= P.nseg) return;
     const unsigned long long ncodes = (unsigned long long)P.L.ncubes * G::CS;
     unsigned long long cur = P.seg_first[k];
-    const unsigned long long nxt = P.seg_first[k + 1];
-    const unsigned long long lo = (cur + 15) & ~15ull;
-    unsigned long long hi = (nxt + 15) & ~15ull;
+    unsigned long long hi = P.seg_first[k + 1];
     if (hi > ncodes) hi = ncodes;
-    if (lo >= hi) return;
-    uint32_t *stage = s_stage + threadIdx.x * kStageWords;
-    int16_t *stage16 = reinterpret_cast<int16_t *>(stage);
-#pragma unroll
-    for (int i = 0; i < 8; i++) stage[i] = 0;
-    bool dirty = false;
-    auto flush = [&](unsigned long long chunk) {
-        uint2 *dst = reinterpret_cast<uint2 *>(P.zzg + chunk * 16);
-        const uint2 *src = reinterpret_cast<const uint2 *>(stage);
-#pragma unroll
-        for (int i = 0; i < 4; i++) { dst[i] = src[i]; }
-#pragma unroll
-        for (int i = 0; i < 8; i++) stage[i] = 0;
-        atomicOr(P.cmask + chunk / G::CHUNKS, 1u << (unsigned)(chunk % G::CHUNKS));
-        dirty = false;
-    };
+    if (cur >= hi) return;
+    const uint16_t *lin = zz_lin<C>();
     BitReader<StagedSource> br(src, src.rel(P.start_bit + k * (unsigned long long)P.seg_bits) + P.seg_over[k]);
+    // the slot of an entry comes back from an atomicAdd; the entry is stored one non-zero code later so
+    // that the atomic's latency is not on the parse loop's dependency chain
+    bool pend = false;
+    uint32_t pend_slot = 0, pend_entry = 0;
+    unsigned long long pend_cube = 0;
     while (cur < hi) {
         // one iteration = a run of one-bits (zero coefficients) followed by one longer code
         br.refill();
         unsigned long long ones = (unsigned)clz32(~br.hi);
         const unsigned long long room = hi - cur;
         if (ones > room) ones = room;
-        const unsigned long long nc = cur + ones;
-        if (dirty && (nc >> 4) != (cur >> 4)) flush(cur >> 4);
-        cur = nc;
+        cur += ones;
         br.skip((int)ones);
         if (cur >= hi) break;
         br.refill();
@@ -876,31 +861,33 @@ seg_parse_kernel(const DecParams P)
         uint32_t m;
         const uint32_t at = br.pos;
         if (!br.take_code(m)) { atomicOr(P.err, at + 17u >= src.rel(P.nbits_total) ? 4u : 2u); return; }
-        if (cur >= lo) {
-            stage16[cur & 15] = (int16_t)eg_unmap(m);
-            dirty = true;
-        }
+        if (pend) P.coo[pend_cube * G::CS + pend_slot] = pend_entry;
+        const unsigned long long cube = cur / G::CS;
+        const uint32_t pos = (uint32_t)(cur - cube * G::CS);
+        pend_slot = atomicAdd(P.coo_cnt + cube, 1u);
+        pend_entry = ((uint32_t)lin[pos] << 16) | ((uint32_t)eg_unmap(m) & 0xffffu);
+        pend_cube = cube;
+        pend = true;
         cur++;
-        if (dirty && (cur & 15) == 0) flush((cur - 1) >> 4);
     }
+    if (pend) P.coo[pend_cube * G::CS + pend_slot] = pend_entry;
     if (hi == ncodes) *P.end_bit = src.w0 * 32ull + br.pos;
 }
 
-// zig-zag chunk scratch -> dense natural-order int16 cubes (dct3d_eg_decode_i16).  Warp per cube.
+// non-zero lists -> dense natural-order int16 cubes (dct3d_eg_decode_i16; qcubes zeroed beforehand).
 template <int C>
 __global__ void __launch_bounds__(kThreads)
-zz_scatter_kernel(const DecParams P)
+coo_scatter_kernel(const DecParams P)
 {
     using G = Geo<C>;
     const int lane = threadIdx.x & 31;
     const long long wid = (long long)blockIdx.x * kWarps + (threadIdx.x >> 5);
     const long long nw = (long long)gridDim.x * kWarps;
-    const uint16_t *lin = zz_lin<C>();
     for (long long cube = wid; cube < P.L.ncubes; cube += nw) {
-        const uint32_t cm = P.cmask[cube];
-        for (int pos = lane; pos < G::CS; pos += 32) {
-            const int16_t v = ((cm >> (pos >> 4)) & 1u) ? P.zzg[(size_t)cube * G::CS + pos] : (int16_t)0;
-            P.qcubes[(size_t)cube * G::CS + lin[pos]] = v;
+        const uint32_t n = min(P.coo_cnt[cube], (uint32_t)G::CS);
+        for (uint32_t i = lane; i < n; i += 32) {
+            const uint32_t e = P.coo[(size_t)cube * G::CS + i];
+            P.qcubes[(size_t)cube * G::CS + (e >> 16)] = (int16_t)(e & 0xffffu);
         }
     }
 }
@@ -1059,6 +1046,89 @@ reconstruct_zz_kernel(const Layout L, const int16_t *__restrict__ zzg, const uin
         for (int k = 0; k < ITER; k++) { m0[k] = m1[k]; m1[k] = m2[k]; }
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+// Non-zero lists -> u8 frames (the decoder's inverse kernel).  Per warp and group of CPW cubes:
+// C lanes per cube scatter the cube's entries into a natural-order int16 cube in shared memory that
+// is kept all-zero (the same lanes wipe their entries afterwards); every thread then reads the C
+// rows (k0, k1 = lane) it needs with LDS.128, conflict-free.  Counts and the first 3*C entries of the
+// NEXT group are prefetched into registers while the current group is transformed.
+template <int C>
+struct CooSmem {
+    using G = Geo<C>;
+    static constexpr int NAT_WARP = G::CPW * G::CS * 2;            // bytes: CPW natural-order int16 cubes
+    static constexpr int WARP_BYTES = NAT_WARP + Xch<C, float>::WARP_BYTES;
+    static constexpr int TOTAL = kWarps * WARP_BYTES;
+};
+
+template <int C>
+__global__ void __launch_bounds__(kThreads, 4)
+reconstruct_coo_kernel(const Layout L, const uint32_t *__restrict__ coo, const uint32_t *__restrict__ coo_cnt,
+                       uint8_t *__restrict__ frames)
+{
+    using G = Geo<C>;
+    using S = CooSmem<C>;
+    constexpr int PRE = 3;                                          // prefetched entries per lane
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int cl = lane / C, r = lane % C;
+    int16_t *nat = reinterpret_cast<int16_t *>(smem + warp * S::WARP_BYTES) + cl * G::CS;   // this thread's cube
+    uint8_t *xbuf = smem + warp * S::WARP_BYTES + S::NAT_WARP;
+    float dq[G::NDIAG];
+#pragma unroll
+    for (int s = 0; s < G::NDIAG; s++) dq[s] = (float)quant_divisor(s + r) * lane_scale<C>(r);
+    for (int i = lane; i < S::NAT_WARP / 16; i += 32) reinterpret_cast<uint4 *>(smem + warp * S::WARP_BYTES)[i] = make_uint4(0, 0, 0, 0);
+    __syncwarp();
+
+    const long long ngroups = (L.ncubes + G::CPW - 1) / G::CPW;
+    const long long stride = (long long)gridDim.x * kWarps;
+    long long g = (long long)blockIdx.x * kWarps + warp;
+    uint32_t cnt_n = 0, e_n[PRE];
+    auto prefetch = [&](long long grp) {
+        const long long cube = grp * G::CPW + cl;
+        const bool ok = grp < ngroups && cube < L.ncubes;
+        cnt_n = ok ? min(__ldg(coo_cnt + cube), (uint32_t)G::CS) : 0u;
+#pragma unroll
+        for (int k = 0; k < PRE; k++) e_n[k] = ok ? __ldg(coo + (size_t)cube * G::CS + r + k * C) : 0u;   // speculative: valid iff < cnt
+    };
+    prefetch(g);
+    for (; g < ngroups; g += stride) {
+        const uint32_t cnt = cnt_n;
+        uint32_t e[PRE];
+#pragma unroll
+        for (int k = 0; k < PRE; k++) e[k] = e_n[k];
+        const long long cube = g * G::CPW + cl;
+        prefetch(g + stride);
+        // scatter this cube's entries (lane r of the cube takes entries r, r+C, r+2C, ...)
+#pragma unroll
+        for (int k = 0; k < PRE; k++)
+            if ((uint32_t)(r + k * C) < cnt) nat[e[k] >> 16] = (int16_t)(e[k] & 0xffffu);
+        for (uint32_t i = r + PRE * C; i < cnt; i += C) {
+            const uint32_t x = __ldg(coo + (size_t)cube * G::CS + i);
+            nat[x >> 16] = (int16_t)(x & 0xffffu);
+        }
+        __syncwarp();
+        float b[C][C];
+#pragma unroll
+        for (int k0 = 0; k0 < C; k0++) {
+            uint32_t w[4] = {0, 0, 0, 0};
+            const int16_t *row = nat + (k0 * C + r) * C;
+            if (C == 8) { const uint4 v = *reinterpret_cast<const uint4 *>(row); w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w; }
+            else { const uint2 v = *reinterpret_cast<const uint2 *>(row); w[0] = v.x; w[1] = v.y; }
+#pragma unroll
+            for (int k2 = 0; k2 < C; k2++) {
+                const int q = (int)(int16_t)((w[k2 / 2] >> ((k2 & 1) * 16)) & 0xffffu);
+                b[k0][k2] = (float)q * dq[k0 + k2];
+            }
+        }
+        __syncwarp();
+        // wipe what was scattered
+#pragma unroll
+        for (int k = 0; k < PRE; k++)
+            if ((uint32_t)(r + k * C) < cnt) nat[e[k] >> 16] = 0;
+        for (uint32_t i = r + PRE * C; i < cnt; i += C) nat[__ldg(coo + (size_t)cube * G::CS + i) >> 16] = 0;
+        idct_store<C>(b, xbuf, cl, r, cube < L.ncubes, L, cube, frames);
+    }
 }
 
 // int16 natural-order cubes -> u8 frames: dequantise, inverse butterflies, clamp, truncate.
