@@ -925,129 +925,6 @@ __device__ __forceinline__ void idct_store(float (&b)[C][C], uint8_t *xbuf, int 
     }
 }
 
-// zig-zag chunk scratch + masks -> u8 frames.  Per warp and group of CPW cubes: the non-zero
-// chunks are copied global -> shared with cp.async (lane <-> chunk) one group AHEAD into the other
-// half of a double buffer, the chunk masks two groups ahead, so neither latency is exposed.  Each
-// thread then gathers its 64 coefficients through the same per-lane run bases the encoder
-// scatters with -- only the runs that touch a non-zero chunk -- dequantises and runs the inverse
-// transform.  The buffers are kept all-zero: a lane wipes the chunks it copied in.
-template <int C>
-struct RecSmem {
-    using G = Geo<C>;
-    static constexpr int ZZ_GROUP = G::CPW * G::ZZ_STRIDE * 2;     // bytes, one group of cubes
-    static constexpr int WARP_BYTES = 2 * ZZ_GROUP + Xch<C, float>::WARP_BYTES;
-    static constexpr int TOTAL = kWarps * WARP_BYTES;
-};
-
-__device__ __forceinline__ void cp_async16(void *dst, const void *src)
-{
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-}
-
-template <int C>
-__global__ void __launch_bounds__(kThreads, 4)
-reconstruct_zz_kernel(const Layout L, const int16_t *__restrict__ zzg, const uint32_t *__restrict__ cmask,
-                      uint8_t *__restrict__ frames)
-{
-    using G = Geo<C>;
-    using S = RecSmem<C>;
-    extern __shared__ __align__(1024) uint8_t smem[];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int cl = lane / C, r = lane % C;
-    uint8_t *wbase = smem + warp * S::WARP_BYTES;
-    uint8_t *xbuf = wbase + 2 * S::ZZ_GROUP;
-    // per-lane run bases and, per diagonal, the mask of the (at most two) chunks the run lies in
-    uint32_t zb[G::NDIAG], rm[G::NDIAG];
-#pragma unroll
-    for (int s = 0; s < G::NDIAG; s++) {
-        zb[s] = zz_base<C>(r, s);
-        const int len = s < C ? s + 1 : 2 * C - 1 - s;
-        rm[s] = (1u << (zb[s] >> 4)) | (1u << ((zb[s] + len - 1) >> 4));
-    }
-    const float r5 = 5.0f * (float)r;
-    const float sj = lane_scale<C>(r);       // S[k1] expected by the scaled inverse butterflies
-    constexpr int ITER = (G::CPW * G::CHUNKS) / 32;   // chunk <-> lane rounds per group: 4 (C=8) / 1 (C=4)
-    for (int i = lane; i < 2 * S::ZZ_GROUP / 16; i += 32) reinterpret_cast<uint4 *>(wbase)[i] = make_uint4(0, 0, 0, 0);
-    __syncwarp();
-
-    const long long ngroups = (L.ncubes + G::CPW - 1) / G::CPW;
-    const long long stride = (long long)gridDim.x * kWarps;
-    long long g = (long long)blockIdx.x * kWarps + warp;
-    // masks of the cubes of a group, as the chunk-copy rounds need them: lane's cube in round k
-    auto load_masks = [&](long long grp, uint32_t (&m)[ITER]) {
-#pragma unroll
-        for (int k = 0; k < ITER; k++) {
-            const long long gc = grp * G::CPW + (k * 32 + lane) / G::CHUNKS;
-            m[k] = (grp < ngroups && gc < L.ncubes) ? __ldg(cmask + gc) : 0u;
-        }
-    };
-    auto issue_copy = [&](long long grp, const uint32_t (&m)[ITER], int buf) {
-#pragma unroll
-        for (int k = 0; k < ITER; k++) {
-            const int ci = k * 32 + lane;
-            const int c = ci / G::CHUNKS, chunk = ci % G::CHUNKS;
-            if ((m[k] >> chunk) & 1u) {
-                const int16_t *src = zzg + (size_t)(grp * G::CPW + c) * G::CS + chunk * 16;
-                int16_t *dst = reinterpret_cast<int16_t *>(wbase + buf * S::ZZ_GROUP) + c * G::ZZ_STRIDE + chunk * 16;
-                cp_async16(dst, src);
-                cp_async16(dst + 8, src + 8);
-            }
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    uint32_t m0[ITER], m1[ITER], m2[ITER];
-    load_masks(g, m0);
-    load_masks(g + stride, m1);
-    issue_copy(g, m0, 0);
-    int buf = 0;
-    for (; g < ngroups; g += stride, buf ^= 1) {
-        load_masks(g + 2 * stride, m2);                 // consumed two iterations from now
-        issue_copy(g + stride, m1, buf ^ 1);            // lands while this group is transformed
-        asm volatile("cp.async.wait_group 1;" ::: "memory");
-        __syncwarp();
-        const long long cube = g * G::CPW + cl;
-        // this thread's cube mask: round (cl * CHUNKS) / 32 of m0 (all lanes of that round hold it)
-        uint32_t cm;
-        if (G::CHUNKS == 32) {
-            cm = m0[0];
-#pragma unroll
-            for (int k = 1; k < ITER; k++) cm = cl == k ? m0[k] : cm;
-        } else {
-            cm = __shfl_sync(0xffffffffu, m0[0], cl * G::CHUNKS);
-        }
-        const int16_t *zz = reinterpret_cast<const int16_t *>(wbase + buf * S::ZZ_GROUP) + cl * G::ZZ_STRIDE;
-        float b[C][C];
-#pragma unroll
-        for (int k0 = 0; k0 < C; k0++) {
-#pragma unroll
-            for (int k2 = 0; k2 < C; k2++) {
-                const int s = k0 + k2;
-                const int k0min = s > C - 1 ? s - (C - 1) : 0;
-                // only runs that touch a non-zero chunk are read (everything else is zero)
-                float v = 0.0f;
-                if (cm & rm[s]) v = (float)(int)zz[zb[s] + (k0 - k0min)] * (fmaxf(1.0f, r5 + 5.0f * (float)s) * sj);
-                b[k0][k2] = v;
-            }
-        }
-        __syncwarp();
-#pragma unroll
-        for (int k = 0; k < ITER; k++) {
-            const int ci = k * 32 + lane;
-            const int chunk = ci % G::CHUNKS;
-            if ((m0[k] >> chunk) & 1u) {
-                uint4 *dst = reinterpret_cast<uint4 *>(reinterpret_cast<int16_t *>(wbase + buf * S::ZZ_GROUP) +
-                                                       (ci / G::CHUNKS) * G::ZZ_STRIDE + chunk * 16);
-                dst[0] = make_uint4(0, 0, 0, 0);
-                dst[1] = make_uint4(0, 0, 0, 0);
-            }
-        }
-        idct_store<C>(b, xbuf, cl, r, cube < L.ncubes, L, cube, frames);
-#pragma unroll
-        for (int k = 0; k < ITER; k++) { m0[k] = m1[k]; m1[k] = m2[k]; }
-    }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-}
-
 // Non-zero lists -> u8 frames (the decoder's inverse kernel).  Per warp and group of CPW cubes:
 // C lanes per cube scatter the cube's entries into a natural-order int16 cube in shared memory that
 // is kept all-zero (the same lanes wipe their entries afterwards); every thread then reads the C
@@ -1174,10 +1051,27 @@ reconstruct_kernel(const Layout L, const int16_t *__restrict__ qcubes, uint8_t *
 //   CUBEMAJOR = false: T planar [F][H][W] in and out      (Java's Transform boundary)
 // ------------------------------------------------------------------------------------------
 // C contiguous elements of T as 16-byte vectors (rows are 16-byte aligned in both layouts).
+__device__ __forceinline__ void ld_global_256(const void *p, uint4 &a, uint4 &b)
+{
+    asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
+}
+
 template <int C, typename T>
 __device__ __forceinline__ void load_row(const T *p, T (&row)[C], bool valid)
 {
     constexpr int NV = C * sizeof(T) / 16, VEC = 16 / sizeof(T);
+    if (NV % 2 == 0 && (reinterpret_cast<uintptr_t>(p) & 31) == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; i += 2) {
+            uint4 v0 = make_uint4(0, 0, 0, 0), v1 = make_uint4(0, 0, 0, 0);
+            if (valid) ld_global_256(reinterpret_cast<const uint4 *>(p) + i, v0, v1);
+            const T *p0 = reinterpret_cast<const T *>(&v0), *p1 = reinterpret_cast<const T *>(&v1);
+#pragma unroll
+            for (int e = 0; e < VEC; e++) { row[i * VEC + e] = p0[e]; row[(i + 1) * VEC + e] = p1[e]; }
+        }
+        return;
+    }
 #pragma unroll
     for (int i = 0; i < NV; i++) {
         uint4 v = make_uint4(0, 0, 0, 0);
@@ -1187,10 +1081,28 @@ __device__ __forceinline__ void load_row(const T *p, T (&row)[C], bool valid)
         for (int e = 0; e < VEC; e++) row[i * VEC + e] = pv[e];
     }
 }
+// one 256-bit store (sm_100: st.global.v8.b32) writes a whole 32-byte sector from a single lane
+__device__ __forceinline__ void st_global_256(void *p, const uint4 &a, const uint4 &b)
+{
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
+                 "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
+}
+
 template <int C, typename T>
 __device__ __forceinline__ void store_row(T *p, const T (&row)[C])
 {
     constexpr int NV = C * sizeof(T) / 16, VEC = 16 / sizeof(T);
+    if (NV % 2 == 0 && (reinterpret_cast<uintptr_t>(p) & 31) == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; i += 2) {
+            uint4 v0, v1;
+            T *p0 = reinterpret_cast<T *>(&v0), *p1 = reinterpret_cast<T *>(&v1);
+#pragma unroll
+            for (int e = 0; e < VEC; e++) { p0[e] = row[i * VEC + e]; p1[e] = row[(i + 1) * VEC + e]; }
+            st_global_256(reinterpret_cast<uint4 *>(p) + i, v0, v1);
+        }
+        return;
+    }
 #pragma unroll
     for (int i = 0; i < NV; i++) {
         uint4 v;

@@ -66,4 +66,3 @@ def test_sass_is_blackwell_native():
     out = subprocess.run(["cuobjdump", "-sass", pkg("_lib").lib_path()], capture_output=True, text=True).stdout
     assert "sm_100a" in out
     assert "UTMALDG" in out and "SYNCS" in out
-    assert "LDGSTS" in out                        # cp.async prefetch of the inverse kernel
