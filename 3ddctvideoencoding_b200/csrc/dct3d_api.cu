@@ -263,7 +263,7 @@ static int launch_reconstruct_zz(dct3d_ctx *ctx, const Layout &L, void *d_frames
     const long long groups = (L.ncubes + Geo<C>::CPW - 1) / Geo<C>::CPW;
     const long long grid = std::min<long long>((groups + kWarps - 1) / kWarps, (long long)ctx->num_sms * std::max(occ, 1));
     cudaEventRecord(ctx->ev[2], st);
-    kern<<<(unsigned)grid, kThreads, smem, st>>>(L, (const uint32_t *)ctx->coo.p, (const uint32_t *)ctx->coocnt.p, (uint8_t *)d_frames);
+    kern<<<(unsigned)grid, kThreads, smem, st>>>(L, (const uint32_t *)ctx->coo.p, (const unsigned long long *)ctx->coocnt.p, (uint8_t *)d_frames);
     cudaEventRecord(ctx->ev[3], st);
     ctx->ev_valid[1] = true;
     ctx->launches++;
@@ -587,25 +587,25 @@ static int parse_common(dct3d_ctx *ctx, const void *d_stream, size_t nbytes, uin
     P.start_bit = start_bit;
     P.seg_bits = kSegWords * 32;
     P.nseg = (P.nbits_total - start_bit + P.seg_bits - 1) / P.seg_bits;
-    // seg arrays: count[nseg] over[nseg+1] used[nseg] work[nseg] (u32) first[nseg+1] (u64)
+    // seg arrays: count[nseg] over[nseg+1] used[nseg] work[nseg] (u32) first[nseg+1] nzfirst[nseg+1] (u64)
     const size_t n = (size_t)P.nseg;
     const size_t off_first = ((4 * n + 1) * 4 + 7) & ~(size_t)7;
-    CU_CHECK(ctx, ctx->seg.reserve(off_first + (n + 1) * 8));
+    CU_CHECK(ctx, ctx->seg.reserve(off_first + 2 * (n + 1) * 8));
     CU_CHECK(ctx, ctx->ctrl.reserve(sizeof(Ctrl)));
-    CU_CHECK(ctx, ctx->coo.reserve(ncubes * CS * sizeof(uint32_t)));
-    CU_CHECK(ctx, ctx->coocnt.reserve(ncubes * 4));
+    CU_CHECK(ctx, ctx->coo.reserve(ncubes * CS * sizeof(uint32_t) + 256));   // worst case: every coefficient non-zero
+    CU_CHECK(ctx, ctx->coocnt.reserve((ncubes + 1) * 8));
     P.seg_count = (unsigned int *)ctx->seg.p;
     P.seg_over = P.seg_count + n;
     P.seg_used = P.seg_over + n + 1;
     P.seg_work = P.seg_used + n;
     P.seg_first = (unsigned long long *)((uint8_t *)ctx->seg.p + off_first);
+    P.seg_nzfirst = P.seg_first + n + 1;
     Ctrl *dc = (Ctrl *)ctx->ctrl.p;
     P.changed = &dc->changed; P.err = &dc->err; P.end_bit = &dc->end_bit; P.nwork = &dc->nwork;
     P.coo = (uint32_t *)ctx->coo.p;
-    P.coo_cnt = (uint32_t *)ctx->coocnt.p;
+    P.coo_start = (unsigned long long *)ctx->coocnt.p;
     CU_CHECK(ctx, cudaMemsetAsync(ctx->ctrl.p, 0, sizeof(Ctrl), st));
     CU_CHECK(ctx, cudaMemsetAsync(P.seg_over, 0, 4, st));
-    CU_CHECK(ctx, cudaMemsetAsync(P.coo_cnt, 0, ncubes * 4, st));
     const unsigned sb = kSegThreads, sg = (unsigned)((P.nseg + sb - 1) / sb);
     seg_scan_kernel<<<sg, sb, 0, st>>>(P);
     ctx->launches++;
@@ -618,11 +618,12 @@ static int parse_common(dct3d_ctx *ctx, const void *d_stream, size_t nbytes, uin
     };
     auto prefix_and_parse = [&]() -> int {
         const long long stiles = (long long)((P.nseg + kScanThreads * kScanItems - 1) / (kScanThreads * kScanItems));
-        CU_CHECK(ctx, ctx->status.reserve((size_t)stiles * 8));
-        CU_CHECK(ctx, cudaMemsetAsync(ctx->status.p, 0, (size_t)stiles * 8, st));
+        CU_CHECK(ctx, ctx->status.reserve((size_t)stiles * 16));
+        CU_CHECK(ctx, cudaMemsetAsync(ctx->status.p, 0, (size_t)stiles * 16, st));
         CU_CHECK(ctx, cudaMemsetAsync(&dc->ticket, 0, 4, st));
         const long long grid = std::min<long long>(stiles, (long long)ctx->num_sms * 8);
-        seg_prefix_kernel<<<(unsigned)grid, kScanThreads, 0, st>>>(P, (unsigned long long *)ctx->status.p, &dc->ticket);
+        seg_prefix_kernel<<<(unsigned)grid, kScanThreads, 0, st>>>(P, (unsigned long long *)ctx->status.p,
+                                                                   (unsigned long long *)ctx->status.p + stiles, &dc->ticket);
         const unsigned pg = (unsigned)((P.nseg + kParseThreads - 1) / kParseThreads);
         if (C == 8) seg_parse_kernel<8><<<pg, kParseThreads, 0, st>>>(P); else seg_parse_kernel<4><<<pg, kParseThreads, 0, st>>>(P);
         ctx->launches += 2;
@@ -642,7 +643,6 @@ static int parse_common(dct3d_ctx *ctx, const void *d_stream, size_t nbytes, uin
             if ((rc = fix_round()) || (rc = fetch_ctrl(ctx, st))) return rc;
         }
         CU_CHECK(ctx, cudaMemsetAsync(&dc->err, 0, 4, st));
-        CU_CHECK(ctx, cudaMemsetAsync(P.coo_cnt, 0, ncubes * 4, st));
         if ((rc = prefix_and_parse())) return rc;
         CU_CHECK(ctx, cudaMemcpyAsync(ctx->h_u64, P.seg_first + n, 8, cudaMemcpyDeviceToHost, st));
         if ((rc = fetch_ctrl(ctx, st))) return rc;
@@ -669,7 +669,7 @@ int dct3d_eg_decode_i16_dev(dct3d_ctx *ctx, const void *d_stream, size_t nbytes,
     P.L = make_layout(ctx->W, ctx->H, ctx->C, 0);
     P.L.ncubes = (long long)ncubes;
     P.coo = (uint32_t *)ctx->coo.p;
-    P.coo_cnt = (uint32_t *)ctx->coocnt.p;
+    P.coo_start = (unsigned long long *)ctx->coocnt.p;
     P.qcubes = (int16_t *)d_qcubes;
     CU_CHECK(ctx, cudaMemsetAsync(d_qcubes, 0, ncubes * (size_t)ctx->C * ctx->C * ctx->C * sizeof(int16_t), st));
     const long long grid = std::min<long long>(((long long)ncubes + kWarps - 1) / kWarps, (long long)ctx->num_sms * 16);

@@ -689,19 +689,20 @@ struct DecParams {
     unsigned long long start_bit;
     // index discovery
     unsigned int seg_bits; unsigned long long nseg;
-    unsigned int *seg_count;            // [nseg] codes starting in the segment
+    unsigned int *seg_count;            // [nseg] codes starting in the segment | non-zero codes << 16 | malformed << 31
     unsigned int *seg_over;             // [nseg+1] overhang INTO segment k (seg_over[0] = 0)
     unsigned int *seg_used;             // [nseg] entry overhang used for the current count
     unsigned int *seg_work;             // [nseg] worklist of segments to re-scan
     unsigned int *nwork;
-    unsigned long long *seg_first;      // [nseg+1] exclusive prefix of seg_count
+    unsigned long long *seg_first;      // [nseg+1] exclusive prefix of the code counts
+    unsigned long long *seg_nzfirst;    // [nseg+1] exclusive prefix of the non-zero code counts
     unsigned int *changed;              // fix-up flag
     unsigned int *err;                  // bit1 = malformed, bit2 = truncated
     unsigned long long *end_bit;        // out: first bit after the last code
     int16_t *zzg;                       // zig-zag chunk scratch [cube][CS] (zz_scatter_kernel input)
     uint32_t *cmask;                    // [cube] chunk masks (zz_scatter_kernel input)
-    uint32_t *coo;                      // [cube][CS] non-zero list: natural index << 16 | value (sparsely touched)
-    uint32_t *coo_cnt;                  // [cube] entries in the list, zeroed before seg_parse_kernel
+    uint32_t *coo;                      // non-zero coefficients of the whole stream, in stream order: natural index << 16 | value
+    unsigned long long *coo_start;      // [ncubes+1] first entry of every cube (CSR row pointers)
     int16_t *qcubes;                    // natural-order cubes (zz_scatter_kernel)
     uint8_t *frames;
 };
@@ -719,13 +720,13 @@ seg_scan_kernel(const DecParams P)
     const uint32_t eos = src.rel(P.nbits_total);
     uint32_t lim = seg0 + P.seg_bits;
     if (lim > eos) lim = eos;
-    uint32_t n = 0, next = 0;
+    uint32_t n = 0, next = 0, nz = 0;
     // A scan from a wrongly assumed entry point may run into an impossible code; that is only an
     // error if it is still there once the entry points have converged, so it is recorded per segment.
     unsigned int bad = 0;
     if (seg0 >= lim) { n = 0; next = seg0; }
-    else if (!eg_scan_segment(src, seg0, lim, eos, n, next)) { bad = 0x80000000u; n = 0; next = lim; }
-    P.seg_count[k] = n | bad;
+    else if (!eg_scan_segment(src, seg0, lim, eos, n, next, &nz)) { bad = 0x80000000u; n = 0; nz = 0; next = lim; }
+    P.seg_count[k] = n | (nz << 16) | bad;
     P.seg_used[k] = 0u;
     P.seg_over[k + 1] = next > lim ? next - lim : 0u;
 }
@@ -753,26 +754,27 @@ __global__ void seg_fix_kernel(const DecParams P)
         const uint32_t eos = src.rel(P.nbits_total);
         uint32_t lim = seg0 + P.seg_bits;
         if (lim > eos) lim = eos;
-        uint32_t n = 0, next = 0;
+        uint32_t n = 0, next = 0, nz = 0;
         unsigned int bad = 0;
         if (seg0 + entry >= lim) { n = 0; next = seg0 + entry; }
-        else if (!eg_scan_segment(src, seg0 + entry, lim, eos, n, next)) { bad = 0x80000000u; n = 0; next = lim; }
-        P.seg_count[k] = n | bad;
+        else if (!eg_scan_segment(src, seg0 + entry, lim, eos, n, next, &nz)) { bad = 0x80000000u; n = 0; nz = 0; next = lim; }
+        P.seg_count[k] = n | (nz << 16) | bad;
         P.seg_used[k] = entry;
         const unsigned int over = next > lim ? next - lim : 0u;
         if (P.seg_over[k + 1] != over) { P.seg_over[k + 1] = over; *P.changed = 1u; }
     }
 }
 
-// Exclusive prefix sum of seg_count over all segments: 1024 segments per CTA tile, block scan,
-// decoupled look-back across tiles (same machinery as the bit packer).  seg_first[nseg] = total.
+// Exclusive prefix sums over all segments of (a) the code counts and (b) the non-zero code counts:
+// 1024 segments per CTA tile, block scan, decoupled look-back across tiles (same machinery as the
+// bit packer; one status array per quantity).  seg_first[nseg] / seg_nzfirst[nseg] = totals.
 constexpr int kScanThreads = 256, kScanItems = 4;
 
 __global__ void __launch_bounds__(kScanThreads)
-seg_prefix_kernel(const DecParams P, unsigned long long *tile_status, unsigned int *ticket)
+seg_prefix_kernel(const DecParams P, unsigned long long *status_codes, unsigned long long *status_nz, unsigned int *ticket)
 {
-    __shared__ unsigned long long s_wsum[kScanThreads / 32];
-    __shared__ unsigned long long s_off;
+    __shared__ unsigned long long s_wsum[2][kScanThreads / 32];
+    __shared__ unsigned long long s_off[2];
     __shared__ long long s_tile;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int TILE = kScanThreads * kScanItems;
@@ -783,47 +785,57 @@ seg_prefix_kernel(const DecParams P, unsigned long long *tile_status, unsigned i
         const long long tile = s_tile;
         if (tile >= ntiles) break;
         const unsigned long long k0 = (unsigned long long)tile * TILE + (unsigned long long)tid * kScanItems;
-        unsigned long long v[kScanItems], sum = 0;
+        unsigned long long v[2][kScanItems], sum[2] = {0, 0}, incl[2];
 #pragma unroll
         for (int i = 0; i < kScanItems; i++) {
-            unsigned long long x = k0 + i < P.nseg ? P.seg_count[k0 + i] : 0ull;
-            if (x & 0x80000000ull) { atomicOr(P.err, 2u); x &= 0x7fffffffull; }   // still malformed after convergence
-            v[i] = x;
-            sum += x;
+            unsigned int x = k0 + i < P.nseg ? P.seg_count[k0 + i] : 0u;
+            if (x & 0x80000000u) { atomicOr(P.err, 2u); x = 0; }                  // still malformed after convergence
+            v[0][i] = x & 0xffffu;
+            v[1][i] = (x >> 16) & 0x7fffu;
+            sum[0] += v[0][i];
+            sum[1] += v[1][i];
         }
-        unsigned long long incl = sum;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { const unsigned long long o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
-        if (lane == 31) s_wsum[warp] = incl;
+        for (int q = 0; q < 2; q++) {
+            incl[q] = sum[q];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const unsigned long long o = __shfl_up_sync(0xffffffffu, incl[q], d); if (lane >= d) incl[q] += o; }
+            if (lane == 31) s_wsum[q][warp] = incl[q];
+        }
         __syncthreads();
-        if (warp == 0) {
-            const unsigned long long w = lane < kScanThreads / 32 ? s_wsum[lane] : 0ull;
+        if (warp < 2) {
+            const int q = warp;
+            const unsigned long long w = lane < kScanThreads / 32 ? s_wsum[q][lane] : 0ull;
             unsigned long long wi = w;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) { const unsigned long long o = __shfl_up_sync(0xffffffffu, wi, d); if (lane >= d) wi += o; }
-            if (lane < kScanThreads / 32) s_wsum[lane] = wi - w;
+            if (lane < kScanThreads / 32) s_wsum[q][lane] = wi - w;
             const unsigned long long total = __shfl_sync(0xffffffffu, wi, 31);
-            const unsigned long long off = tile_lookback(tile_status, tile, total, 0ull, lane, P.err);
+            const unsigned long long off = tile_lookback(q == 0 ? status_codes : status_nz, tile, total, 0ull, lane, P.err);
             if (lane == 0) {
-                s_off = off;
-                if (tile == ntiles - 1) P.seg_first[P.nseg] = off + total;
+                s_off[q] = off;
+                if (tile == ntiles - 1) (q == 0 ? P.seg_first : P.seg_nzfirst)[P.nseg] = off + total;
             }
         }
         __syncthreads();
-        unsigned long long run = s_off + s_wsum[warp] + incl - sum;
 #pragma unroll
-        for (int i = 0; i < kScanItems; i++) {
-            if (k0 + i < P.nseg) P.seg_first[k0 + i] = run;
-            run += v[i];
+        for (int q = 0; q < 2; q++) {
+            unsigned long long run = s_off[q] + s_wsum[q][warp] + incl[q] - sum[q];
+            unsigned long long *dst = q == 0 ? P.seg_first : P.seg_nzfirst;
+#pragma unroll
+            for (int i = 0; i < kScanItems; i++) {
+                if (k0 + i < P.nseg) dst[k0 + i] = run;
+                run += v[q][i];
+            }
         }
         __syncthreads();
     }
 }
 
-// Every thread re-walks its segment, now knowing the index of its first code, and appends every
-// non-zero coefficient to its cube's list: (natural index << 16 | value) at slot atomicAdd(count).
-// The lists are dense-addressed ([cube][CS] words) and sparsely touched (14 entries = two sectors per
-// cube on natural content); their order inside a cube does not matter to the inverse kernel.
+// Every thread re-walks its segment, now knowing the index of its first code AND the rank of its
+// first non-zero code in the whole stream, and writes every non-zero coefficient as
+// (natural index << 16 | value) at its rank: a CSR matrix of the cubes with no atomics and contiguous
+// stores.  The thread that passes a cube's first code records the cube's row pointer.
 constexpr int kParseThreads = kSegThreads;
 
 template <int C>
@@ -840,38 +852,37 @@ seg_parse_kernel(const DecParams P)
     unsigned long long hi = P.seg_first[k + 1];
     if (hi > ncodes) hi = ncodes;
     if (cur >= hi) return;
+    unsigned long long zrank = P.seg_nzfirst[k];
+    uint32_t pos = (uint32_t)(cur % G::CS);            // position inside the current cube
+    unsigned long long cube = cur / G::CS;
     const uint16_t *lin = zz_lin<C>();
     BitReader<StagedSource> br(src, src.rel(P.start_bit + k * (unsigned long long)P.seg_bits) + P.seg_over[k]);
-    // the slot of an entry comes back from an atomicAdd; the entry is stored one non-zero code later so
-    // that the atomic's latency is not on the parse loop's dependency chain
-    bool pend = false;
-    uint32_t pend_slot = 0, pend_entry = 0;
-    unsigned long long pend_cube = 0;
     while (cur < hi) {
-        // one iteration = a run of one-bits (zero coefficients) followed by one longer code
+        if (pos == 0) P.coo_start[cube] = zrank;       // this thread owns the cube's first code
+        // one iteration = a run of one-bits (zero coefficients, cut at the cube end) + one longer code
         br.refill();
-        unsigned long long ones = (unsigned)clz32(~br.hi);
+        uint32_t ones = (uint32_t)clz32(~br.hi);
         const unsigned long long room = hi - cur;
-        if (ones > room) ones = room;
+        if (ones > room) ones = (uint32_t)room;
+        if (ones > (uint32_t)G::CS - pos) ones = (uint32_t)G::CS - pos;
         cur += ones;
+        pos += ones;
         br.skip((int)ones);
+        if (pos == (uint32_t)G::CS) { pos = 0; cube++; continue; }
         if (cur >= hi) break;
         br.refill();
         if (br.hi >> 31) continue;
         uint32_t m;
         const uint32_t at = br.pos;
         if (!br.take_code(m)) { atomicOr(P.err, at + 17u >= src.rel(P.nbits_total) ? 4u : 2u); return; }
-        if (pend) P.coo[pend_cube * G::CS + pend_slot] = pend_entry;
-        const unsigned long long cube = cur / G::CS;
-        const uint32_t pos = (uint32_t)(cur - cube * G::CS);
-        pend_slot = atomicAdd(P.coo_cnt + cube, 1u);
-        pend_entry = ((uint32_t)lin[pos] << 16) | ((uint32_t)eg_unmap(m) & 0xffffu);
-        pend_cube = cube;
-        pend = true;
+        P.coo[zrank++] = ((uint32_t)lin[pos] << 16) | ((uint32_t)eg_unmap(m) & 0xffffu);
         cur++;
+        if (++pos == (uint32_t)G::CS) { pos = 0; cube++; }
     }
-    if (pend) P.coo[pend_cube * G::CS + pend_slot] = pend_entry;
-    if (hi == ncodes) *P.end_bit = src.w0 * 32ull + br.pos;
+    if (hi == ncodes) {
+        *P.end_bit = src.w0 * 32ull + br.pos;
+        P.coo_start[P.L.ncubes] = zrank;
+    }
 }
 
 // non-zero lists -> dense natural-order int16 cubes (dct3d_eg_decode_i16; qcubes zeroed beforehand).
@@ -884,10 +895,11 @@ coo_scatter_kernel(const DecParams P)
     const long long wid = (long long)blockIdx.x * kWarps + (threadIdx.x >> 5);
     const long long nw = (long long)gridDim.x * kWarps;
     for (long long cube = wid; cube < P.L.ncubes; cube += nw) {
-        const uint32_t n = min(P.coo_cnt[cube], (uint32_t)G::CS);
+        const unsigned long long z0 = P.coo_start[cube];
+        const uint32_t n = (uint32_t)min(P.coo_start[cube + 1] - z0, (unsigned long long)G::CS);
         for (uint32_t i = lane; i < n; i += 32) {
-            const uint32_t e = P.coo[(size_t)cube * G::CS + i];
-            P.qcubes[(size_t)cube * G::CS + (e >> 16)] = (int16_t)(e & 0xffffu);
+            const uint32_t e = P.coo[z0 + i];
+            P.qcubes[(size_t)cube * G::CS + ((e >> 16) & (G::CS - 1))] = (int16_t)(e & 0xffffu);
         }
     }
 }
@@ -940,7 +952,7 @@ struct CooSmem {
 
 template <int C>
 __global__ void __launch_bounds__(kThreads, 4)
-reconstruct_coo_kernel(const Layout L, const uint32_t *__restrict__ coo, const uint32_t *__restrict__ coo_cnt,
+reconstruct_coo_kernel(const Layout L, const uint32_t *__restrict__ coo, const unsigned long long *__restrict__ coo_start,
                        uint8_t *__restrict__ frames)
 {
     using G = Geo<C>;
@@ -960,29 +972,40 @@ reconstruct_coo_kernel(const Layout L, const uint32_t *__restrict__ coo, const u
     const long long ngroups = (L.ncubes + G::CPW - 1) / G::CPW;
     const long long stride = (long long)gridDim.x * kWarps;
     long long g = (long long)blockIdx.x * kWarps + warp;
-    uint32_t cnt_n = 0, e_n[PRE];
-    auto prefetch = [&](long long grp) {
+    // pipeline: row pointers two groups ahead, the first PRE*C entries one group ahead
+    unsigned long long z_nn = 0, z_n = 0;      // first entry of this thread's cube, groups g+2 and g+1
+    uint32_t c_nn = 0, c_n = 0, e_n[PRE];
+    auto fetch_rows = [&](long long grp) {
         const long long cube = grp * G::CPW + cl;
         const bool ok = grp < ngroups && cube < L.ncubes;
-        cnt_n = ok ? min(__ldg(coo_cnt + cube), (uint32_t)G::CS) : 0u;
-#pragma unroll
-        for (int k = 0; k < PRE; k++) e_n[k] = ok ? __ldg(coo + (size_t)cube * G::CS + r + k * C) : 0u;   // speculative: valid iff < cnt
+        z_nn = ok ? __ldg(coo_start + cube) : 0ull;
+        c_nn = ok ? (uint32_t)min(__ldg(coo_start + cube + 1) - z_nn, (unsigned long long)G::CS) : 0u;
     };
-    prefetch(g);
+    auto fetch_entries = [&]() {               // for the group whose row pointers are in z_n / c_n
+#pragma unroll
+        for (int k = 0; k < PRE; k++) e_n[k] = (uint32_t)(r + k * C) < c_n ? __ldg(coo + z_n + r + k * C) : 0u;
+    };
+    fetch_rows(g);
+    z_n = z_nn; c_n = c_nn;
+    fetch_entries();
+    fetch_rows(g + stride);
     for (; g < ngroups; g += stride) {
-        const uint32_t cnt = cnt_n;
+        const uint32_t cnt = c_n;
+        const unsigned long long z0 = z_n;
         uint32_t e[PRE];
 #pragma unroll
         for (int k = 0; k < PRE; k++) e[k] = e_n[k];
         const long long cube = g * G::CPW + cl;
-        prefetch(g + stride);
+        z_n = z_nn; c_n = c_nn;
+        fetch_entries();                        // group g + stride
+        fetch_rows(g + 2 * stride);
         // scatter this cube's entries (lane r of the cube takes entries r, r+C, r+2C, ...)
 #pragma unroll
         for (int k = 0; k < PRE; k++)
-            if ((uint32_t)(r + k * C) < cnt) nat[e[k] >> 16] = (int16_t)(e[k] & 0xffffu);
+            if ((uint32_t)(r + k * C) < cnt) nat[(e[k] >> 16) & (G::CS - 1)] = (int16_t)(e[k] & 0xffffu);
         for (uint32_t i = r + PRE * C; i < cnt; i += C) {
-            const uint32_t x = __ldg(coo + (size_t)cube * G::CS + i);
-            nat[x >> 16] = (int16_t)(x & 0xffffu);
+            const uint32_t x = __ldg(coo + z0 + i);
+            nat[(x >> 16) & (G::CS - 1)] = (int16_t)(x & 0xffffu);
         }
         __syncwarp();
         float b[C][C];
@@ -1002,8 +1025,8 @@ reconstruct_coo_kernel(const Layout L, const uint32_t *__restrict__ coo, const u
         // wipe what was scattered
 #pragma unroll
         for (int k = 0; k < PRE; k++)
-            if ((uint32_t)(r + k * C) < cnt) nat[e[k] >> 16] = 0;
-        for (uint32_t i = r + PRE * C; i < cnt; i += C) nat[__ldg(coo + (size_t)cube * G::CS + i) >> 16] = 0;
+            if ((uint32_t)(r + k * C) < cnt) nat[(e[k] >> 16) & (G::CS - 1)] = 0;
+        for (uint32_t i = r + PRE * C; i < cnt; i += C) nat[(__ldg(coo + z0 + i) >> 16) & (G::CS - 1)] = 0;
         idct_store<C>(b, xbuf, cl, r, cube < L.ncubes, L, cube, frames);
     }
 }

@@ -296,10 +296,10 @@ EG_HD uint32_t eg_parse_cube(const Source &src, uint32_t start, const uint16_t *
 // (zero padding after the last code of the stream is not an error).
 template <typename Source>
 EG_HD bool eg_scan_segment(const Source &src, uint32_t start, uint32_t limit, uint32_t end_of_stream,
-                           uint32_t &ncodes, uint32_t &next_start)
+                           uint32_t &ncodes, uint32_t &next_start, uint32_t *nonzero = nullptr)
 {
     BitReader<Source> br(src, start);
-    uint32_t n = 0;
+    uint32_t n = 0, nz = 0;
     while (br.pos < limit) {
         br.refill();
         uint32_t ones = (uint32_t)clz32(~br.hi);
@@ -317,9 +317,11 @@ EG_HD bool eg_scan_segment(const Source &src, uint32_t start, uint32_t limit, ui
             return false;
         }
         n++;
+        nz++;
     }
     ncodes = n;
     next_start = br.pos;
+    if (nonzero) *nonzero = nz;
     return true;
 }
 
