@@ -399,3 +399,17 @@ def test_full_size_configs_properties(codec_mod, W, H, F, cube):
 def C_u64():
     import ctypes
     return ctypes.c_uint64()
+
+
+def test_decode_worst_case_resynchronisation(codec_mod, oracle):
+    """A stream of equal 33-bit codes never resynchronises: every 1024-bit segment's entry point depends on
+    its predecessor's, so index discovery needs one fix-up round per segment (the host fallback loop)."""
+    q = np.full((4, 8, 8, 8), -32768, np.int16)
+    q[1, 0, 0, 0] = 5          # a little structure so that the cubes differ
+    q[3, 7, 7, 7] = 0
+    ref, ref_end = oracle.eg_encode_cubes(q.astype(np.int32), 8, cap=5 * q.size + 16)
+    with make(codec_mod, 64, 64, 8) as c:
+        out, end = c.eg_encode_i16(q)
+        assert end == ref_end and out.tobytes() == ref.tobytes()
+        back, dend = c.eg_decode_i16(out, 4)
+        assert dend == ref_end and (back == q).all()
