@@ -319,7 +319,7 @@ def run_ours(args):
         alg_bytes = N + S      # algorithmic bytes of encode_u8 and of decode_u8: pixels + stream
         # dominant kernel of the step = the longer of the two transform kernels, timed live by CUDA events
         # recorded around it on the launching stream inside libdct3d
-        dom = ("reconstruct_zz_kernel<8>", krec_ms) if krec_ms >= kenc_ms else ("encode_kernel<8,MODE_ZZ>", kenc_ms)
+        dom = ("reconstruct_coo_kernel<8>", krec_ms) if krec_ms >= kenc_ms else ("encode_kernel<8,MODE_ZZ>", kenc_ms)
         achieved = alg_bytes / (dom[1] * 1e-3) / 1e9
         cores = os.cpu_count() or 1
         cpu = None
@@ -338,12 +338,12 @@ def run_ours(args):
             "encode_fps": world * F / (enc_ms_max * 1e-3), "decode_fps": world * F / (dec_ms_max * 1e-3),
             "encode_ms": enc_ms_max, "decode_ms": dec_ms_max,
             "roofline": {"bound": "hbm", "kernel": dom[0], "kernel_ms": dom[1], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": 666.7e6 if dom[0].startswith("recon") else 632.9e6,
+                         "frac": achieved / peak, "traffic": 544.1e6 if dom[0].startswith("recon") else 632.8e6,
                          "peak_source": peak_src, "algorithmic_bytes": int(alg_bytes),
                          "traffic_source": "ncu dram__bytes_read+write of that kernel, profiles/r1_summary.md",
-                         "note": "the fused u8<->bitstream kernels are FP32-issue-bound (SM 71-76%, DRAM 14-17%), not HBM-bound: "
+                         "note": "the fused u8<->bitstream kernels are issue-bound (SM 69-79%, DRAM 11-20%), not HBM-bound: "
                                  "DESIGN.md 4; the HBM-bound float seam is in roofline_f32_seam"},
-            "kernels_ms": {"encode_kernel": kenc_ms, "reconstruct_zz_kernel": krec_ms},
+            "kernels_ms": {"encode_kernel": kenc_ms, "reconstruct_coo_kernel": krec_ms},
             "roofline_f32_seam": None if seam is None else {
                 "bound": "hbm", "unit": "GB/s", "peak": peak, "algorithmic_bytes_per_sample": 8,
                 "forward_f32": seam["forward_f32"], "inverse_f32": seam["inverse_f32"],
