@@ -63,8 +63,10 @@ const char *dct3d_last_error(const dct3d_ctx *ctx);
  * with 1, a buffer the context packed into on its previous call (same pointer, same capacity, end bit
  * read back) is only wiped up to where that call wrote -- the caller promises not to have written
  * beyond it in between.
- * Statistics (dct3d_get_stat): "launches" = kernels launched by the context so far,
- * "flips_near_tie" is reported by the tests, not here. */
+ * "debug" (1 = print per-stage diagnostics to stderr).
+ * Statistics (dct3d_get_stat): "launches" = kernels launched by the context so far; "tma" = 1 when the
+ * TMA path is active; "num_sms"; "ns_encode_kernel" / "ns_reconstruct_kernel" = duration in ns of the
+ * last transform kernel of each direction, from CUDA events recorded around it on the launching stream. */
 int dct3d_set_option(dct3d_ctx *ctx, const char *key, long value);
 long dct3d_get_stat(const dct3d_ctx *ctx, const char *key);
 
