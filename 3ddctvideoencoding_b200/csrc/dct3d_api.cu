@@ -93,11 +93,10 @@ Layout make_layout(int W, int H, int C, int nslabs)
     Layout L;
     L.W = W; L.H = H; L.C = C;
     L.bx = W / C; L.by = H / C;
-    const int cpb = kBoxW / C;
-    L.bxb = (L.bx + cpb - 1) / cpb;
+    const int cpu = kUnitW / C;
+    L.bxu = (L.bx + cpu - 1) / cpu;
     L.nslabs = nslabs;
-    L.nboxes = (long long)nslabs * L.by * L.bxb;
-    L.ntiles = L.nboxes;      // fused encoder: one tile = one TMA box
+    L.nunits = (long long)nslabs * L.by * L.bxu;   // fused encoder: one unit = one TMA box = one warp pass
     L.ncubes = (long long)nslabs * L.by * L.bx;
     return L;
 }
@@ -163,17 +162,18 @@ EncodeTiledFn get_encode_tiled()
     return fn;
 }
 
-// Tensor map over the u8 frame stack [F][H][W]; box = 128 px x 1 row x C frames, SWIZZLE_128B.
+// Tensor map over the u8 frame stack [F][H][W], presented as {W, F, H} (frames before rows) so that one
+// box {32 px, C frames, C rows} lands in shared memory as [y][t][32 px]: the image a warp unit wants.
 bool make_tmap(CUtensorMap *tm, const void *frames, int W, int H, int F, int C)
 {
     EncodeTiledFn fn = get_encode_tiled();
     if (!fn) return false;
-    cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)F};
-    cuuint64_t strides[2] = {(cuuint64_t)W, (cuuint64_t)W * H};
-    cuuint32_t box[3] = {(cuuint32_t)kBoxW, 1u, (cuuint32_t)C};
+    cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)F, (cuuint64_t)H};
+    cuuint64_t strides[2] = {(cuuint64_t)W * H, (cuuint64_t)W};
+    cuuint32_t box[3] = {(cuuint32_t)kUnitW, (cuuint32_t)C, (cuuint32_t)C};
     cuuint32_t es[3] = {1, 1, 1};
     return fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void *>(frames), dims, strides, box, es,
-              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -203,7 +203,7 @@ int launch_encode(dct3d_ctx *ctx, const EncParams &P, const CUtensorMap &tm, cud
         CU_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem));
     }
     if (occ < 1) return fail(ctx, DCT3D_E_CUDA, "encode kernel does not fit on an SM");
-    const long long grid = std::min<long long>(P.L.ntiles, (long long)ctx->num_sms * occ);
+    const long long grid = std::min<long long>((P.L.nunits + kWarps - 1) / kWarps, (long long)ctx->num_sms * occ);
     if (MODE == MODE_ZZ) cudaEventRecord(ctx->ev[0], st);
     kern<<<(unsigned)grid, kThreads, smem, st>>>(tm, P);
     if (MODE == MODE_ZZ) { cudaEventRecord(ctx->ev[1], st); ctx->ev_valid[0] = true; }

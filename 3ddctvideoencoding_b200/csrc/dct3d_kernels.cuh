@@ -29,7 +29,7 @@
 
 namespace dct3d {
 
-constexpr int kBoxW = 128;       // pixels (bytes) per TMA box row
+constexpr int kUnitW = 32;       // pixels (bytes) per warp unit = TMA box row
 constexpr int kWarps = 4;        // transform warps per CTA
 constexpr int kThreads = kWarps * 32;
 
@@ -37,9 +37,7 @@ template <int C>
 struct Geo {
     static constexpr int CS = C * C * C;
     static constexpr int CPW = 32 / C;                       // cubes per warp pass
-    static constexpr int CUBES_PER_BOX = kBoxW / C;          // 16 (C=8) / 32 (C=4)
-    static constexpr int ROW_BYTES = kBoxW * C;              // one TMA op: C frames of one row
-    static constexpr int BOX_BYTES = ROW_BYTES * C;
+    static constexpr int UNIT_BYTES = kUnitW * C * C;        // one TMA op: 32 px x C frames x C rows
     static constexpr int ZZ_STRIDE = CS + 8;                 // int16 units; odd multiple of 16 B
     static constexpr int NDIAG = 2 * C - 1;
     static constexpr int CHUNKS = CS / 16;                   // 16-coefficient chunks per cube
@@ -49,9 +47,9 @@ struct Geo {
 struct Layout {
     int W, H, C;
     int bx, by;          // cubes per row / cube rows
-    int bxb;             // boxes per cube row
+    int bxu;             // warp units (32 px = 32/C cubes) per cube row
     int nslabs;
-    long long nboxes, ntiles, ncubes;
+    long long nunits, ncubes;
 };
 
 struct EncParams {
@@ -118,33 +116,32 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *tmap, 
 }
 
 // ------------------------------------------------------------------------------------------
-// Box geometry
+// Unit geometry.  A unit is what one warp transforms per pass: 32 px x C rows x C frames =
+// 32/C cubes side by side.  Shared-memory image of a unit: [y][t][32 px], which is what one TMA
+// box {32, C frames, C rows} over the tensor {W, F, H} delivers; the 32 lanes of a warp (lane =
+// cube*C + t) then read row y as 32*C contiguous bytes: conflict-free without a swizzle.
 // ------------------------------------------------------------------------------------------
-struct BoxPos { int slab, byi, bxb, nvalid; long long cube0; };
+struct UnitPos { int slab, byi, bxu; };
 
-template <int C>
-__device__ __forceinline__ BoxPos box_pos(const Layout &L, long long b)
+__device__ __forceinline__ UnitPos unit_pos(const Layout &L, long long u)
 {
-    BoxPos p;
-    const int per_slab = L.by * L.bxb;
-    p.slab = (int)(b / per_slab);
-    const int rem = (int)(b - (long long)p.slab * per_slab);
-    p.byi = rem / L.bxb;
-    p.bxb = rem - p.byi * L.bxb;
-    const int bxi0 = p.bxb * Geo<C>::CUBES_PER_BOX;
-    p.nvalid = min(Geo<C>::CUBES_PER_BOX, L.bx - bxi0);
-    p.cube0 = ((long long)p.slab * L.by + p.byi) * L.bx + bxi0;
+    UnitPos p;
+    const int per_slab = L.by * L.bxu;
+    p.slab = (int)(u / per_slab);
+    const int rem = (int)(u - (long long)p.slab * per_slab);
+    p.byi = rem / L.bxu;
+    p.bxu = rem - p.byi * L.bxu;
     return p;
 }
 
-// Shared-memory address of byte xb of row (y, t) inside a box, SWIZZLE_128B pattern: the box
-// is C blocks (one per y) of C rows (t) of 128 B; the 16-byte chunk index is XORed with
-// bits [7:9] of the byte offset.
-template <int C>
-__device__ __forceinline__ int in_offset(int y, int t, int xb)
+// advance by (ds, dy, dx) = the decomposition of the grid stride, with carries
+__device__ __forceinline__ void unit_advance(const Layout &L, UnitPos &p, const UnitPos &d)
 {
-    const int row = y * C + t;
-    return row * 128 + ((((xb >> 4) ^ row) & 7) << 4) + (xb & 15);
+    p.bxu += d.bxu;
+    p.byi += d.byi;
+    p.slab += d.slab;
+    if (p.bxu >= L.bxu) { p.bxu -= L.bxu; p.byi++; }
+    if (p.byi >= L.by) { p.byi -= L.by; p.slab++; }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -270,6 +267,17 @@ __device__ __forceinline__ float byte_to_float(uint32_t word, int i)
     return __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7540u + i)) - 8388608.0f;
 }
 
+// u8 -> 2^15 + value in ONE PRMT (the byte becomes mantissa bits 8..15 of 2^15).  The bias is not
+// subtracted per sample: the first butterfly level forms exact sums and differences, every output
+// but DC is built from differences (the bias cancels exactly), and the DC term carries C*2^15 per
+// axis, all still exact in fp32 (integers below 2^24 * ulp).  One FADD per plane removes it after
+// the x and y passes (kBiasXY), instead of one per sample.
+__device__ __forceinline__ float byte_to_float_biased(uint32_t word, int i)
+{
+    return __uint_as_float(__byte_perm(word, 0x47000000u, 0x7404u + (i << 4)));
+}
+template <int C> struct BiasXY { static constexpr float value = (C == 8 ? 64.0f : 4.0f) * 32768.0f; };
+
 // ------------------------------------------------------------------------------------------
 // Entropy stage, shared by the fused encoder and the int16-cube encoder.
 // ------------------------------------------------------------------------------------------
@@ -343,21 +351,21 @@ __device__ __forceinline__ unsigned long long tile_lookback(unsigned long long *
 //             that hold a non-zero value are ever written (3.3 of 32 on natural content), and
 //             kernel 2 only reads those.  This is the one place a coefficient is written.
 //   MODE_NAT: natural-order int16 cubes (the dct3d_quantize_u8 stage entry point).
-// One tile = one TMA box = 128 px x C rows x C frames = kWarps*CPW cubes; tiles are double
-// buffered so the next box lands while the current one is transformed.
+// Every warp runs its own pipeline: a unit (32 px x C rows x C frames = 32/C cubes) arrives by ONE
+// TMA box into the warp's private double buffer and completes on the warp's own mbarrier, so the
+// warps of a CTA never wait for each other (no CTA-wide barrier in the loop).
 // ------------------------------------------------------------------------------------------
 constexpr int MODE_ZZ = 0, MODE_NAT = 1;
 
 template <int C>
 struct EncSmem {
     using G = Geo<C>;
-    static constexpr int TILE = G::CUBES_PER_BOX;
-    static constexpr int IN_OFF = 0;                                              // 2 x BOX_BYTES (1024-aligned)
-    static constexpr int XCH_OFF = IN_OFF + 2 * G::BOX_BYTES;
-    static constexpr int ZZ_OFF = XCH_OFF + kWarps * Xch<C, float>::WARP_BYTES;
-    static constexpr int ZZ_BYTES = TILE * G::ZZ_STRIDE * 2;
-    static constexpr int BAR_OFF = ZZ_OFF + ZZ_BYTES;
-    static constexpr int TOTAL = BAR_OFF + 16;
+    static constexpr int IN_BYTES = 2 * G::UNIT_BYTES;                              // double buffer
+    static constexpr int XCH_BYTES = Xch<C, float>::WARP_BYTES;
+    static constexpr int ZZ_BYTES = G::CPW * G::ZZ_STRIDE * 2;
+    static constexpr int WARP_BYTES = (IN_BYTES + XCH_BYTES + ZZ_BYTES + 127) / 128 * 128;
+    static constexpr int BAR_OFF = kWarps * WARP_BYTES;
+    static constexpr int TOTAL = BAR_OFF + kWarps * 16;
 };
 
 template <int C, int MODE>
@@ -367,14 +375,15 @@ encode_kernel(const __grid_constant__ CUtensorMap tmap, const EncParams P)
     using G = Geo<C>;
     using S = EncSmem<C>;
     extern __shared__ __align__(1024) uint8_t smem[];
-    uint8_t *s_in = smem + S::IN_OFF;
-    uint8_t *s_xch = smem + S::XCH_OFF;
-    int16_t *s_zz = reinterpret_cast<int16_t *>(smem + S::ZZ_OFF);
-    uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem + S::BAR_OFF);
-
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint8_t *s_in = smem + warp * S::WARP_BYTES;
+    uint8_t *s_xch = s_in + S::IN_BYTES;
+    int16_t *s_zz = reinterpret_cast<int16_t *>(s_xch + S::XCH_BYTES);
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem + S::BAR_OFF) + warp * 2;
+
     const int cl = lane / C, r = lane % C;   // cube within the warp; t (stage 1) or k1 (stage 2)
     const Layout &L = P.L;
+    const bool tma = P.use_tma != 0;
 
     float rq[G::NDIAG];
     uint32_t zb[G::NDIAG];
@@ -383,80 +392,91 @@ encode_kernel(const __grid_constant__ CUtensorMap tmap, const EncParams P)
         rq[s] = lane_scale<C>(r) / (float)quant_divisor(s + r);   // S[k1] of the scaled butterflies folded in
         zb[s] = zz_base<C>(r, s);
     }
-    auto issue_tma = [&](long long tile, int h) {
+    // unit counts fit 31 bits (checked by the host)
+    const int nw = (int)gridDim.x * kWarps, nunits = (int)L.nunits;
+    int u = (int)blockIdx.x * kWarps + warp;
+    UnitPos pos = unit_pos(L, u);
+    const UnitPos step = unit_pos(L, nw);
+
+    auto issue_tma = [&](const UnitPos &q, int h) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_expect_tx(&s_bar[h], G::BOX_BYTES);
-        const BoxPos bp = box_pos<C>(L, tile);
-#pragma unroll 1
-        for (int y = 0; y < C; y++)
-            tma_load_3d(s_in + h * G::BOX_BYTES + y * G::ROW_BYTES, &tmap, bp.bxb * kBoxW, bp.byi * C + y, bp.slab * C, &s_bar[h]);
+        mbar_expect_tx(&s_bar[h], G::UNIT_BYTES);
+        tma_load_3d(s_in + h * G::UNIT_BYTES, &tmap, q.bxu * kUnitW, q.slab * C, q.byi * C, &s_bar[h]);
     };
-    if (tid == 0 && P.use_tma) {
+    if (lane == 0 && tma) {
         mbar_init(&s_bar[0], 1);
         mbar_init(&s_bar[1], 1);
-        if ((long long)blockIdx.x < L.ntiles) issue_tma(blockIdx.x, 0);
+        if (u < nunits) issue_tma(pos, 0);
     }
-    // The zig-zag buffer is kept all-zero between tiles: only non-zero coefficients are scattered
+    // The zig-zag buffer is kept all-zero between units: only non-zero coefficients are scattered
     // into it (97% are zero), and the lanes that find a non-zero chunk wipe it after storing it.
-    for (int i = tid; i < S::ZZ_BYTES / 16; i += kThreads) reinterpret_cast<uint4 *>(s_zz)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = lane; i < S::ZZ_BYTES / 16; i += 32) reinterpret_cast<uint4 *>(s_zz)[i] = make_uint4(0, 0, 0, 0);
+    __syncwarp();
 
-    int it = 0;
-    for (long long tile = blockIdx.x; tile < L.ntiles; tile += gridDim.x, it++) {
+    for (int it = 0; u < nunits; u += nw, it++) {
         const int h = it & 1;
-        __syncthreads();                       // iteration it-1 is done with in[h^1]; barrier init visible
-        if (tid == 0 && P.use_tma && tile + gridDim.x < L.ntiles) issue_tma(tile + gridDim.x, h ^ 1);
-        const BoxPos bp = box_pos<C>(L, tile);
-        uint8_t *box = s_in + h * G::BOX_BYTES;
-        if (!P.use_tma) {
-            // plain loader: C-byte pieces (always aligned since W % C == 0), same swizzled layout
-            constexpr int PIECES = G::BOX_BYTES / C;
-            for (int i = tid; i < PIECES; i += kThreads) {
-                const int row = i / (kBoxW / C);            // y*C + t
-                const int cb = i - row * (kBoxW / C);       // cube in box
+        uint8_t *box = s_in + h * G::UNIT_BYTES;
+        // every lane finished reading in[h^1] before the exchange barriers of the previous pass
+        if (lane == 0 && tma && u + nw < nunits) {
+            UnitPos nx = pos;
+            unit_advance(L, nx, step);
+            issue_tma(nx, h ^ 1);
+        }
+        const int bxi0 = pos.bxu * G::CPW;
+        const int nvalid = min(G::CPW, L.bx - bxi0);
+        const long long cube0 = ((long long)pos.slab * L.by + pos.byi) * L.bx + bxi0;
+        if (!tma) {
+            // plain loader: C-byte pieces (always aligned since W % C == 0), same layout
+            constexpr int PIECES = G::UNIT_BYTES / C;
+#pragma unroll
+            for (int i = lane; i < PIECES; i += 32) {
+                const int row = i / G::CPW;                 // y*C + t
+                const int cb = i - row * G::CPW;            // cube in unit
                 const int y = row / C, t = row - y * C;
                 uint32_t lo = 0, hi = 0;
-                if (cb < bp.nvalid) {
-                    const uint8_t *src = P.frames + ((size_t)(bp.slab * C + t) * L.H + (bp.byi * C + y)) * L.W +
-                                         bp.bxb * kBoxW + cb * C;
+                if (cb < nvalid) {
+                    const uint8_t *src = P.frames + ((size_t)(pos.slab * C + t) * L.H + (pos.byi * C + y)) * L.W +
+                                         (size_t)(bxi0 + cb) * C;
                     if (C == 8) { const uint2 v = *reinterpret_cast<const uint2 *>(src); lo = v.x; hi = v.y; }
                     else lo = *reinterpret_cast<const uint32_t *>(src);
                 }
-                uint8_t *dst = box + in_offset<C>(y, t, cb * C);
+                uint8_t *dst = box + row * kUnitW + cb * C;
                 if (C == 8) *reinterpret_cast<uint2 *>(dst) = make_uint2(lo, hi);
                 else *reinterpret_cast<uint32_t *>(dst) = lo;
             }
-            __syncthreads();
+            __syncwarp();
         } else {
             const uint32_t parity = (uint32_t)(it >> 1) & 1u;
             unsigned spins = 0;
             while (!mbar_try_wait(&s_bar[h], parity)) {
-                if (++spins > (1u << 22)) { if (tid == 0) atomicOr(P.err, 16u); break; }   // never hang the GPU
+                if (++spins > (1u << 22)) { if (lane == 0) atomicOr(P.err, 16u); break; }   // never hang the GPU
             }
         }
+        unit_advance(L, pos, step);
 
         // ---- transform: one cube per C threads ---------------------------------------------
-        const int slot = warp * G::CPW + cl;     // cube in the tile
         float a[C][C], bq[C][C];
 #pragma unroll
         for (int y = 0; y < C; y++) {
-            const uint8_t *src = box + in_offset<C>(y, r, slot * C);
+            const uint8_t *src = box + (y * C + r) * kUnitW + cl * C;
             if (C == 8) {
                 const uint2 v = *reinterpret_cast<const uint2 *>(src);
 #pragma unroll
-                for (int x = 0; x < 4; x++) { a[y][x] = byte_to_float(v.x, x); a[y][(x + 4) % C] = byte_to_float(v.y, x); }
+                for (int x = 0; x < 4; x++) { a[y][x] = byte_to_float_biased(v.x, x); a[y][(x + 4) % C] = byte_to_float_biased(v.y, x); }
             } else {
                 const uint32_t v = *reinterpret_cast<const uint32_t *>(src);
 #pragma unroll
-                for (int x = 0; x < 4; x++) a[y][x % C] = byte_to_float(v, x);
+                for (int x = 0; x < 4; x++) a[y][x % C] = byte_to_float_biased(v, x);
             }
         }
         fwd_xy_n<C, float>(a);
-        Xch<C, float>::transpose(s_xch + warp * Xch<C, float>::WARP_BYTES, cl, r, a, bq);
+        a[0][0] -= BiasXY<C>::value;
+        Xch<C, float>::transpose(s_xch, cl, r, a, bq);
         fwd_t_g<C, float>(bq);
         // bq[k0][k2] is coefficient (k0, k1 = r, k2)
         if (MODE == MODE_NAT) {
-            if (slot < bp.nvalid) {
-                int16_t *dst = P.qcubes + (size_t)(bp.cube0 + slot) * G::CS + r * C;
+            if (cl < nvalid) {
+                int16_t *dst = P.qcubes + (size_t)(cube0 + cl) * G::CS + r * C;
 #pragma unroll
                 for (int k0 = 0; k0 < C; k0++) {
                     uint32_t w[C / 2];
@@ -473,7 +493,7 @@ encode_kernel(const __grid_constant__ CUtensorMap tmap, const EncParams P)
             continue;
         }
         // zig-zag scatter into this warp's private cubes (runs of a diagonal are contiguous)
-        int16_t *zz = s_zz + slot * G::ZZ_STRIDE;
+        int16_t *zz = s_zz + cl * G::ZZ_STRIDE;
 #pragma unroll
         for (int k0 = 0; k0 < C; k0++) {
 #pragma unroll
@@ -488,33 +508,32 @@ encode_kernel(const __grid_constant__ CUtensorMap tmap, const EncParams P)
         __syncwarp();
         // chunk masks + sparse store: lane <-> 16-coefficient chunk
         constexpr int ITER = (G::CPW * G::CHUNKS) / 32;   // 4 (C=8) / 1 (C=4)
-        const int slot0 = warp * G::CPW;
 #pragma unroll
         for (int k = 0; k < ITER; k++) {
             const int ci = k * 32 + lane;
             const int cube = ci / G::CHUNKS, chunk = ci % G::CHUNKS;
-            uint4 *q = reinterpret_cast<uint4 *>(s_zz + (slot0 + cube) * G::ZZ_STRIDE + chunk * 16);
+            uint4 *q = reinterpret_cast<uint4 *>(s_zz + cube * G::ZZ_STRIDE + chunk * 16);
             // lanes 4..7 of every 8 read their two 16-byte halves in the other order: the quarter
             // warp then touches 8 distinct bank groups instead of 4 twice
             const int hsel = (lane >> 2) & 1;
             const uint4 va = q[hsel], vb = q[hsel ^ 1];
             const uint32_t any = va.x | va.y | va.z | va.w | vb.x | vb.y | vb.z | vb.w;
-            const bool ok = slot0 + cube < bp.nvalid;
+            const bool ok = cube < nvalid;
             const uint32_t bal = __ballot_sync(0xffffffffu, any != 0);
-            const long long gc = bp.cube0 + slot0 + cube;
+            const long long gc = cube0 + cube;
             if (any != 0) {
                 if (ok) {
                     uint4 *dst = reinterpret_cast<uint4 *>(P.zzg + (size_t)gc * G::CS + chunk * 16);
                     dst[hsel] = va;
                     dst[hsel ^ 1] = vb;
                 }
-                q[0] = make_uint4(0, 0, 0, 0);      // leave the buffer clean for the next tile
+                q[0] = make_uint4(0, 0, 0, 0);      // leave the buffer clean for the next unit
                 q[1] = make_uint4(0, 0, 0, 0);
             }
             if (G::CHUNKS == 32) { if (lane == 0 && ok) P.cmask[gc] = bal; }
             else { if (chunk == 0 && ok) P.cmask[gc] = (bal >> (cube * G::CHUNKS)) & ((1u << (G::CHUNKS & 31)) - 1u); }
         }
-        __syncwarp();                           // zz is rewritten by the next tile
+        __syncwarp();                           // zz is rewritten by the next unit
     }
 }
 

@@ -135,7 +135,9 @@ int dct3d_eg_decode_i16(dct3d_ctx *ctx, const uint8_t *stream, size_t nbytes, ui
 
 /* ---- device-resident variants ------------------------------------------------------------
  * All pointers are device pointers on the context's GPU; `cuda_stream` is a cudaStream_t (NULL =
- * the context's own stream).  Work is enqueued on that stream; scalar results are written to
+ * the context's own stream, which is non-blocking: it does not synchronise with the legacy default
+ * stream, so work the caller has pending on the buffers must be complete, or the caller passes the
+ * stream that work was enqueued on).  Work is enqueued on that stream; scalar results are written to
  * host memory after an internal stream synchronisation unless the pointer is NULL.
  * d_stream must be 4-byte aligned, zero-filled from start_bit on, and `cap` must include 8
  * bytes of slack. */

@@ -358,6 +358,9 @@ def test_full_size_configs_properties(codec_mod, W, H, F, cube):
     dev = frames.device
     with make(codec_mod, W, H, cube) as c:
         d_stream = torch.zeros(cap, dtype=torch.uint8, device=dev)
+        # the context runs on its own non-blocking stream (stream argument 0): torch's pending work on
+        # these tensors (clip generation, zero fills) must be complete before each call
+        torch.cuda.synchronize()
         end = c.encode_u8_dev(frames, F, d_stream, cap)
         nbytes = end // 8 + 1
         q = torch.empty(N, dtype=torch.int16, device=dev)
@@ -365,6 +368,7 @@ def test_full_size_configs_properties(codec_mod, W, H, F, cube):
         torch.cuda.synchronize()
         # stage path: cubes -> stream must be the same bits
         d2 = torch.zeros(cap, dtype=torch.uint8, device=dev)
+        torch.cuda.synchronize()
         e2 = C_u64()
         c._check(c.L.dct3d_eg_encode_i16_dev(c.h, q.data_ptr(), N // cube ** 3, 0, d2.data_ptr(), cap, e2, 0))
         torch.cuda.synchronize()
@@ -389,6 +393,7 @@ def test_full_size_configs_properties(codec_mod, W, H, F, cube):
         for g in range(4):
             lo, hi = sh.slab_range(nsl, g, 4)
             part = torch.zeros(cap, dtype=torch.uint8, device=dev)
+            torch.cuda.synchronize()
             e = c.encode_u8_dev(frames[lo * cube:hi * cube], (hi - lo) * cube, part, cap)
             parts.append(part[: e // 8 + 1].cpu().numpy())
             nb.append(e)
