@@ -126,7 +126,10 @@ int upload_tables(dct3d_ctx *ctx)
         build_zz(C, lin);
         std::vector<int> pos(C * C * C);
         for (int i = 0; i < (int)lin.size(); i++) pos[lin[i]] = i;
-        for (int i = 0; i < C * C * C; i++) (C == 8 ? t.lin8[i] : t.lin4[i]) = (uint16_t)lin[i];
+        for (int i = 0; i < C * C * C; i++) {
+            (C == 8 ? t.lin8[i] : t.lin4[i]) = (uint16_t)lin[i];
+            (C == 8 ? t.slin8[i] : t.slin4[i]) = (uint16_t)(C == 8 ? coo_swizzle<8>(lin[i]) : coo_swizzle<4>(lin[i]));
+        }
         for (int j = 0; j < C; j++)
             for (int s = 0; s < 2 * C - 1; s++) {
                 const int k0min = s > C - 1 ? s - (C - 1) : 0, k0max = std::min(s, C - 1);
@@ -163,7 +166,8 @@ EncodeTiledFn get_encode_tiled()
 }
 
 // Tensor map over the u8 frame stack [F][H][W], presented as {W, F, H} (frames before rows) so that one
-// box {32 px, C frames, C rows} lands in shared memory as [y][t][32 px]: the image a warp unit wants.
+// box {32 px, C frames, C rows} lands in shared memory as [y][t][32 px] (SWIZZLE_32B): the image a warp
+// unit wants (unit_offset() in dct3d_kernels.cuh).
 bool make_tmap(CUtensorMap *tm, const void *frames, int W, int H, int F, int C)
 {
     EncodeTiledFn fn = get_encode_tiled();
@@ -173,7 +177,7 @@ bool make_tmap(CUtensorMap *tm, const void *frames, int W, int H, int F, int C)
     cuuint32_t box[3] = {(cuuint32_t)kUnitW, (cuuint32_t)C, (cuuint32_t)C};
     cuuint32_t es[3] = {1, 1, 1};
     return fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void *>(frames), dims, strides, box, es,
-              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -274,7 +278,7 @@ static int launch_reconstruct_zz(dct3d_ctx *ctx, const Layout &L, void *d_frames
 template <int C>
 static int launch_reconstruct(dct3d_ctx *ctx, const Layout &L, const void *d_q, void *d_frames, cudaStream_t st)
 {
-    const int smem = kWarps * Xch<C, float>::WARP_BYTES;
+    const int smem = kWarps * Xch<C, float>::WARP_BYTES + C * C * C * 4;   // exchange buffers + dequantiser table
     const long long groups = (L.ncubes + Geo<C>::CPW - 1) / Geo<C>::CPW;
     const long long grid = std::min<long long>((groups + kWarps - 1) / kWarps, (long long)ctx->num_sms * 8);
     reconstruct_kernel<C><<<(unsigned)grid, kThreads, smem, st>>>(L, (const int16_t *)d_q, (uint8_t *)d_frames);

@@ -78,11 +78,22 @@ struct ZzTables {
     uint16_t base4[4][7];
     uint16_t lin8[512];      // zig-zag position -> natural index k2 + 8*k1 + 64*k0
     uint16_t lin4[64];
+    uint16_t slin8[512];     // the same through coo_swizzle(): index space of the decoder's lists
+    uint16_t slin4[64];
 };
 __constant__ ZzTables c_zz;
 
 template <int C> __device__ __forceinline__ uint16_t zz_base(int j, int s) { return C == 8 ? c_zz.base8[j][s] : c_zz.base4[j][s]; }
 template <int C> __device__ __forceinline__ const uint16_t *zz_lin() { return C == 8 ? c_zz.lin8 : c_zz.lin4; }
+template <int C> __device__ __forceinline__ const uint16_t *zz_slin() { return C == 8 ? c_zz.slin8 : c_zz.slin4; }
+
+// Index space of the decoder's non-zero lists: the natural index with the two 4-float halves of a row
+// exchanged for k1 >= 4 (C = 8), so that the 8 lanes k1 = 0..7 of a cube read their 16-byte half rows
+// of the float cube in shared memory (row stride 32 B) from 8 distinct bank groups.  An involution.
+template <int C> __host__ __device__ __forceinline__ constexpr uint32_t coo_swizzle(uint32_t idx)
+{
+    return C == 8 ? idx ^ ((idx >> 3) & 4u) : idx;
+}
 
 // ------------------------------------------------------------------------------------------
 // PTX helpers: mbarrier + TMA
@@ -118,10 +129,19 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *tmap, 
 // ------------------------------------------------------------------------------------------
 // Unit geometry.  A unit is what one warp transforms per pass: 32 px x C rows x C frames =
 // 32/C cubes side by side.  Shared-memory image of a unit: [y][t][32 px], which is what one TMA
-// box {32, C frames, C rows} over the tensor {W, F, H} delivers; the 32 lanes of a warp (lane =
-// cube*C + t) then read row y as 32*C contiguous bytes: conflict-free without a swizzle.
+// box {32, C frames, C rows} over the tensor {W, F, H} delivers.  With SWIZZLE_32B the two 16-byte
+// halves of a 32-byte row are exchanged when bit 7 of the address is set (rows t = 4..7 of every y for
+// C = 8), so the 16 lanes of a half warp (2 cubes x 8 frames, 8 bytes each) cover all 32 banks once.
 // ------------------------------------------------------------------------------------------
 struct UnitPos { int slab, byi, bxu; };
+
+// byte offset of pixel xb (0..31) of row (y, t) inside a unit buffer (256-byte aligned)
+template <int C>
+__device__ __forceinline__ int unit_offset(int y, int t, int xb)
+{
+    const int row = y * C + t;
+    return row * kUnitW + (xb ^ (((row >> 2) & 1) << 4));
+}
 
 __device__ __forceinline__ UnitPos unit_pos(const Layout &L, long long u)
 {
@@ -229,6 +249,12 @@ __device__ __forceinline__ void inv_t_g(T (&b)[C][C])
 {
 #pragma unroll
     for (int x = 0; x < C; x++) Dct1D<C, T>::template inv_g<C>(&b[0][x], Dct1D<C, T>::scale(x));
+}
+template <int C, typename T>
+__device__ __forceinline__ void inv_t_n(T (&b)[C][C])
+{
+#pragma unroll
+    for (int x = 0; x < C; x++) Dct1D<C, T>::template inv_n<C>(&b[0][x]);
 }
 // S[k1] for a run-time k1 (the lane)
 template <int C>
@@ -363,7 +389,7 @@ struct EncSmem {
     static constexpr int IN_BYTES = 2 * G::UNIT_BYTES;                              // double buffer
     static constexpr int XCH_BYTES = Xch<C, float>::WARP_BYTES;
     static constexpr int ZZ_BYTES = G::CPW * G::ZZ_STRIDE * 2;
-    static constexpr int WARP_BYTES = (IN_BYTES + XCH_BYTES + ZZ_BYTES + 127) / 128 * 128;
+    static constexpr int WARP_BYTES = (IN_BYTES + XCH_BYTES + ZZ_BYTES + 255) / 256 * 256;   // swizzle phase = address bit 7
     static constexpr int BAR_OFF = kWarps * WARP_BYTES;
     static constexpr int TOTAL = BAR_OFF + kWarps * 16;
 };
@@ -440,7 +466,7 @@ encode_kernel(const __grid_constant__ CUtensorMap tmap, const EncParams P)
                     if (C == 8) { const uint2 v = *reinterpret_cast<const uint2 *>(src); lo = v.x; hi = v.y; }
                     else lo = *reinterpret_cast<const uint32_t *>(src);
                 }
-                uint8_t *dst = box + row * kUnitW + cb * C;
+                uint8_t *dst = box + unit_offset<C>(y, t, cb * C);
                 if (C == 8) *reinterpret_cast<uint2 *>(dst) = make_uint2(lo, hi);
                 else *reinterpret_cast<uint32_t *>(dst) = lo;
             }
@@ -458,7 +484,7 @@ encode_kernel(const __grid_constant__ CUtensorMap tmap, const EncParams P)
         float a[C][C], bq[C][C];
 #pragma unroll
         for (int y = 0; y < C; y++) {
-            const uint8_t *src = box + (y * C + r) * kUnitW + cl * C;
+            const uint8_t *src = box + unit_offset<C>(y, r, cl * C);
             if (C == 8) {
                 const uint2 v = *reinterpret_cast<const uint2 *>(src);
 #pragma unroll
@@ -874,7 +900,7 @@ seg_parse_kernel(const DecParams P)
     unsigned long long zrank = P.seg_nzfirst[k];
     uint32_t pos = (uint32_t)(cur % G::CS);            // position inside the current cube
     unsigned long long cube = cur / G::CS;
-    const uint16_t *lin = zz_lin<C>();
+    const uint16_t *lin = zz_slin<C>();
     BitReader<StagedSource> br(src, src.rel(P.start_bit + k * (unsigned long long)P.seg_bits) + P.seg_over[k]);
     while (cur < hi) {
         if (pos == 0) P.coo_start[cube] = zrank;       // this thread owns the cube's first code
@@ -918,20 +944,33 @@ coo_scatter_kernel(const DecParams P)
         const uint32_t n = (uint32_t)min(P.coo_start[cube + 1] - z0, (unsigned long long)G::CS);
         for (uint32_t i = lane; i < n; i += 32) {
             const uint32_t e = P.coo[z0 + i];
-            P.qcubes[(size_t)cube * G::CS + ((e >> 16) & (G::CS - 1))] = (int16_t)(e & 0xffffu);
+            P.qcubes[(size_t)cube * G::CS + coo_swizzle<C>((e >> 16) & (G::CS - 1))] = (int16_t)(e & 0xffffu);
         }
+    }
+}
+
+// Dequantiser table of both reconstruct kernels, in coo_swizzle() index space:
+// max(1, 5(k0+k1+k2)) (Decoder.java:89, decoder.c:54) times S[k0] S[k1] S[k2], the factors the
+// un-normalised inverse butterflies expect on their inputs.
+template <int C>
+__device__ __forceinline__ void build_dequant_table(float *tab, int tid)
+{
+    for (int i = tid; i < C * C * C; i += kThreads) {
+        const int k2 = i % C, k1 = (i / C) % C, k0 = i / (C * C);
+        tab[coo_swizzle<C>(i)] = (float)quant_divisor(k0 + k1 + k2) * (lane_scale<C>(k0) * lane_scale<C>(k1) * lane_scale<C>(k2));
     }
 }
 
 // Inverse tail shared by both reconstruct kernels: b[k0][k2] holds the dequantised coefficients of
 // row-frequency k1 = r.  Inverse butterflies along t, exchange, along y and x, clamp to [0,255],
 // truncate (Decoder.java:112, decoder.c:29), store the thread's frame plane.
-template <int C>
+template <int C, bool ALL_SCALED = false>
 __device__ __forceinline__ void idct_store(float (&b)[C][C], uint8_t *xbuf, int cl, int r, bool valid, const Layout &L,
                                            long long cube, uint8_t *__restrict__ frames)
 {
     float a[C][C];
-    inv_t_g<C, float>(b);
+    // ALL_SCALED: b already carries S[k0] S[k1] S[k2]; otherwise S[k1] only and the t stage folds in S[k2]
+    if (ALL_SCALED) inv_t_n<C, float>(b); else inv_t_g<C, float>(b);
     Xch<C, float>::transpose(xbuf, cl, r, b, a);   // the exchange is its own inverse
     inv_yx_n<C, float>(a);
     if (!valid) return;
@@ -957,16 +996,20 @@ __device__ __forceinline__ void idct_store(float (&b)[C][C], uint8_t *xbuf, int 
 }
 
 // Non-zero lists -> u8 frames (the decoder's inverse kernel).  Per warp and group of CPW cubes:
-// C lanes per cube scatter the cube's entries into a natural-order int16 cube in shared memory that
-// is kept all-zero (the same lanes wipe their entries afterwards); every thread then reads the C
-// rows (k0, k1 = lane) it needs with LDS.128, conflict-free.  Counts and the first 3*C entries of the
-// NEXT group are prefetched into registers while the current group is transformed.
+// C lanes per cube scatter the cube's entries, ALREADY DEQUANTISED (one multiply by the table entry
+// max(1,5(k0+k1+k2)) * S[k0] S[k1] S[k2], so that all three butterfly passes run un-normalised), into
+// a natural-order float cube in shared memory that is kept all-zero (the same lanes wipe their
+// entries afterwards); every thread then reads the C rows (k0, k1 = lane) it needs with LDS.128,
+// conflict-free.  Only the 3% non-zero coefficients are ever converted or multiplied.  Counts and the
+// first 3*C entries of the NEXT group are prefetched into registers while the current group is
+// transformed.
 template <int C>
 struct CooSmem {
     using G = Geo<C>;
-    static constexpr int NAT_WARP = G::CPW * G::CS * 2;            // bytes: CPW natural-order int16 cubes
+    static constexpr int NAT_WARP = G::CPW * G::CS * 4;            // bytes: CPW natural-order float cubes
     static constexpr int WARP_BYTES = NAT_WARP + Xch<C, float>::WARP_BYTES;
-    static constexpr int TOTAL = kWarps * WARP_BYTES;
+    static constexpr int TAB_OFF = kWarps * WARP_BYTES;            // float[CS] dequantiser table
+    static constexpr int TOTAL = TAB_OFF + G::CS * 4;
 };
 
 template <int C>
@@ -980,32 +1023,39 @@ reconstruct_coo_kernel(const Layout L, const uint32_t *__restrict__ coo, const u
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int cl = lane / C, r = lane % C;
-    int16_t *nat = reinterpret_cast<int16_t *>(smem + warp * S::WARP_BYTES) + cl * G::CS;   // this thread's cube
+    float *nat = reinterpret_cast<float *>(smem + warp * S::WARP_BYTES) + cl * G::CS;   // this thread's cube
     uint8_t *xbuf = smem + warp * S::WARP_BYTES + S::NAT_WARP;
-    float dq[G::NDIAG];
-#pragma unroll
-    for (int s = 0; s < G::NDIAG; s++) dq[s] = (float)quant_divisor(s + r) * lane_scale<C>(r);
+    float *tab = reinterpret_cast<float *>(smem + S::TAB_OFF);
+    build_dequant_table<C>(tab, tid);
     for (int i = lane; i < S::NAT_WARP / 16; i += 32) reinterpret_cast<uint4 *>(smem + warp * S::WARP_BYTES)[i] = make_uint4(0, 0, 0, 0);
-    __syncwarp();
+    __syncthreads();
 
     const long long ngroups = (L.ncubes + G::CPW - 1) / G::CPW;
     const long long stride = (long long)gridDim.x * kWarps;
     long long g = (long long)blockIdx.x * kWarps + warp;
     // pipeline: row pointers two groups ahead, the first PRE*C entries one group ahead
     unsigned long long z_nn = 0, z_n = 0;      // first entry of this thread's cube, groups g+2 and g+1
-    uint32_t c_nn = 0, c_n = 0, e_n[PRE];
+    uint32_t zend_nn = 0, c_n = 0, e_n[PRE];   // low word of the next row pointer: the count is formed a pass later
     auto fetch_rows = [&](long long grp) {
         const long long cube = grp * G::CPW + cl;
         const bool ok = grp < ngroups && cube < L.ncubes;
         z_nn = ok ? __ldg(coo_start + cube) : 0ull;
-        c_nn = ok ? (uint32_t)min(__ldg(coo_start + cube + 1) - z_nn, (unsigned long long)G::CS) : 0u;
+        zend_nn = ok ? __ldg(reinterpret_cast<const uint32_t *>(coo_start + cube + 1)) : 0u;
+    };
+    auto rotate_rows = [&]() {
+        z_n = z_nn;
+        c_n = min(zend_nn - (uint32_t)z_nn, (uint32_t)G::CS);
     };
     auto fetch_entries = [&]() {               // for the group whose row pointers are in z_n / c_n
 #pragma unroll
         for (int k = 0; k < PRE; k++) e_n[k] = (uint32_t)(r + k * C) < c_n ? __ldg(coo + z_n + r + k * C) : 0u;
     };
+    auto put = [&](uint32_t x) {
+        const uint32_t idx = (x >> 16) & (G::CS - 1);
+        nat[idx] = (float)(int)(int16_t)(x & 0xffffu) * tab[idx];
+    };
     fetch_rows(g);
-    z_n = z_nn; c_n = c_nn;
+    rotate_rows();
     fetch_entries();
     fetch_rows(g + stride);
     for (; g < ngroups; g += stride) {
@@ -1015,38 +1065,32 @@ reconstruct_coo_kernel(const Layout L, const uint32_t *__restrict__ coo, const u
 #pragma unroll
         for (int k = 0; k < PRE; k++) e[k] = e_n[k];
         const long long cube = g * G::CPW + cl;
-        z_n = z_nn; c_n = c_nn;
+        rotate_rows();
         fetch_entries();                        // group g + stride
         fetch_rows(g + 2 * stride);
         // scatter this cube's entries (lane r of the cube takes entries r, r+C, r+2C, ...)
 #pragma unroll
         for (int k = 0; k < PRE; k++)
-            if ((uint32_t)(r + k * C) < cnt) nat[(e[k] >> 16) & (G::CS - 1)] = (int16_t)(e[k] & 0xffffu);
-        for (uint32_t i = r + PRE * C; i < cnt; i += C) {
-            const uint32_t x = __ldg(coo + z0 + i);
-            nat[(x >> 16) & (G::CS - 1)] = (int16_t)(x & 0xffffu);
-        }
+            if ((uint32_t)(r + k * C) < cnt) put(e[k]);
+        for (uint32_t i = r + PRE * C; i < cnt; i += C) put(__ldg(coo + z0 + i));
         __syncwarp();
         float b[C][C];
 #pragma unroll
         for (int k0 = 0; k0 < C; k0++) {
-            uint32_t w[4] = {0, 0, 0, 0};
-            const int16_t *row = nat + (k0 * C + r) * C;
-            if (C == 8) { const uint4 v = *reinterpret_cast<const uint4 *>(row); w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w; }
-            else { const uint2 v = *reinterpret_cast<const uint2 *>(row); w[0] = v.x; w[1] = v.y; }
+            const float *row = nat + (k0 * C + r) * C;
 #pragma unroll
-            for (int k2 = 0; k2 < C; k2++) {
-                const int q = (int)(int16_t)((w[k2 / 2] >> ((k2 & 1) * 16)) & 0xffffu);
-                b[k0][k2] = (float)q * dq[k0 + k2];
+            for (int k2 = 0; k2 < C; k2 += 4) {
+                const float4 v = *reinterpret_cast<const float4 *>(row + (C == 8 ? k2 ^ (r & 4) : k2));   // coo_swizzle
+                b[k0][k2] = v.x; b[k0][k2 + 1] = v.y; b[k0][k2 + 2] = v.z; b[k0][k2 + 3] = v.w;
             }
         }
         __syncwarp();
         // wipe what was scattered
 #pragma unroll
         for (int k = 0; k < PRE; k++)
-            if ((uint32_t)(r + k * C) < cnt) nat[(e[k] >> 16) & (G::CS - 1)] = 0;
-        for (uint32_t i = r + PRE * C; i < cnt; i += C) nat[(__ldg(coo + z0 + i) >> 16) & (G::CS - 1)] = 0;
-        idct_store<C>(b, xbuf, cl, r, cube < L.ncubes, L, cube, frames);
+            if ((uint32_t)(r + k * C) < cnt) nat[(e[k] >> 16) & (G::CS - 1)] = 0.0f;
+        for (uint32_t i = r + PRE * C; i < cnt; i += C) nat[(__ldg(coo + z0 + i) >> 16) & (G::CS - 1)] = 0.0f;
+        idct_store<C, true>(b, xbuf, cl, r, cube < L.ncubes, L, cube, frames);
     }
 }
 
@@ -1060,9 +1104,9 @@ reconstruct_kernel(const Layout L, const int16_t *__restrict__ qcubes, uint8_t *
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int cl = lane / C, r = lane % C;
-    float dq[G::NDIAG];
-#pragma unroll
-    for (int s = 0; s < G::NDIAG; s++) dq[s] = (float)quant_divisor(s + r) * lane_scale<C>(r);
+    float *tab = reinterpret_cast<float *>(smem + kWarps * Xch<C, float>::WARP_BYTES);   // float[CS]
+    build_dequant_table<C>(tab, tid);
+    __syncthreads();
     const long long ngroups = (L.ncubes + G::CPW - 1) / G::CPW;
     for (long long g = (long long)blockIdx.x * kWarps + warp; g < ngroups; g += (long long)gridDim.x * kWarps) {
         const long long cube = g * G::CPW + cl;
@@ -1077,13 +1121,19 @@ reconstruct_kernel(const Layout L, const int16_t *__restrict__ qcubes, uint8_t *
                 if (C == 8) { const uint4 v = __ldg(reinterpret_cast<const uint4 *>(src + k0 * C * C)); w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w; }
                 else { const uint2 v = __ldg(reinterpret_cast<const uint2 *>(src + k0 * C * C)); w[0] = v.x; w[1] = v.y; }
             }
+            const float *trow = tab + (k0 * C + r) * C;
 #pragma unroll
-            for (int k2 = 0; k2 < C; k2++) {
-                const int q = (int)(int16_t)((w[k2 / 2] >> ((k2 & 1) * 16)) & 0xffffu);
-                b[k0][k2] = (float)q * dq[k0 + k2];
+            for (int k2 = 0; k2 < C; k2 += 4) {
+                const float4 m = *reinterpret_cast<const float4 *>(trow + (C == 8 ? k2 ^ (r & 4) : k2));   // coo_swizzle
+                const float mm[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    const int q = (int)(int16_t)((w[(k2 + e) / 2] >> (((k2 + e) & 1) * 16)) & 0xffffu);
+                    b[k0][k2 + e] = (float)q * mm[e];     // the same product reconstruct_coo_kernel forms at scatter time
+                }
             }
         }
-        idct_store<C>(b, smem + warp * Xch<C, float>::WARP_BYTES, cl, r, valid, L, cube, frames);
+        idct_store<C, true>(b, smem + warp * Xch<C, float>::WARP_BYTES, cl, r, valid, L, cube, frames);
     }
 }
 
