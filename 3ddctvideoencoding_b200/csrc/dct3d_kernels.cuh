@@ -964,13 +964,13 @@ __device__ __forceinline__ void build_dequant_table(float *tab, int tid)
 // Inverse tail shared by both reconstruct kernels: b[k0][k2] holds the dequantised coefficients of
 // row-frequency k1 = r.  Inverse butterflies along t, exchange, along y and x, clamp to [0,255],
 // truncate (Decoder.java:112, decoder.c:29), store the thread's frame plane.
-template <int C, bool ALL_SCALED = false>
+template <int C, bool ALL_SCALED = false, bool T_DONE = false>
 __device__ __forceinline__ void idct_store(float (&b)[C][C], uint8_t *xbuf, int cl, int r, bool valid, const Layout &L,
                                            long long cube, uint8_t *__restrict__ frames)
 {
     float a[C][C];
     // ALL_SCALED: b already carries S[k0] S[k1] S[k2]; otherwise S[k1] only and the t stage folds in S[k2]
-    if (ALL_SCALED) inv_t_n<C, float>(b); else inv_t_g<C, float>(b);
+    if (!T_DONE) { if (ALL_SCALED) inv_t_n<C, float>(b); else inv_t_g<C, float>(b); }
     Xch<C, float>::transpose(xbuf, cl, r, b, a);   // the exchange is its own inverse
     inv_yx_n<C, float>(a);
     if (!valid) return;
@@ -1069,28 +1069,40 @@ reconstruct_coo_kernel(const Layout L, const uint32_t *__restrict__ coo, const u
         fetch_entries();                        // group g + stride
         fetch_rows(g + 2 * stride);
         // scatter this cube's entries (lane r of the cube takes entries r, r+C, r+2C, ...)
+        {
+            // the table loads of the prefetched entries are issued together (index 0 for an absent entry)
+            uint32_t ix[PRE];
+            float tv[PRE];
 #pragma unroll
-        for (int k = 0; k < PRE; k++)
-            if ((uint32_t)(r + k * C) < cnt) put(e[k]);
+            for (int k = 0; k < PRE; k++) { ix[k] = (e[k] >> 16) & (G::CS - 1); tv[k] = tab[ix[k]]; }
+#pragma unroll
+            for (int k = 0; k < PRE; k++) tv[k] *= (float)(int)(int16_t)(e[k] & 0xffffu);
+#pragma unroll
+            for (int k = 0; k < PRE; k++)
+                if ((uint32_t)(r + k * C) < cnt) nat[ix[k]] = tv[k];
+        }
         for (uint32_t i = r + PRE * C; i < cnt; i += C) put(__ldg(coo + z0 + i));
         __syncwarp();
         float b[C][C];
+        // first halves of all rows, then second halves: the t pass of columns 0..3 starts while the
+        // second halves are still in flight
 #pragma unroll
-        for (int k0 = 0; k0 < C; k0++) {
-            const float *row = nat + (k0 * C + r) * C;
+        for (int k2 = 0; k2 < C; k2 += 4) {
 #pragma unroll
-            for (int k2 = 0; k2 < C; k2 += 4) {
+            for (int k0 = 0; k0 < C; k0++) {
+                const float *row = nat + (k0 * C + r) * C;
                 const float4 v = *reinterpret_cast<const float4 *>(row + (C == 8 ? k2 ^ (r & 4) : k2));   // coo_swizzle
                 b[k0][k2] = v.x; b[k0][k2 + 1] = v.y; b[k0][k2 + 2] = v.z; b[k0][k2 + 3] = v.w;
             }
         }
+        inv_t_n<C, float>(b);
+        // wipe what was scattered, after the t pass: by now every lane's row loads have long landed
         __syncwarp();
-        // wipe what was scattered
 #pragma unroll
         for (int k = 0; k < PRE; k++)
             if ((uint32_t)(r + k * C) < cnt) nat[(e[k] >> 16) & (G::CS - 1)] = 0.0f;
         for (uint32_t i = r + PRE * C; i < cnt; i += C) nat[(__ldg(coo + z0 + i) >> 16) & (G::CS - 1)] = 0.0f;
-        idct_store<C, true>(b, xbuf, cl, r, cube < L.ncubes, L, cube, frames);
+        idct_store<C, true, true>(b, xbuf, cl, r, cube < L.ncubes, L, cube, frames);
     }
 }
 
