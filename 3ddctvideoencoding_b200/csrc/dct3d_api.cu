@@ -57,7 +57,7 @@ struct dct3d_ctx {
     long launches = 0;
     cudaStream_t stream = nullptr;
     std::string err;
-    DevBuf frames, bits, q, status, ctrl, seg, fa, fb, zz, cmask, coo, coocnt;
+    DevBuf frames, bits, q, status, ctrl, seg, seglist, fa, fb, zz, cmask, coo, coocnt;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // around encode_kernel / reconstruct_zz_kernel
     bool ev_valid[2] = {false, false};
     Ctrl *h_ctrl = nullptr;          // pinned
@@ -142,6 +142,7 @@ int upload_tables(dct3d_ctx *ctx)
             }
     }
     CU_CHECK(ctx, cudaMemcpyToSymbol(c_zz, &t, sizeof t));
+    CU_CHECK(ctx, cudaMemcpyToSymbol(g_zz, &t, sizeof t));
     if (ctx->device < 64) g_tables_ready[ctx->device] = true;
     return DCT3D_OK;
 }
@@ -393,7 +394,7 @@ void dct3d_destroy(dct3d_ctx *ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    for (DevBuf *b : {&ctx->frames, &ctx->bits, &ctx->q, &ctx->status, &ctx->ctrl, &ctx->seg, &ctx->fa, &ctx->fb, &ctx->zz, &ctx->cmask, &ctx->coo, &ctx->coocnt}) b->release();
+    for (DevBuf *b : {&ctx->frames, &ctx->bits, &ctx->q, &ctx->status, &ctx->ctrl, &ctx->seg, &ctx->seglist, &ctx->fa, &ctx->fb, &ctx->zz, &ctx->cmask, &ctx->coo, &ctx->coocnt}) b->release();
     for (int i = 0; i < 4; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->h_ctrl) cudaFreeHost(ctx->h_ctrl);
     if (ctx->h_u64) cudaFreeHost(ctx->h_u64);
@@ -573,7 +574,7 @@ int dct3d_eg_encode_i16_dev(dct3d_ctx *ctx, const void *d_qcubes, size_t ncubes,
     return run_pack(ctx, P, d_stream, cap, start_bit, end_bit, st);
 }
 
-// Index discovery + parse: stream -> zig-zag chunk scratch (ctx->zz, ctx->cmask).
+// Index discovery + emit: stream -> CSR lists of the cubes' non-zero coefficients (ctx->coo, ctx->coocnt).
 static int parse_common(dct3d_ctx *ctx, const void *d_stream, size_t nbytes, uint64_t start_bit, size_t ncubes,
                         uint64_t *end_bit, cudaStream_t st)
 {
@@ -595,6 +596,7 @@ static int parse_common(dct3d_ctx *ctx, const void *d_stream, size_t nbytes, uin
     const size_t n = (size_t)P.nseg;
     const size_t off_first = ((4 * n + 1) * 4 + 7) & ~(size_t)7;
     CU_CHECK(ctx, ctx->seg.reserve(off_first + 2 * (n + 1) * 8));
+    CU_CHECK(ctx, ctx->seglist.reserve(((n + 31) / 32) * 32 * kSegListVec * sizeof(uint4)));   // dense-addressed, only the heads are touched
     CU_CHECK(ctx, ctx->ctrl.reserve(sizeof(Ctrl)));
     CU_CHECK(ctx, ctx->coo.reserve(ncubes * CS * sizeof(uint32_t) + 256));   // worst case: every coefficient non-zero
     CU_CHECK(ctx, ctx->coocnt.reserve((ncubes + 1) * 8));
@@ -602,6 +604,7 @@ static int parse_common(dct3d_ctx *ctx, const void *d_stream, size_t nbytes, uin
     P.seg_over = P.seg_count + n;
     P.seg_used = P.seg_over + n + 1;
     P.seg_work = P.seg_used + n;
+    P.seg_list = (uint4 *)ctx->seglist.p;
     P.seg_first = (unsigned long long *)((uint8_t *)ctx->seg.p + off_first);
     P.seg_nzfirst = P.seg_first + n + 1;
     Ctrl *dc = (Ctrl *)ctx->ctrl.p;
@@ -628,8 +631,8 @@ static int parse_common(dct3d_ctx *ctx, const void *d_stream, size_t nbytes, uin
         const long long grid = std::min<long long>(stiles, (long long)ctx->num_sms * 8);
         seg_prefix_kernel<<<(unsigned)grid, kScanThreads, 0, st>>>(P, (unsigned long long *)ctx->status.p,
                                                                    (unsigned long long *)ctx->status.p + stiles, &dc->ticket);
-        const unsigned pg = (unsigned)((P.nseg + kParseThreads - 1) / kParseThreads);
-        if (C == 8) seg_parse_kernel<8><<<pg, kParseThreads, 0, st>>>(P); else seg_parse_kernel<4><<<pg, kParseThreads, 0, st>>>(P);
+        const unsigned pg = (unsigned)std::min<unsigned long long>((P.nseg + kEmitThreads - 1) / kEmitThreads, (unsigned long long)ctx->num_sms * 6);
+        if (C == 8) seg_emit_kernel<8><<<pg, kEmitThreads, 0, st>>>(P); else seg_emit_kernel<4><<<pg, kEmitThreads, 0, st>>>(P);
         ctx->launches += 2;
         CU_CHECK(ctx, cudaGetLastError());
         return DCT3D_OK;

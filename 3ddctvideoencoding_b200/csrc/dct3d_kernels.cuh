@@ -82,6 +82,7 @@ struct ZzTables {
     uint16_t slin4[64];
 };
 __constant__ ZzTables c_zz;
+__device__ ZzTables g_zz;        // the same tables in global memory, for lookups with a per-thread index
 
 template <int C> __device__ __forceinline__ uint16_t zz_base(int j, int s) { return C == 8 ? c_zz.base8[j][s] : c_zz.base4[j][s]; }
 template <int C> __device__ __forceinline__ const uint16_t *zz_lin() { return C == 8 ? c_zz.lin8 : c_zz.lin4; }
@@ -713,6 +714,19 @@ struct GlobalSource : WordBase {
     }
 };
 
+// One segment (plus the reader's look-ahead) copied into the thread's local memory with independent
+// loads: for the single thread that re-walks a segment serially.
+constexpr int kLocalWords = kSegWords + 8;
+struct LocalSource : WordBase {
+    uint32_t w[kLocalWords];
+    __device__ __forceinline__ void fill(const uint32_t *words, unsigned long long nwords)
+    {
+#pragma unroll
+        for (int j = 0; j < kLocalWords; j++) w[j] = w0 + j < nwords ? bswap32(__ldg(words + w0 + j)) : 0u;
+    }
+    __device__ __forceinline__ uint32_t word(uint32_t j) const { return w[min(j, (uint32_t)kLocalWords - 1u)]; }
+};
+
 __device__ __forceinline__ StagedSource stage_stream(uint32_t *s_words, const uint32_t *words, unsigned long long nwords,
                                                      unsigned long long start_bit, unsigned long long first_seg)
 {
@@ -728,6 +742,30 @@ __device__ __forceinline__ StagedSource stage_stream(uint32_t *s_words, const ui
     return src;
 }
 
+// A 1024-bit segment holds at most 342 non-zero codes (3 bits each at least).  The lists live in a
+// dense-addressed scratch of which only the heads (about 24 entries per segment on natural content) are
+// ever touched, interleaved over the 32 segments of a warp: vector v (4 entries) of segment k sits at
+// [k / 32][v][k % 32], so a warp that walks 32 consecutive segments reads and writes whole 512-byte
+// lines.  Entries leave the scanning thread four at a time as one 16-byte store.
+constexpr int kSegListVec = 86;                      // uint4 per segment: 344 entries >= 342
+__device__ __forceinline__ unsigned long long seg_list_base(unsigned long long k)
+{
+    return (k >> 5) * (unsigned long long)(kSegListVec * 32) + (k & 31);
+}
+struct SegListSink {
+    uint4 *dst;                                      // next vector of this segment (stride 32 vectors)
+    uint32_t e0, e1, e2, e3;                         // shift register: branch-free in the scan's hot loop
+    __device__ __forceinline__ void push(uint32_t i, uint32_t e)
+    {
+        e0 = e1; e1 = e2; e2 = e3; e3 = e;
+        if ((i & 3u) == 3u) { *dst = make_uint4(e0, e1, e2, e3); dst += 32; }
+    }
+    __device__ __forceinline__ void flush(uint32_t n)
+    {
+        while (n & 3u) push(n++, 0u);                // pad the last vector
+    }
+};
+
 struct DecParams {
     Layout L;
     const uint32_t *words; unsigned long long nwords; unsigned long long nbits_total;  // stream
@@ -737,6 +775,7 @@ struct DecParams {
     unsigned int *seg_count;            // [nseg] codes starting in the segment | non-zero codes << 16 | malformed << 31
     unsigned int *seg_over;             // [nseg+1] overhang INTO segment k (seg_over[0] = 0)
     unsigned int *seg_used;             // [nseg] entry overhang used for the current count
+    uint4 *seg_list;                    // [nseg][kSegListVec] non-zero codes of each segment (sparsely touched)
     unsigned int *seg_work;             // [nseg] worklist of segments to re-scan
     unsigned int *nwork;
     unsigned long long *seg_first;      // [nseg+1] exclusive prefix of the code counts
@@ -769,8 +808,11 @@ seg_scan_kernel(const DecParams P)
     // A scan from a wrongly assumed entry point may run into an impossible code; that is only an
     // error if it is still there once the entry points have converged, so it is recorded per segment.
     unsigned int bad = 0;
+    SegListSink sink;
+    sink.dst = P.seg_list + seg_list_base(k);
+    sink.e0 = sink.e1 = sink.e2 = sink.e3 = 0u;
     if (seg0 >= lim) { n = 0; next = seg0; }
-    else if (!eg_scan_segment(src, seg0, lim, eos, n, next, &nz)) { bad = 0x80000000u; n = 0; nz = 0; next = lim; }
+    else if (!eg_scan_segment(src, seg0, lim, eos, n, next, &nz, sink)) { bad = 0x80000000u; n = 0; nz = 0; next = lim; }
     P.seg_count[k] = n | (nz << 16) | bad;
     P.seg_used[k] = 0u;
     P.seg_over[k + 1] = next > lim ? next - lim : 0u;
@@ -801,8 +843,11 @@ __global__ void seg_fix_kernel(const DecParams P)
         if (lim > eos) lim = eos;
         uint32_t n = 0, next = 0, nz = 0;
         unsigned int bad = 0;
+        SegListSink sink;
+        sink.dst = P.seg_list + seg_list_base(k);
+        sink.e0 = sink.e1 = sink.e2 = sink.e3 = 0u;
         if (seg0 + entry >= lim) { n = 0; next = seg0 + entry; }
-        else if (!eg_scan_segment(src, seg0 + entry, lim, eos, n, next, &nz)) { bad = 0x80000000u; n = 0; nz = 0; next = lim; }
+        else if (!eg_scan_segment(src, seg0 + entry, lim, eos, n, next, &nz, sink)) { bad = 0x80000000u; n = 0; nz = 0; next = lim; }
         P.seg_count[k] = n | (nz << 16) | bad;
         P.seg_used[k] = entry;
         const unsigned int over = next > lim ? next - lim : 0u;
@@ -877,56 +922,96 @@ seg_prefix_kernel(const DecParams P, unsigned long long *status_codes, unsigned 
     }
 }
 
-// Every thread re-walks its segment, now knowing the index of its first code AND the rank of its
-// first non-zero code in the whole stream, and writes every non-zero coefficient as
-// (natural index << 16 | value) at its rank: a CSR matrix of the cubes with no atomics and contiguous
-// stores.  The thread that passes a cube's first code records the cube's row pointer.
-constexpr int kParseThreads = kSegThreads;
+// Every thread turns its segment's list into rows of a CSR matrix of the cubes: it now knows the index
+// of its first code AND the rank of its first non-zero code in the whole stream, so entry i of its list
+// goes to coo[rank + i] as (list index space of the coefficient << 16 | value) -- contiguous stores, no
+// atomics -- and every cube whose first code lies in the segment gets its row pointer.  No bit is parsed
+// a second time; only the one thread that holds the clip's last code re-walks its segment to report
+// where the stream ends.
+constexpr int kEmitThreads = 128;
+constexpr int kEmitWin = 2048;                        // entries a warp gathers in shared memory before storing them
 
 template <int C>
-__global__ void __launch_bounds__(kParseThreads)
-seg_parse_kernel(const DecParams P)
+__global__ void __launch_bounds__(kEmitThreads)
+seg_emit_kernel(const DecParams P)
 {
     using G = Geo<C>;
-    __shared__ uint32_t s_words[kStageSmem];
-    const unsigned long long k = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
-    const StagedSource src = stage_stream(s_words, P.words, P.nwords, P.start_bit, blockIdx.x * (unsigned long long)kParseThreads);
-    if (k >= P.nseg) return;
+    __shared__ uint16_t s_lin[G::CS];
+    __shared__ uint32_t s_out[kEmitThreads / 32][kEmitWin];
+    for (int i = threadIdx.x; i < G::CS; i += kEmitThreads) s_lin[i] = (C == 8 ? g_zz.slin8 : g_zz.slin4)[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    uint32_t *wout = s_out[threadIdx.x >> 5];
+    for (unsigned long long blk = blockIdx.x; blk * kEmitThreads < P.nseg; blk += gridDim.x) {
+    const unsigned long long k = blk * (unsigned long long)kEmitThreads + threadIdx.x;
+    if (k - lane >= P.nseg) break;                       // whole warp beyond the stream
     const unsigned long long ncodes = (unsigned long long)P.L.ncubes * G::CS;
-    unsigned long long cur = P.seg_first[k];
-    unsigned long long hi = P.seg_first[k + 1];
+    const bool inside = k < P.nseg;
+    const unsigned long long cur = inside ? P.seg_first[k] : ncodes;
+    unsigned long long hi = inside ? P.seg_first[k + 1] : ncodes;
+    const bool last = cur < ncodes && hi >= ncodes;     // this segment holds the clip's last code
     if (hi > ncodes) hi = ncodes;
-    if (cur >= hi) return;
-    unsigned long long zrank = P.seg_nzfirst[k];
-    uint32_t pos = (uint32_t)(cur % G::CS);            // position inside the current cube
-    unsigned long long cube = cur / G::CS;
-    const uint16_t *lin = zz_slin<C>();
-    BitReader<StagedSource> br(src, src.rel(P.start_bit + k * (unsigned long long)P.seg_bits) + P.seg_over[k]);
-    while (cur < hi) {
-        if (pos == 0) P.coo_start[cube] = zrank;       // this thread owns the cube's first code
-        // one iteration = a run of one-bits (zero coefficients, cut at the cube end) + one longer code
-        br.refill();
-        uint32_t ones = (uint32_t)clz32(~br.hi);
-        const unsigned long long room = hi - cur;
-        if (ones > room) ones = (uint32_t)room;
-        if (ones > (uint32_t)G::CS - pos) ones = (uint32_t)G::CS - pos;
-        cur += ones;
-        pos += ones;
-        br.skip((int)ones);
-        if (pos == (uint32_t)G::CS) { pos = 0; cube++; continue; }
-        if (cur >= hi) break;
-        br.refill();
-        if (br.hi >> 31) continue;
-        uint32_t m;
-        const uint32_t at = br.pos;
-        if (!br.take_code(m)) { atomicOr(P.err, at + 17u >= src.rel(P.nbits_total) ? 4u : 2u); return; }
-        P.coo[zrank++] = ((uint32_t)lin[pos] << 16) | ((uint32_t)eg_unmap(m) & 0xffffu);
-        cur++;
-        if (++pos == (uint32_t)G::CS) { pos = 0; cube++; }
+    const bool active = cur < hi;
+    const uint32_t span = active ? (uint32_t)(hi - cur) : 0u;   // codes of this segment that belong to the clip
+    const uint32_t nz = active ? (P.seg_count[k] >> 16) & 0x7fffu : 0u;
+    const unsigned long long zr = inside ? P.seg_nzfirst[k] : 0ull;
+    // The 32 segments of the warp own one contiguous range of the output, starting at lane 0's rank:
+    // entries are gathered in the warp's window and leave as whole lines (entries past the window,
+    // i.e. dense content, are stored directly).
+    const unsigned long long zr0 = __shfl_sync(0xffffffffu, zr, 0);
+    const unsigned long long off = zr - zr0;
+    const uint32_t pos0 = (uint32_t)(cur % G::CS);      // position of the first code inside its cube
+    unsigned long long cube = cur / G::CS + (pos0 ? 1 : 0);   // next cube to start at or after `cur`
+    uint32_t nb = pos0 ? (uint32_t)G::CS - pos0 : 0u;   // its first code, relative to `cur`
+    const uint4 *lst = P.seg_list + seg_list_base(k);
+    uint32_t i = 0;
+    auto take = [&](uint32_t e, uint32_t idx) {
+        const uint32_t rel = e >> 17;
+        if (idx < nz && rel < span) {
+            while (nb <= rel) { P.coo_start[cube++] = zr + i; nb += G::CS; }
+            const uint32_t x = ((uint32_t)s_lin[(pos0 + rel) & (G::CS - 1)] << 16) | ((uint32_t)eg_unmap(e & 0x1ffffu) & 0xffffu);
+            if (off + i < (unsigned long long)kEmitWin) wout[(uint32_t)off + i] = x; else P.coo[zr + i] = x;
+            i++;
+        }
+    };
+    // the first 32 entries (all of them on natural content) are fetched with independent loads
+    constexpr int PRE = 8;
+    uint4 q[PRE];
+#pragma unroll
+    for (int v = 0; v < PRE; v++) q[v] = (uint32_t)v * 4 < nz ? __ldg(lst + v * 32) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (int v = 0; v < PRE; v++) {
+        if ((uint32_t)v * 4 < nz) {
+            take(q[v].x, v * 4); take(q[v].y, v * 4 + 1); take(q[v].z, v * 4 + 2); take(q[v].w, v * 4 + 3);
+        }
     }
-    if (hi == ncodes) {
-        *P.end_bit = src.w0 * 32ull + br.pos;
-        P.coo_start[P.L.ncubes] = zrank;
+    for (uint32_t v = PRE; v * 4 < nz; v++) {
+        const uint4 x = __ldg(lst + v * 32);
+        take(x.x, v * 4); take(x.y, v * 4 + 1); take(x.z, v * 4 + 2); take(x.w, v * 4 + 3);
+    }
+    while (nb < span) { P.coo_start[cube++] = zr + i; nb += G::CS; }
+    // flush the window
+    unsigned long long top = active ? off + i : 0ull;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) top = max(top, __shfl_xor_sync(0xffffffffu, top, d));
+    const uint32_t nflush = (uint32_t)min(top, (unsigned long long)kEmitWin);
+    __syncwarp();
+    for (uint32_t j = lane; j < nflush; j += 32) P.coo[zr0 + j] = wout[j];
+    if (last) {
+        P.coo_start[P.L.ncubes] = zr + i;
+        // where does the clip end?  re-walk this one segment up to its last code
+        LocalSource src;
+        src.w0 = (P.start_bit >> 5) + k * kSegWords;
+        src.fill(P.words, P.nwords);
+        const uint32_t seg0 = src.rel(P.start_bit + k * (unsigned long long)P.seg_bits);
+        const uint32_t eos = src.rel(P.nbits_total);
+        uint32_t lim = seg0 + P.seg_bits;
+        if (lim > eos) lim = eos;
+        uint32_t n = 0, next = seg0 + P.seg_over[k];
+        if (!eg_scan_segment<LocalSource, NullNzSink, true>(src, seg0 + P.seg_over[k], lim, eos, n, next, nullptr, NullNzSink(), span)) atomicOr(P.err, 2u);
+        *P.end_bit = src.w0 * 32ull + next;
+    }
+    __syncwarp();                                        // the window is reused by the next block
     }
 }
 

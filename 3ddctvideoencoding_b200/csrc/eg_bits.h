@@ -291,12 +291,22 @@ EG_HD uint32_t eg_parse_cube(const Source &src, uint32_t start, const uint16_t *
     return br.pos;
 }
 
+// Sink for the non-zero codes a segment scan meets: push(i, e) receives the i-th non-zero code of the
+// segment as e = (code index relative to the segment's first code) << 17 | m, with m the 17-bit code
+// number (value = eg_unmap(m)); the hot loop of the scan leaves the sign mapping to the reader.
+struct NullNzSink {
+    EG_HD void push(uint32_t, uint32_t) {}
+    EG_HD void flush(uint32_t) {}
+};
+
 // Count the codes that START in [start, limit) and report where the first code at or after
 // `limit` starts (stream segments for index discovery).  Returns false on a malformed code
-// (zero padding after the last code of the stream is not an error).
-template <typename Source>
+// (zero padding after the last code of the stream is not an error).  With STOP the scan ends after
+// stop_after codes instead (next_start = first bit after them).
+template <typename Source, typename NzSink = NullNzSink, bool STOP = false>
 EG_HD bool eg_scan_segment(const Source &src, uint32_t start, uint32_t limit, uint32_t end_of_stream,
-                           uint32_t &ncodes, uint32_t &next_start, uint32_t *nonzero = nullptr)
+                           uint32_t &ncodes, uint32_t &next_start, uint32_t *nonzero = nullptr, NzSink sink = NzSink(),
+                           uint32_t stop_after = 0)
 {
     BitReader<Source> br(src, start);
     uint32_t n = 0, nz = 0;
@@ -305,9 +315,10 @@ EG_HD bool eg_scan_segment(const Source &src, uint32_t start, uint32_t limit, ui
         uint32_t ones = (uint32_t)clz32(~br.hi);
         const uint32_t room = limit - br.pos;
         if (ones > room) ones = room;
+        if (STOP && ones > stop_after - n) ones = stop_after - n;
         n += ones;
         br.skip((int)ones);
-        if (br.pos >= limit) break;
+        if (br.pos >= limit || (STOP && n >= stop_after)) break;
         br.refill();
         if (br.hi >> 31) continue;
         uint32_t m;
@@ -316,9 +327,12 @@ EG_HD bool eg_scan_segment(const Source &src, uint32_t start, uint32_t limit, ui
             if (at + 17 >= end_of_stream || clz32(br.hi) + at >= end_of_stream) { br.pos = limit > at ? limit : at; break; }
             return false;
         }
+        sink.push(nz, (n << 17) | m);
         n++;
         nz++;
+        if (STOP && n >= stop_after) break;
     }
+    sink.flush(nz);
     ncodes = n;
     next_start = br.pos;
     if (nonzero) *nonzero = nz;
