@@ -631,7 +631,7 @@ static int parse_common(dct3d_ctx *ctx, const void *d_stream, size_t nbytes, uin
         const long long grid = std::min<long long>(stiles, (long long)ctx->num_sms * 8);
         seg_prefix_kernel<<<(unsigned)grid, kScanThreads, 0, st>>>(P, (unsigned long long *)ctx->status.p,
                                                                    (unsigned long long *)ctx->status.p + stiles, &dc->ticket);
-        const unsigned pg = (unsigned)std::min<unsigned long long>((P.nseg + kEmitThreads - 1) / kEmitThreads, (unsigned long long)ctx->num_sms * 6);
+        const unsigned pg = (unsigned)std::min<unsigned long long>((P.nseg + kEmitThreads - 1) / kEmitThreads, (unsigned long long)ctx->num_sms * 8);
         if (C == 8) seg_emit_kernel<8><<<pg, kEmitThreads, 0, st>>>(P); else seg_emit_kernel<4><<<pg, kEmitThreads, 0, st>>>(P);
         ctx->launches += 2;
         CU_CHECK(ctx, cudaGetLastError());

@@ -678,6 +678,7 @@ eg_pack_kernel(const EncParams P)
 // byte-swapped, one padding word per 32 so that threads 32 words apart hit different banks.
 constexpr int kSegWords = 32;                       // 1024-bit segments
 constexpr int kSegThreads = 128;
+constexpr unsigned kLeadBits = 96;                  // lead-in walk of the speculative scan
 constexpr int kStageN = kSegThreads * kSegWords + 32;   // + margin for codes running past the last segment
 constexpr int kStageSmem = kStageN + kStageN / 32 + 1;
 
@@ -728,9 +729,10 @@ struct LocalSource : WordBase {
 };
 
 __device__ __forceinline__ StagedSource stage_stream(uint32_t *s_words, const uint32_t *words, unsigned long long nwords,
-                                                     unsigned long long start_bit, unsigned long long first_seg)
+                                                     unsigned long long start_bit, unsigned long long first_seg,
+                                                     unsigned int lead_words = 0)
 {
-    const unsigned long long w0 = (start_bit >> 5) + first_seg * kSegWords;
+    const unsigned long long w0 = (start_bit >> 5) + first_seg * kSegWords - lead_words;
     for (int j = threadIdx.x; j < kStageN; j += blockDim.x) {
         const unsigned long long i = w0 + j;
         s_words[j + (j >> 5)] = i < nwords ? bswap32(__ldg(words + i)) : 0u;
@@ -791,36 +793,47 @@ struct DecParams {
     uint8_t *frames;
 };
 
-// Pass 1: every thread scans one segment assuming that a code starts at its first bit, and
-// records how far its last code runs into the next segment (seg_over[k+1]).
+// Pass 1: every thread scans one segment from a guessed entry point (see the lead-in walk), keeps the
+// non-zero codes it meets, and records how far its last code runs into the next segment (seg_over[k+1]).
 __global__ void __launch_bounds__(kSegThreads)
 seg_scan_kernel(const DecParams P)
 {
     __shared__ uint32_t s_words[kStageSmem];
     const unsigned long long k = blockIdx.x * (unsigned long long)kSegThreads + threadIdx.x;
-    const StagedSource src = stage_stream(s_words, P.words, P.nwords, P.start_bit, blockIdx.x * (unsigned long long)kSegThreads);
+    // the window starts 4 words early (not for the first CTA): room for the lead-in walk below
+    const StagedSource src = stage_stream(s_words, P.words, P.nwords, P.start_bit, blockIdx.x * (unsigned long long)kSegThreads,
+                                          blockIdx.x ? 4u : 0u);
     if (k >= P.nseg) return;
     const uint32_t seg0 = src.rel(P.start_bit + k * (unsigned long long)P.seg_bits);
     const uint32_t eos = src.rel(P.nbits_total);
     uint32_t lim = seg0 + P.seg_bits;
     if (lim > eos) lim = eos;
     uint32_t n = 0, next = 0, nz = 0;
+    // Guess the entry point: walk the last kLeadBits bits of the previous segment from an arbitrary
+    // phase.  Exp-Golomb streams resynchronise within a few codes (every run of one-bits is a run of
+    // complete codes), so the walk usually arrives at the segment's first code; the guess is verified
+    // against the predecessor's overhang by seg_check_kernel like any other.
+    uint32_t entry = 0;
+    if (k > 0 && seg0 < lim) {
+        uint32_t nd, nx;
+        if (eg_scan_segment(src, seg0 - kLeadBits, seg0, eos, nd, nx) && nx - seg0 <= 33u) entry = nx - seg0;
+    }
     // A scan from a wrongly assumed entry point may run into an impossible code; that is only an
     // error if it is still there once the entry points have converged, so it is recorded per segment.
     unsigned int bad = 0;
     SegListSink sink;
     sink.dst = P.seg_list + seg_list_base(k);
     sink.e0 = sink.e1 = sink.e2 = sink.e3 = 0u;
-    if (seg0 >= lim) { n = 0; next = seg0; }
-    else if (!eg_scan_segment(src, seg0, lim, eos, n, next, &nz, sink)) { bad = 0x80000000u; n = 0; nz = 0; next = lim; }
+    if (seg0 + entry >= lim) { n = 0; next = seg0 + entry; }
+    else if (!eg_scan_segment(src, seg0 + entry, lim, eos, n, next, &nz, sink)) { bad = 0x80000000u; n = 0; nz = 0; next = lim; }
     P.seg_count[k] = n | (nz << 16) | bad;
-    P.seg_used[k] = 0u;
+    P.seg_used[k] = entry;
     P.seg_over[k + 1] = next > lim ? next - lim : 0u;
 }
 
 // Fix-up rounds: list the segments whose true entry point (the predecessor's overhang) differs from
-// the one they were scanned with, then re-scan only those (about one in seven on the first round,
-// almost none afterwards), until nothing changes.
+// the one they were scanned with, then re-scan only those (one in seven without the lead-in walk, far
+// fewer with it; almost none on the second round), until nothing changes.
 __global__ void seg_check_kernel(const DecParams P)
 {
     const unsigned long long k = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
@@ -833,9 +846,9 @@ __global__ void seg_fix_kernel(const DecParams P)
     const unsigned int nwork = *P.nwork;
     for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < nwork; i += gridDim.x * blockDim.x) {
         const unsigned long long k = P.seg_work[i];
-        const unsigned long long w0 = (P.start_bit >> 5) + k * kSegWords;
-        GlobalSource src;                                      // scattered segments: plain global reads
-        src.w0 = w0; src.words = P.words; src.nwords = P.nwords;
+        LocalSource src;                                       // the segment is fetched with independent loads, then walked
+        src.w0 = (P.start_bit >> 5) + k * kSegWords;
+        src.fill(P.words, P.nwords);
         const unsigned int entry = P.seg_over[k];
         const uint32_t seg0 = src.rel(P.start_bit + k * (unsigned long long)P.seg_bits);
         const uint32_t eos = src.rel(P.nbits_total);
@@ -929,10 +942,10 @@ seg_prefix_kernel(const DecParams P, unsigned long long *status_codes, unsigned 
 // a second time; only the one thread that holds the clip's last code re-walks its segment to report
 // where the stream ends.
 constexpr int kEmitThreads = 128;
-constexpr int kEmitWin = 2048;                        // entries a warp gathers in shared memory before storing them
+constexpr int kEmitWin = 1024;                        // entries a warp gathers in shared memory before storing them
 
 template <int C>
-__global__ void __launch_bounds__(kEmitThreads)
+__global__ void __launch_bounds__(kEmitThreads, 8)
 seg_emit_kernel(const DecParams P)
 {
     using G = Geo<C>;
