@@ -598,7 +598,7 @@ static int parse_common(dct3d_ctx *ctx, const void *d_stream, size_t nbytes, uin
     CU_CHECK(ctx, ctx->seg.reserve(off_first + 2 * (n + 1) * 8));
     CU_CHECK(ctx, ctx->seglist.reserve(((n + 31) / 32) * 32 * kSegListVec * sizeof(uint4)));   // dense-addressed, only the heads are touched
     CU_CHECK(ctx, ctx->ctrl.reserve(sizeof(Ctrl)));
-    CU_CHECK(ctx, ctx->coo.reserve(ncubes * CS * sizeof(uint32_t) + 256));   // worst case: every coefficient non-zero
+    CU_CHECK(ctx, ctx->coo.reserve(ncubes * CS * sizeof(uint32_t) + 2048));   // worst case: every coefficient non-zero, + the tail of the last segment's list
     CU_CHECK(ctx, ctx->coocnt.reserve((ncubes + 1) * 8));
     P.seg_count = (unsigned int *)ctx->seg.p;
     P.seg_over = P.seg_count + n;
@@ -631,7 +631,7 @@ static int parse_common(dct3d_ctx *ctx, const void *d_stream, size_t nbytes, uin
         const long long grid = std::min<long long>(stiles, (long long)ctx->num_sms * 8);
         seg_prefix_kernel<<<(unsigned)grid, kScanThreads, 0, st>>>(P, (unsigned long long *)ctx->status.p,
                                                                    (unsigned long long *)ctx->status.p + stiles, &dc->ticket);
-        const unsigned pg = (unsigned)std::min<unsigned long long>((P.nseg + kEmitThreads - 1) / kEmitThreads, (unsigned long long)ctx->num_sms * 8);
+        const unsigned pg = (unsigned)std::min<unsigned long long>((P.nseg + kEmitThreads - 1) / kEmitThreads, (unsigned long long)ctx->num_sms * 12);
         if (C == 8) seg_emit_kernel<8><<<pg, kEmitThreads, 0, st>>>(P); else seg_emit_kernel<4><<<pg, kEmitThreads, 0, st>>>(P);
         ctx->launches += 2;
         CU_CHECK(ctx, cudaGetLastError());

@@ -935,96 +935,101 @@ seg_prefix_kernel(const DecParams P, unsigned long long *status_codes, unsigned 
     }
 }
 
-// Every thread turns its segment's list into rows of a CSR matrix of the cubes: it now knows the index
-// of its first code AND the rank of its first non-zero code in the whole stream, so entry i of its list
-// goes to coo[rank + i] as (list index space of the coefficient << 16 | value) -- contiguous stores, no
-// atomics -- and every cube whose first code lies in the segment gets its row pointer.  No bit is parsed
-// a second time; only the one thread that holds the clip's last code re-walks its segment to report
-// where the stream ends.
+// Segment lists -> rows of a CSR matrix of the cubes.  A warp owns 32 consecutive segments; every lane
+// knows its segment's first code index and the rank of its first non-zero code in the whole stream, so
+// entry i of segment s goes to coo[rank_s + i] as (list index space of the coefficient << 16 | value).
+// The copy is ENTRY-parallel: the warp walks the concatenation of its 32 lists 32 entries at a time
+// (a lane finds its entry's segment by a shuffle binary search over the prefix of the list lengths), so
+// sparse and dense content keep all lanes busy and the stores are contiguous.  Row pointers: each lane
+// bisects its own (sorted) list for every cube whose first code lies in its segment.  No bit is parsed a
+// second time; only the one thread that holds the clip's last code re-walks its segment to report where
+// the stream ends.
 constexpr int kEmitThreads = 128;
-constexpr int kEmitWin = 1024;                        // entries a warp gathers in shared memory before storing them
 
 template <int C>
-__global__ void __launch_bounds__(kEmitThreads, 8)
+__global__ void __launch_bounds__(kEmitThreads, 12)
 seg_emit_kernel(const DecParams P)
 {
     using G = Geo<C>;
     __shared__ uint16_t s_lin[G::CS];
-    __shared__ uint32_t s_out[kEmitThreads / 32][kEmitWin];
     for (int i = threadIdx.x; i < G::CS; i += kEmitThreads) s_lin[i] = (C == 8 ? g_zz.slin8 : g_zz.slin4)[i];
     __syncthreads();
     const int lane = threadIdx.x & 31;
-    uint32_t *wout = s_out[threadIdx.x >> 5];
-    for (unsigned long long blk = blockIdx.x; blk * kEmitThreads < P.nseg; blk += gridDim.x) {
-    const unsigned long long k = blk * (unsigned long long)kEmitThreads + threadIdx.x;
-    if (k - lane >= P.nseg) break;                       // whole warp beyond the stream
+    const uint32_t *lists = reinterpret_cast<const uint32_t *>(P.seg_list);
     const unsigned long long ncodes = (unsigned long long)P.L.ncubes * G::CS;
-    const bool inside = k < P.nseg;
-    const unsigned long long cur = inside ? P.seg_first[k] : ncodes;
-    unsigned long long hi = inside ? P.seg_first[k + 1] : ncodes;
-    const bool last = cur < ncodes && hi >= ncodes;     // this segment holds the clip's last code
-    if (hi > ncodes) hi = ncodes;
-    const bool active = cur < hi;
-    const uint32_t span = active ? (uint32_t)(hi - cur) : 0u;   // codes of this segment that belong to the clip
-    const uint32_t nz = active ? (P.seg_count[k] >> 16) & 0x7fffu : 0u;
-    const unsigned long long zr = inside ? P.seg_nzfirst[k] : 0ull;
-    // The 32 segments of the warp own one contiguous range of the output, starting at lane 0's rank:
-    // entries are gathered in the warp's window and leave as whole lines (entries past the window,
-    // i.e. dense content, are stored directly).
-    const unsigned long long zr0 = __shfl_sync(0xffffffffu, zr, 0);
-    const unsigned long long off = zr - zr0;
-    const uint32_t pos0 = (uint32_t)(cur % G::CS);      // position of the first code inside its cube
-    unsigned long long cube = cur / G::CS + (pos0 ? 1 : 0);   // next cube to start at or after `cur`
-    uint32_t nb = pos0 ? (uint32_t)G::CS - pos0 : 0u;   // its first code, relative to `cur`
-    const uint4 *lst = P.seg_list + seg_list_base(k);
-    uint32_t i = 0;
-    auto take = [&](uint32_t e, uint32_t idx) {
-        const uint32_t rel = e >> 17;
-        if (idx < nz && rel < span) {
-            while (nb <= rel) { P.coo_start[cube++] = zr + i; nb += G::CS; }
-            const uint32_t x = ((uint32_t)s_lin[(pos0 + rel) & (G::CS - 1)] << 16) | ((uint32_t)eg_unmap(e & 0x1ffffu) & 0xffffu);
-            if (off + i < (unsigned long long)kEmitWin) wout[(uint32_t)off + i] = x; else P.coo[zr + i] = x;
-            i++;
+    for (unsigned long long blk = blockIdx.x; blk * kEmitThreads < P.nseg; blk += gridDim.x) {
+        const unsigned long long k = blk * (unsigned long long)kEmitThreads + threadIdx.x;
+        const unsigned long long kw = k - lane;                  // the warp's first segment
+        if (kw >= P.nseg) break;                                 // whole warp beyond the stream
+        const bool inside = k < P.nseg;
+        const unsigned long long cur = inside ? P.seg_first[k] : ncodes;
+        unsigned long long hi = inside ? P.seg_first[k + 1] : ncodes;
+        const bool last = cur < ncodes && hi >= ncodes;          // this segment holds the clip's last code
+        if (hi > ncodes) hi = ncodes;
+        const bool active = cur < hi;
+        const uint32_t span = active ? (uint32_t)(hi - cur) : 0u;   // codes of this segment that belong to the clip
+        const uint32_t cnt = active ? (P.seg_count[k] >> 16) & 0x7fffu : 0u;
+        const unsigned long long zr = inside ? P.seg_nzfirst[k] : 0ull;
+        const uint32_t pos0 = (uint32_t)(cur % G::CS);           // position of the first code inside its cube
+        // word address of entry i of segment kw + s:  wbase + s * 4 + (i >> 2) * 128 + (i & 3)
+        const unsigned long long wbase = (kw >> 5) * (unsigned long long)(kSegListVec * 32 * 4);
+        auto entry = [&](int s, uint32_t i) { return __ldg(lists + wbase + (unsigned)s * 4u + (i >> 2) * 128u + (i & 3u)); };
+
+        // ---- entries: warp-wide, 32 at a time -----------------------------------------------------
+        uint32_t off = cnt;                                      // exclusive prefix of the list lengths
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, off, d); if (lane >= d) off += o; }
+        const uint32_t total = __shfl_sync(0xffffffffu, off, 31);
+        off -= cnt;
+        const unsigned long long dst0 = zr - off;                // coo index of this segment's entry i is dst0 + off + i
+#pragma unroll 8
+        for (uint32_t j0 = 0; j0 < total; j0 += 32) {
+            const uint32_t j = j0 + lane;
+            int s = 0;
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1) {
+                const uint32_t o = __shfl_sync(0xffffffffu, off, (s + step) & 31);
+                if (s + step < 32 && o <= j) s += step;
+            }
+            const uint32_t so = __shfl_sync(0xffffffffu, off, s);
+            const uint32_t sp = __shfl_sync(0xffffffffu, pos0, s);
+            const unsigned long long sd = __shfl_sync(0xffffffffu, dst0, s);
+            if (j < total) {
+                const uint32_t e = entry(s, j - so);
+                const uint32_t rel = e >> 17;
+                P.coo[sd + j] = ((uint32_t)s_lin[(sp + rel) & (G::CS - 1)] << 16) | ((uint32_t)eg_unmap(e & 0x1ffffu) & 0xffffu);
+            }
         }
-    };
-    // the first 32 entries (all of them on natural content) are fetched with independent loads
-    constexpr int PRE = 8;
-    uint4 q[PRE];
-#pragma unroll
-    for (int v = 0; v < PRE; v++) q[v] = (uint32_t)v * 4 < nz ? __ldg(lst + v * 32) : make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-    for (int v = 0; v < PRE; v++) {
-        if ((uint32_t)v * 4 < nz) {
-            take(q[v].x, v * 4); take(q[v].y, v * 4 + 1); take(q[v].z, v * 4 + 2); take(q[v].w, v * 4 + 3);
+
+        // ---- row pointers: this lane's cubes ------------------------------------------------------
+        // first entry with rel >= bound (the list is sorted by rel)
+        auto lower_bound = [&](uint32_t bound) {
+            uint32_t lo = 0, up = cnt;
+            while (lo < up) {
+                const uint32_t mid = (lo + up) >> 1;
+                if ((entry(lane, mid) >> 17) < bound) lo = mid + 1; else up = mid;
+            }
+            return lo;
+        };
+        if (active) {
+            unsigned long long cube = cur / G::CS + (pos0 ? 1 : 0);       // next cube to start at or after `cur`
+            for (uint32_t nb = pos0 ? (uint32_t)G::CS - pos0 : 0u; nb < span; nb += G::CS)
+                P.coo_start[cube++] = zr + (nb ? lower_bound(nb) : 0u);
         }
-    }
-    for (uint32_t v = PRE; v * 4 < nz; v++) {
-        const uint4 x = __ldg(lst + v * 32);
-        take(x.x, v * 4); take(x.y, v * 4 + 1); take(x.z, v * 4 + 2); take(x.w, v * 4 + 3);
-    }
-    while (nb < span) { P.coo_start[cube++] = zr + i; nb += G::CS; }
-    // flush the window
-    unsigned long long top = active ? off + i : 0ull;
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) top = max(top, __shfl_xor_sync(0xffffffffu, top, d));
-    const uint32_t nflush = (uint32_t)min(top, (unsigned long long)kEmitWin);
-    __syncwarp();
-    for (uint32_t j = lane; j < nflush; j += 32) P.coo[zr0 + j] = wout[j];
-    if (last) {
-        P.coo_start[P.L.ncubes] = zr + i;
-        // where does the clip end?  re-walk this one segment up to its last code
-        LocalSource src;
-        src.w0 = (P.start_bit >> 5) + k * kSegWords;
-        src.fill(P.words, P.nwords);
-        const uint32_t seg0 = src.rel(P.start_bit + k * (unsigned long long)P.seg_bits);
-        const uint32_t eos = src.rel(P.nbits_total);
-        uint32_t lim = seg0 + P.seg_bits;
-        if (lim > eos) lim = eos;
-        uint32_t n = 0, next = seg0 + P.seg_over[k];
-        if (!eg_scan_segment<LocalSource, NullNzSink, true>(src, seg0 + P.seg_over[k], lim, eos, n, next, nullptr, NullNzSink(), span)) atomicOr(P.err, 2u);
-        *P.end_bit = src.w0 * 32ull + next;
-    }
-    __syncwarp();                                        // the window is reused by the next block
+        if (last) {
+            P.coo_start[P.L.ncubes] = zr + lower_bound(span);
+            // where does the clip end?  re-walk this one segment up to its last code
+            LocalSource src;
+            src.w0 = (P.start_bit >> 5) + k * kSegWords;
+            src.fill(P.words, P.nwords);
+            const uint32_t seg0 = src.rel(P.start_bit + k * (unsigned long long)P.seg_bits);
+            const uint32_t eos = src.rel(P.nbits_total);
+            uint32_t lim = seg0 + P.seg_bits;
+            if (lim > eos) lim = eos;
+            uint32_t n = 0, next = seg0 + P.seg_over[k];
+            if (!eg_scan_segment<LocalSource, NullNzSink, true>(src, seg0 + P.seg_over[k], lim, eos, n, next, nullptr, NullNzSink(), span)) atomicOr(P.err, 2u);
+            *P.end_bit = src.w0 * 32ull + next;
+        }
     }
 }
 
