@@ -1184,7 +1184,15 @@ reconstruct_coo_kernel(const Layout L, const uint32_t *__restrict__ coo, const u
             for (int k = 0; k < PRE; k++)
                 if ((uint32_t)(r + k * C) < cnt) nat[ix[k]] = tv[k];
         }
-        for (uint32_t i = r + PRE * C; i < cnt; i += C) put(__ldg(coo + z0 + i));
+        // dense cubes: the rest of the list, four independent loads at a time
+        for (uint32_t i = r + PRE * C; i < cnt; i += 4 * C) {
+            uint32_t x[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) x[k] = i + k * C < cnt ? __ldg(coo + z0 + i + k * C) : 0u;
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (i + k * C < cnt) put(x[k]);
+        }
         __syncwarp();
         float b[C][C];
         // first halves of all rows, then second halves: the t pass of columns 0..3 starts while the
@@ -1204,7 +1212,14 @@ reconstruct_coo_kernel(const Layout L, const uint32_t *__restrict__ coo, const u
 #pragma unroll
         for (int k = 0; k < PRE; k++)
             if ((uint32_t)(r + k * C) < cnt) nat[(e[k] >> 16) & (G::CS - 1)] = 0.0f;
-        for (uint32_t i = r + PRE * C; i < cnt; i += C) nat[(__ldg(coo + z0 + i) >> 16) & (G::CS - 1)] = 0.0f;
+        for (uint32_t i = r + PRE * C; i < cnt; i += 4 * C) {
+            uint32_t x[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) x[k] = i + k * C < cnt ? __ldg(coo + z0 + i + k * C) : 0u;
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (i + k * C < cnt) nat[(x[k] >> 16) & (G::CS - 1)] = 0.0f;
+        }
         idct_store<C, true, true>(b, xbuf, cl, r, cube < L.ncubes, L, cube, frames);
     }
 }
