@@ -353,10 +353,10 @@ def run_ours(args):
             "encode_fps": world * F / (enc_ms_max * 1e-3), "decode_fps": world * F / (dec_ms_max * 1e-3),
             "encode_ms": enc_ms_max, "decode_ms": dec_ms_max,
             "roofline": {"bound": "hbm", "kernel": dom[0], "kernel_ms": dom[1], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": 544.1e6 if dom[0].startswith("recon") else 632.8e6,
+                         "frac": achieved / peak, "traffic": 543.0e6 if dom[0].startswith("recon") else 635.0e6,
                          "peak_source": peak_src, "algorithmic_bytes": int(alg_bytes),
                          "traffic_source": "ncu dram__bytes_read+write of that kernel, profiles/r1_summary.md",
-                         "note": "the fused u8<->bitstream kernels are issue-bound (SM 69-79%, DRAM 11-20%), not HBM-bound: "
+                         "note": "the fused u8<->bitstream kernels are issue-bound (SM 62-82%, DRAM 13-21%), not HBM-bound: "
                                  "DESIGN.md 4; the HBM-bound float seam is in roofline_f32_seam"},
             "kernels_ms": {"encode_kernel": kenc_ms, "reconstruct_coo_kernel": krec_ms},
             "roofline_f32_seam": None if seam is None else {

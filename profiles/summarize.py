@@ -80,33 +80,33 @@ def main():
     lh = lrows[0]
     ki, vi = lh.index("Kernel Name"), lh.index("Metric Value")
     ui = lh.index("Metric Unit")
-    agg = OrderedDict()
+    # bench.py's whole-clip steps run on bench.py's own stream (the stream of the first launch); the
+    # f32 seam measurement shares it, the 32-frame ranges of the e2e leg run on the contexts' streams
+    si = lh.index("Stream")
+    main_stream = None
+    agg, other = OrderedDict(), OrderedDict()
     for r in lrows[1:]:
         if len(r) <= vi or "gpu__time_duration" not in r[lh.index("Metric Name")]:
             continue
         v = float(r[vi].replace(",", ""))
         v = v / 1e3 if r[ui] in ("ns", "nsecond") else v
-        agg.setdefault(short(r[ki]), []).append(v)
-    # bench.py also launches the f32 seam kernels and the 32-frame ranges of the e2e leg: keep the
-    # whole-clip launches (within 2x of the kernel's longest) for the step shares, list the rest apart
-    full = OrderedDict((k, [x for x in v if x > 0.5 * max(v)]) for k, v in agg.items())
-    step = OrderedDict((k, v) for k, v in full.items() if not k.startswith("transform_kernel"))
-    total = sum(sum(v) / len(v) for k, v in step.items())
-    out.append("## Launch list of bench.py (whole-clip launches, 256 frames; warm-up and timed steps alike)")
+        if main_stream is None:
+            main_stream = r[si]
+        name = short(r[ki])
+        (agg if r[si] == main_stream and not name.startswith("transform_kernel") else other).setdefault(name, []).append(v)
+    nsteps = len(agg[next(iter(agg))])
+    total = sum(sum(v) for v in agg.values()) / nsteps
+    out.append(f"## Launch list of bench.py: the {nsteps} whole-clip steps (256 frames; warm-up and timed alike)")
     out.append("")
-    out.append("| kernel | launches | mean us | per step | share of the step's GPU time |")
+    out.append("| kernel | launches per step | mean us | us per step | share of the step's GPU time |")
     out.append("|---|---|---|---|---|")
-    for k, v in sorted(step.items(), key=lambda kv: -sum(kv[1]) / len(kv[1])):
-        per = 1
-        out.append(f"| {k} | {len(v)} | {sum(v) / len(v):.1f} | {per} | {100 * per * sum(v) / len(v) / total:.1f}% |")
+    for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
+        out.append(f"| {k} | {len(v) / nsteps:g} | {sum(v) / len(v):.1f} | {sum(v) / nsteps:.1f} | {100 * sum(v) / nsteps / total:.1f}% |")
     out.append("")
-    out.append(f"Sum of the means: {total:.0f} us per encode+decode step under ncu (serialised, cold cache).")
+    out.append(f"Sum: {total:.0f} us of kernel time per encode+decode step under ncu (serialised, cold cache).")
     out.append("")
-    out.append("Other launches in the same run: " + "; ".join(
-        f"{k} x{len(agg[k]) - len(full[k]) if not k.startswith('transform') else len(agg[k])}"
-        f" (mean {sum(x for x in agg[k] if k.startswith('transform') or x <= 0.5 * max(agg[k])) / max(1, (len(agg[k]) - len(full[k])) if not k.startswith('transform') else len(agg[k])):.1f} us)"
-        for k in agg if k.startswith("transform") or len(agg[k]) > len(full[k]))
-        + " -- the f32 seam measurement, the 32-frame ranges of the e2e leg, and the second (nearly empty) check/fix round of each decode.")
+    out.append("Other launches in the same run: " + "; ".join(f"{k} x{len(v)} (mean {sum(v) / len(v):.1f} us)" for k, v in other.items())
+               + " -- the f32 seam measurement and the 16-frame ranges of the e2e leg.")
     out.append("")
 
     b = json.loads(open(p("bench.json")).read().strip().splitlines()[-1])
