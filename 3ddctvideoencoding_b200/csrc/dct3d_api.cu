@@ -412,6 +412,18 @@ void dct3d_destroy(dct3d_ctx *ctx)
 
 const char *dct3d_last_error(const dct3d_ctx *ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
 
+void *dct3d_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+
+void dct3d_host_free(void *p)
+{
+    if (p) cudaFreeHost(p);
+}
+
 int dct3d_set_option(dct3d_ctx *ctx, const char *key, long value)
 {
     if (!ctx || !key) return fail(ctx, DCT3D_E_INVALID, "null argument");

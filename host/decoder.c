@@ -23,8 +23,10 @@ int decode(char *inputFileName, char *outputFileName, int width, int height, int
     if (!inputFile || !outputFile) { printf("Error opening files\n"); return 1; }
     unsigned char *zlibCompressedData = (unsigned char *)malloc(bufferSize);
     size_t cap = 2 * bufferSize + 64, have = 0;                  /* inflated, not yet consumed */
-    unsigned char *expGolombCodedData = (unsigned char *)malloc(cap);
-    unsigned char *frames = (unsigned char *)malloc(bufferSize);
+    /* page-locked buffers on both sides of the GPU call */
+    unsigned char *expGolombCodedData = (unsigned char *)dct3d_host_alloc(cap);
+    unsigned char *frames = (unsigned char *)dct3d_host_alloc(bufferSize);
+    if (!zlibCompressedData || !expGolombCodedData || !frames) { printf("Error allocating host buffers\n"); return 1; }
 
     z_stream zlibStream;
     memset(&zlibStream, 0, sizeof zlibStream);
@@ -51,7 +53,14 @@ int decode(char *inputFileName, char *outputFileName, int width, int height, int
                 zlibStream.next_in = zlibCompressedData;
                 zlibStream.avail_in = (uInt)got;
             }
-            if (cap - have < bufferSize) { cap *= 2; expGolombCodedData = (unsigned char *)realloc(expGolombCodedData, cap); }
+            if (cap - have < bufferSize) {
+                unsigned char *bigger = (unsigned char *)dct3d_host_alloc(2 * cap);
+                if (!bigger) { printf("Error allocating host buffers\n"); return 1; }
+                memcpy(bigger, expGolombCodedData, have);
+                dct3d_host_free(expGolombCodedData);
+                expGolombCodedData = bigger;
+                cap *= 2;
+            }
             zlibStream.next_out = expGolombCodedData + have;
             zlibStream.avail_out = (uInt)(cap - have);
             int zr = inflate(&zlibStream, Z_NO_FLUSH);
@@ -76,7 +85,7 @@ int decode(char *inputFileName, char *outputFileName, int width, int height, int
     fclose(outputFile);
     fclose(inputFile);
     dct3d_destroy(ctx);
-    free(zlibCompressedData); free(expGolombCodedData); free(frames);
+    free(zlibCompressedData); dct3d_host_free(expGolombCodedData); dct3d_host_free(frames);
     printf("Decoding process completed");
     return 0;
 }

@@ -7,6 +7,9 @@
  * sequence (:209-254), applyQuantization (:47-58) and applyExpGolombCoding (:60-71) with
  * expGolomb_freeBuffer (ExpGolomb.c:112-122) are ONE call, dct3d_stream_encode, which takes the raw
  * u8 frames and returns the complete stream bytes; OpenCLUtils.c is replaced by dct3d_create.
+ * The container stage (deflate, :73-86,266-274) keeps its format -- one zlib stream, level 9 -- but runs
+ * on all host cores (pdeflate.c) while the next slab is read and coded; environment variables
+ * DCT3D_ZLIB_LEVEL / DCT3D_ZLIB_THREADS override level and thread count.
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -15,6 +18,7 @@
 
 #include "../include/dct3d.h"
 #include "codec.h"
+#include "pdeflate.h"
 
 int encode(char *inputFileName, char *outputFileName, int width, int height, int framesToEncode, int platformIndex)
 {
@@ -22,13 +26,15 @@ int encode(char *inputFileName, char *outputFileName, int width, int height, int
     FILE *inputFile = fopen(inputFileName, "rb");
     FILE *outputFile = fopen(outputFileName, "wb");
     if (!inputFile || !outputFile) { printf("Error opening files\n"); return 1; }
-    unsigned char *frames = (unsigned char *)malloc(bufferSize);
-    unsigned char *expGolombBuffer = (unsigned char *)malloc(4 * bufferSize + 64);   /* worst case, bounds-checked by the library */
-    unsigned char *zlibCompressedBuffer = (unsigned char *)malloc(compressBound((uLong)(4 * bufferSize + 64)));
+    /* page-locked staging buffers: the slab goes to the GPU at PCIe speed */
+    unsigned char *frames = (unsigned char *)dct3d_host_alloc(bufferSize);
+    const size_t egCap = 4 * bufferSize + 64;                                          /* worst case, bounds-checked by the library */
+    unsigned char *expGolombBuffer = (unsigned char *)dct3d_host_alloc(egCap);
+    if (!frames || !expGolombBuffer) { printf("Error allocating host buffers\n"); return 1; }
 
-    z_stream zlibStream;
-    memset(&zlibStream, 0, sizeof zlibStream);
-    deflateInit(&zlibStream, Z_BEST_COMPRESSION);
+    const char *lv = getenv("DCT3D_ZLIB_LEVEL"), *th = getenv("DCT3D_ZLIB_THREADS");
+    pdeflate *zlibStream = pdeflate_open(outputFile, lv ? atoi(lv) : Z_BEST_COMPRESSION, th ? atoi(th) : 0, 0);
+    if (!zlibStream) { printf("Error starting deflate\n"); return 1; }
 
     printf("Getting device id\n");
     dct3d_ctx *ctx = NULL;
@@ -50,29 +56,22 @@ int encode(char *inputFileName, char *outputFileName, int width, int height, int
 
         /* DCT + quantization + zig-zag + Exp-Golomb on the GPU; complete bytes come back */
         size_t expGolombCodedDataSize = 0;
-        if (dct3d_stream_encode(ctx, frames, DCT_BLOCK_DEPTH, last, expGolombBuffer, 4 * bufferSize + 64,
+        if (dct3d_stream_encode(ctx, frames, DCT_BLOCK_DEPTH, last, expGolombBuffer, egCap,
                                 &expGolombCodedDataSize) != DCT3D_OK) {
             printf("Error encoding slab: %s\n", dct3d_last_error(ctx));
             return 1;
         }
 
-        /* Deflating the Exp-Golomb coded data. */
-        zlibStream.next_in = expGolombBuffer;
-        zlibStream.avail_in = (uInt)expGolombCodedDataSize;
-        do {
-            zlibStream.next_out = zlibCompressedBuffer;
-            zlibStream.avail_out = (uInt)compressBound((uLong)(4 * bufferSize + 64));
-            deflate(&zlibStream, last ? Z_FINISH : Z_NO_FLUSH);
-            fwrite(zlibCompressedBuffer, 1, compressBound((uLong)(4 * bufferSize + 64)) - zlibStream.avail_out, outputFile);
-        } while (zlibStream.avail_in > 0);
+        /* Deflating the Exp-Golomb coded data (queued; the workers run while the next slab is read). */
+        if (pdeflate_write(zlibStream, expGolombBuffer, expGolombCodedDataSize)) { printf("Error deflating output\n"); return 1; }
         printf("Frames processed: %d\n", framesRead);
     }
-    deflateEnd(&zlibStream);
+    if (pdeflate_close(zlibStream, NULL, NULL)) { printf("Error deflating output\n"); return 1; }
     fflush(outputFile);
     fclose(outputFile);
     fclose(inputFile);
     dct3d_destroy(ctx);
-    free(frames); free(expGolombBuffer); free(zlibCompressedBuffer);
+    dct3d_host_free(frames); dct3d_host_free(expGolombBuffer);
     printf("Encoding process completed");
     return 0;
 }

@@ -58,6 +58,12 @@ void dct3d_destroy(dct3d_ctx *ctx);
 /* Last error text of the context (or of the last failed dct3d_create if ctx is NULL). */
 const char *dct3d_last_error(const dct3d_ctx *ctx);
 
+/* Page-locked host memory (cudaHostAlloc): buffers passed to the host-buffer entry points move at PCIe
+ * speed (about 10x pageable memory) when they come from here.  Replaces the reference's malloc'd
+ * inputData/outputData (C/encoder.c:131-134).  dct3d_host_alloc returns NULL on failure. */
+void *dct3d_host_alloc(size_t bytes);
+void dct3d_host_free(void *p);
+
 /* Options: "tma" (1 = TMA tile loads [default when width % 16 == 0], 0 = plain vector loads);
  * "reuse_zeroed" (default 0): the device-resident encoders zero-fill the stream buffer before packing;
  * with 1, a buffer the context packed into on its previous call (same pointer, same capacity, end bit
