@@ -108,6 +108,31 @@ def cpu_baseline_sample(W, H, frames, threads):
     return frames / (t2 - t0), t1 - t0, t2 - t1, bits
 
 
+def ref_c_host_sample(W, H):
+    """Times the reference's own C host code (encoder.c / decoder.c / ExpGolomb.c / CubeUtils.c compiled unmodified
+    into oracle/_ref/codec_ref, its four OpenCL kernels executed by the CPU shim oracle/ref_shim.c) on one slab."""
+    import subprocess
+    import tempfile
+    exe = os.path.join(ROOT, "oracle", "_ref", "codec_ref")
+    if not os.path.exists(exe):
+        return None
+    synth = importlib.import_module(PKG + ".synth")
+    with tempfile.TemporaryDirectory() as td:
+        raw, dct, out = (os.path.join(td, n) for n in ("a.raw", "a.dct", "a.out"))
+        synth.natural(W, H, 8, 1).tofile(raw)
+        t0 = time.perf_counter()
+        r1 = subprocess.run([exe, "encode", raw, dct, str(W), str(H), "8", "1"], capture_output=True, cwd=os.path.dirname(exe))
+        t1 = time.perf_counter()
+        r2 = subprocess.run([exe, "decode", dct, out, str(W), str(H), "8", "1"], capture_output=True, cwd=os.path.dirname(exe))
+        t2 = time.perf_counter()
+        if r1.returncode or r2.returncode or not os.path.exists(out):
+            return None
+    return {"value": 8 / (t2 - t0), "unit": UNIT, "kind": "reference", "cores": os.cpu_count() or 1,
+            "encode_s_per_slab": t1 - t0, "decode_s_per_slab": t2 - t1,
+            "sample": "8 frames (1 slab), the reference C codec CLI end to end (zlib level 9 included), its O(512^2)-per-cube "
+                      "OpenCL kernels run by a pthreads CPU shim"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -134,6 +159,9 @@ def run_reference(args):
                          "sample": f"{sample} frames (1 slab) of the workload per step, encode+decode"},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "encode_s_per_slab": float(np.mean([v[1] for v in vals])), "decode_s_per_slab": float(np.mean([v[2] for v in vals])),
+        # the other flavour of the reference, for the record: slower than the Java algorithm, so the port above is the
+        # conservative denominator
+        "ref_c_host": ref_c_host_sample(W, H),
     }
     print(json.dumps(line))
     return 0
