@@ -17,6 +17,10 @@ SYMBOLS = {
     "dct3d_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_int, C.c_int]),
     "dct3d_destroy": (None, [_vp]),
     "dct3d_last_error": (C.c_char_p, [_vp]),
+    "dct3d_rgb_split": (C.c_int, [_vp, _vp, C.c_size_t, _vp, _vp, _vp]),
+    "dct3d_rgb_mix": (C.c_int, [_vp, _vp, _vp, _vp, C.c_size_t, _vp]),
+    "dct3d_rgb_split_dev": (C.c_int, [_vp, _vp, C.c_size_t, _vp, _vp, _vp, _vp]),
+    "dct3d_rgb_mix_dev": (C.c_int, [_vp, _vp, _vp, _vp, C.c_size_t, _vp, _vp]),
     "dct3d_host_alloc": (C.c_void_p, [C.c_size_t]),
     "dct3d_host_free": (None, [_vp]),
     "dct3d_set_option": (C.c_int, [_vp, C.c_char_p, C.c_long]),

@@ -234,6 +234,30 @@ class Codec:
         self._check(self.L.dct3d_reconstruct_i16_dev(self.h, _ptr(d_q), nframes, _ptr(d_frames), stream))
 
 
+    # -- colour planes (J/RGBUtils.java:39-131) ------------------------------------------------------------
+    def rgb_split(self, rgb):
+        """Raw RGB24 bytes -> (r, g, b) planes: byte i belongs to plane i % 3 (RGBUtils.split)."""
+        a = np.ascontiguousarray(rgb, np.uint8).reshape(-1)
+        planes = [np.empty((a.size + 2 - p) // 3, np.uint8) for p in range(3)]
+        self._check(self.L.dct3d_rgb_split(self.h, _ptr(a), a.size, _ptr(planes[0]), _ptr(planes[1]), _ptr(planes[2])))
+        return planes
+
+    def rgb_mix(self, r, g, b):
+        """Three equal planes -> raw RGB24 bytes (RGBUtils.mix)."""
+        r, g, b = (np.ascontiguousarray(x, np.uint8).reshape(-1) for x in (r, g, b))
+        if not (r.size == g.size == b.size):
+            raise ValueError("planes differ in size")
+        out = np.empty(3 * r.size, np.uint8)
+        self._check(self.L.dct3d_rgb_mix(self.h, _ptr(r), _ptr(g), _ptr(b), r.size, _ptr(out)))
+        return out
+
+    def rgb_split_dev(self, d_rgb, nbytes: int, d_r, d_g, d_b, stream=0):
+        self._check(self.L.dct3d_rgb_split_dev(self.h, _ptr(d_rgb), nbytes, _ptr(d_r), _ptr(d_g), _ptr(d_b), stream))
+
+    def rgb_mix_dev(self, d_r, d_g, d_b, npixels: int, d_rgb, stream=0):
+        self._check(self.L.dct3d_rgb_mix_dev(self.h, _ptr(d_r), _ptr(d_g), _ptr(d_b), npixels, _ptr(d_rgb), stream))
+
+
 def list_devices() -> str:
     L = _lib.load()
     buf = C.create_string_buffer(4096)
@@ -312,6 +336,27 @@ class Decoder:
             frames = c.decode_u8(stream, depth)
         frames.tofile(args[1])
         print("Complete!")
+        return 0
+
+
+class RGBUtils:
+    """`java RGBUtils split|mix ...` (J/RGBUtils.java:13-37): colour video is coded as three gray streams."""
+
+    @staticmethod
+    def main(args, device: int = 0) -> int:
+        if len(args) < 3 or args[0] not in ("split", "mix"):
+            print("Usage:\n\njava RGBUtils split <input file> <output files names pattern>\n"
+                  "java RGBUtils mix <input files names pattern> <output file>")
+            return 1
+        names = (".red", ".green", ".blue")
+        with Codec(8, 8, 8, device) as c:           # the plane kernels do not depend on the frame geometry
+            if args[0] == "split":
+                for p, ext in zip(c.rgb_split(np.fromfile(args[1], np.uint8)), names):
+                    p.tofile(args[2] + ext)
+            else:
+                planes = [np.fromfile(args[1] + ext, np.uint8) for ext in names]
+                n = planes[0].size                  # mix() takes the red file's length as the pixel count (:113-127)
+                c.rgb_mix(*(np.resize(p, n) if p.size != n else p for p in planes)).tofile(args[2])
         return 0
 
 

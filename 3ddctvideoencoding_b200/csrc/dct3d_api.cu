@@ -745,6 +745,70 @@ int dct3d_decode_u8_dev(dct3d_ctx *ctx, const void *d_stream, size_t nbytes, uin
     return C == 8 ? launch_reconstruct_zz<8>(ctx, L, d_frames, st) : launch_reconstruct_zz<4>(ctx, L, d_frames, st);
 }
 
+static int rgb_dev(dct3d_ctx *ctx, bool split, void *d_rgb, void *d_r, void *d_g, void *d_b, size_t nbytes, void *cuda_stream)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (nbytes == 0) return DCT3D_OK;
+    if (!d_rgb || !d_r || !d_g || !d_b) return fail(ctx, DCT3D_E_INVALID, "null pointer");
+    cudaStream_t st = pick(ctx, cuda_stream);
+    const int vec_ok = !(((uintptr_t)d_rgb | (uintptr_t)d_r | (uintptr_t)d_g | (uintptr_t)d_b) & 15);
+    const unsigned long long work = vec_ok ? nbytes / 48 + 47 : nbytes;
+    const unsigned grid = (unsigned)std::min<unsigned long long>((work + 255) / 256, (unsigned long long)ctx->num_sms * 32);
+    if (split) rgb_planes_kernel<true><<<grid, 256, 0, st>>>((uint8_t *)d_rgb, (uint8_t *)d_r, (uint8_t *)d_g, (uint8_t *)d_b, nbytes, vec_ok);
+    else rgb_planes_kernel<false><<<grid, 256, 0, st>>>((uint8_t *)d_rgb, (uint8_t *)d_r, (uint8_t *)d_g, (uint8_t *)d_b, nbytes, vec_ok);
+    ctx->launches++;
+    CU_CHECK(ctx, cudaGetLastError());
+    return DCT3D_OK;
+}
+
+int dct3d_rgb_split_dev(dct3d_ctx *ctx, const void *d_rgb, size_t nbytes, void *d_r, void *d_g, void *d_b, void *cuda_stream)
+{
+    return rgb_dev(ctx, true, const_cast<void *>(d_rgb), d_r, d_g, d_b, nbytes, cuda_stream);
+}
+
+int dct3d_rgb_mix_dev(dct3d_ctx *ctx, const void *d_r, const void *d_g, const void *d_b, size_t npixels, void *d_rgb, void *cuda_stream)
+{
+    return rgb_dev(ctx, false, d_rgb, const_cast<void *>(d_r), const_cast<void *>(d_g), const_cast<void *>(d_b), npixels * 3, cuda_stream);
+}
+
+// host buffers: plane p of an n-byte RGB file holds (n + 2 - p) / 3 bytes
+int dct3d_rgb_split(dct3d_ctx *ctx, const uint8_t *rgb, size_t nbytes, uint8_t *r, uint8_t *g, uint8_t *b)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (nbytes == 0) return DCT3D_OK;
+    if (!rgb || !r || !g || !b) return fail(ctx, DCT3D_E_INVALID, "null pointer");
+    const size_t np = (nbytes + 2) / 3, pstride = (np + 255) & ~(size_t)255;
+    CU_CHECK(ctx, ctx->fa.reserve(nbytes));
+    CU_CHECK(ctx, ctx->fb.reserve(3 * pstride));
+    uint8_t *d = (uint8_t *)ctx->fb.p;
+    H2D(ctx, ctx->fa.p, rgb, nbytes);
+    if ((rc = rgb_dev(ctx, true, ctx->fa.p, d, d + pstride, d + 2 * pstride, nbytes, nullptr))) return rc;
+    uint8_t *out[3] = {r, g, b};
+    for (int p = 0; p < 3; p++) D2H(ctx, out[p], d + p * pstride, (nbytes + 2 - p) / 3);
+    SYNC(ctx);
+    return DCT3D_OK;
+}
+
+int dct3d_rgb_mix(dct3d_ctx *ctx, const uint8_t *r, const uint8_t *g, const uint8_t *b, size_t npixels, uint8_t *rgb)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (npixels == 0) return DCT3D_OK;
+    if (!rgb || !r || !g || !b) return fail(ctx, DCT3D_E_INVALID, "null pointer");
+    const size_t pstride = (npixels + 255) & ~(size_t)255;
+    CU_CHECK(ctx, ctx->fa.reserve(3 * npixels));
+    CU_CHECK(ctx, ctx->fb.reserve(3 * pstride));
+    uint8_t *d = (uint8_t *)ctx->fb.p;
+    const uint8_t *in[3] = {r, g, b};
+    for (int p = 0; p < 3; p++) H2D(ctx, d + p * pstride, in[p], npixels);
+    if ((rc = rgb_dev(ctx, false, ctx->fa.p, d, d + pstride, d + 2 * pstride, 3 * npixels, nullptr))) return rc;
+    D2H(ctx, rgb, ctx->fa.p, 3 * npixels);
+    SYNC(ctx);
+    return DCT3D_OK;
+}
+
 int dct3d_forward_f32_dev(dct3d_ctx *c, const void *i, void *o, int n, void *s) { return transform_dev<float, true, false>(c, i, o, n, s); }
 int dct3d_inverse_f32_dev(dct3d_ctx *c, const void *i, void *o, int n, void *s) { return transform_dev<float, true, true>(c, i, o, n, s); }
 int dct3d_forward_f64_dev(dct3d_ctx *c, const void *i, void *o, int nframes, void *s)

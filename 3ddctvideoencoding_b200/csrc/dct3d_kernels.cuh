@@ -1390,4 +1390,65 @@ transform_kernel(const Layout L, const T *__restrict__ in, T *__restrict__ out)
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Colour planes: the reference codes colour video as three gray streams and
+// converts with RGBUtils (RGBUtils.java:39-92 split, :94-131 mix): byte i of the raw RGB24 file
+// belongs to plane i % 3.  One thread moves 16 pixels: 3 x 16 bytes one way, 48 contiguous bytes the
+// other, shuffled with PRMT; pure HBM traffic (2 B moved per byte).  Tails and unaligned buffers take
+// the byte path.
+// ------------------------------------------------------------------------------------------
+template <bool SPLIT>
+__global__ void __launch_bounds__(256)
+rgb_planes_kernel(uint8_t *__restrict__ rgb, uint8_t *__restrict__ p0, uint8_t *__restrict__ p1, uint8_t *__restrict__ p2,
+                  unsigned long long nbytes, int vec_ok)
+{
+    const unsigned long long ngroups = vec_ok ? nbytes / 48 : 0;     // 16 pixels each
+    const unsigned long long tid = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    const unsigned long long nthr = gridDim.x * (unsigned long long)blockDim.x;
+    for (unsigned long long g = tid; g < ngroups; g += nthr) {
+        uint32_t w[12], o[3][4];
+        if (SPLIT) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(rgb + g * 48);
+#pragma unroll
+            for (int i = 0; i < 3; i++) { const uint4 v = __ldg(src + i); w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w; }
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    // output word q of plane c = bytes 12q + c + {0, 3, 6, 9} of the group
+                    const int b0 = 12 * q + c;
+                    const uint32_t lo = __byte_perm(w[b0 / 4], w[(b0 + 3) / 4], (b0 % 4) | ((((b0 + 3) % 4) + 4) << 4));
+                    const uint32_t hi = __byte_perm(w[(b0 + 6) / 4], w[(b0 + 9) / 4], ((b0 + 6) % 4) | ((((b0 + 9) % 4) + 4) << 4));
+                    o[c][q] = __byte_perm(lo, hi, 0x5410);
+                }
+            uint8_t *dst[3] = {p0, p1, p2};
+#pragma unroll
+            for (int c = 0; c < 3; c++) *reinterpret_cast<uint4 *>(dst[c] + g * 16) = make_uint4(o[c][0], o[c][1], o[c][2], o[c][3]);
+        } else {
+            const uint8_t *src[3] = {p0, p1, p2};
+#pragma unroll
+            for (int c = 0; c < 3; c++) { const uint4 v = __ldg(reinterpret_cast<const uint4 *>(src[c] + g * 16)); o[c][0] = v.x; o[c][1] = v.y; o[c][2] = v.z; o[c][3] = v.w; }
+#pragma unroll
+            for (int j = 0; j < 12; j++) {
+                // output word j = bytes 4j .. 4j+3 of the group; byte b is pixel b / 3 of plane b % 3
+                uint32_t v = 0;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int b = 4 * j + k, px = b / 3, c = b % 3;
+                    v |= ((o[c][px / 4] >> (8 * (px % 4))) & 0xffu) << (8 * k);
+                }
+                w[j] = v;
+            }
+            uint4 *dst = reinterpret_cast<uint4 *>(rgb + g * 48);
+#pragma unroll
+            for (int i = 0; i < 3; i++) dst[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+        }
+    }
+    // bytes the vector path did not cover
+    uint8_t *pl[3] = {p0, p1, p2};
+    for (unsigned long long i = ngroups * 48 + tid; i < nbytes; i += nthr) {
+        if (SPLIT) pl[i % 3][i / 3] = rgb[i]; else rgb[i] = pl[i % 3][i / 3];
+    }
+}
+
 }  // namespace dct3d

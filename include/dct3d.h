@@ -164,6 +164,16 @@ int dct3d_eg_encode_i16_dev(dct3d_ctx *ctx, const void *d_qcubes, size_t ncubes,
 int dct3d_eg_decode_i16_dev(dct3d_ctx *ctx, const void *d_stream, size_t nbytes, uint64_t start_bit,
                             size_t ncubes, void *d_qcubes, uint64_t *end_bit, void *cuda_stream);
 
+/* ---- colour planes (the reference codes colour video as three gray streams) --------------------
+ * RGBUtils split / mix (J/RGBUtils.java:39-92 and :94-131): byte i of a raw RGB24 buffer belongs to
+ * plane i % 3.  split: nbytes of RGB -> planes of (nbytes+2)/3, (nbytes+1)/3 and nbytes/3 bytes;
+ * mix: three planes of npixels bytes -> 3*npixels bytes of RGB.  The _dev variants use the 16-byte
+ * vector path when all four pointers are 16-byte aligned. */
+int dct3d_rgb_split(dct3d_ctx *ctx, const uint8_t *rgb, size_t nbytes, uint8_t *r, uint8_t *g, uint8_t *b);
+int dct3d_rgb_mix(dct3d_ctx *ctx, const uint8_t *r, const uint8_t *g, const uint8_t *b, size_t npixels, uint8_t *rgb);
+int dct3d_rgb_split_dev(dct3d_ctx *ctx, const void *d_rgb, size_t nbytes, void *d_r, void *d_g, void *d_b, void *cuda_stream);
+int dct3d_rgb_mix_dev(dct3d_ctx *ctx, const void *d_r, const void *d_g, const void *d_b, size_t npixels, void *d_rgb, void *cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -418,3 +418,59 @@ def test_decode_worst_case_resynchronisation(codec_mod, oracle):
         assert end == ref_end and out.tobytes() == ref.tobytes()
         back, dend = c.eg_decode_i16(out, 4)
         assert dend == ref_end and (back == q).all()
+
+
+# ---- colour planes ---------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 47, 48, 49, 50, 3 * 4097, 1_000_001])
+def test_rgb_split_mix_host(codec_mod, n):
+    """RGBUtils.split sends byte i to plane i % 3 (J/RGBUtils.java:67-80); mix interleaves back (:115-119)."""
+    rng = np.random.default_rng(n)
+    rgb = rng.integers(0, 256, n, dtype=np.uint8)
+    with make(codec_mod, 16, 16, 8) as c:
+        r, g, b = c.rgb_split(rgb)
+        assert (r == rgb[0::3]).all() and (g == rgb[1::3]).all() and (b == rgb[2::3]).all()
+        m = n // 3
+        back = c.rgb_mix(r[:m], g[:m], b[:m])
+        assert (back == rgb[: 3 * m]).all()
+
+
+@pytest.mark.gpu
+def test_rgb_dev_aligned_and_unaligned(codec_mod):
+    import torch
+    dev = torch.device("cuda", 0)
+    n = 1920 * 1080 * 3 * 4
+    rgb = torch.randint(0, 256, (n + 16,), dtype=torch.uint8, device=dev)
+    with make(codec_mod, 1920, 1080, 8) as c:
+        for off in (0, 1):                          # 16-byte aligned -> vector path, otherwise the byte path
+            src = rgb[off:off + n]
+            planes = [torch.empty(n // 3 + 16, dtype=torch.uint8, device=dev)[off:off + n // 3] for _ in range(3)]
+            torch.cuda.synchronize()
+            c.rgb_split_dev(src, n, *planes)
+            torch.cuda.synchronize()
+            for p in range(3):
+                assert torch.equal(planes[p], src[p::3])
+            out = torch.zeros(n + 16, dtype=torch.uint8, device=dev)[off:off + n]
+            torch.cuda.synchronize()
+            c.rgb_mix_dev(*planes, n // 3, out)
+            torch.cuda.synchronize()
+            assert torch.equal(out, src)
+
+
+@pytest.mark.gpu
+def test_rgbutils_cli_and_colour_clip(codec_mod, synth, tmp_path):
+    """A colour clip is three gray clips: split, code each plane, decode, mix (README of the reference)."""
+    W, H, F = 64, 48, 8
+    planes = [synth.natural(W, H, F, s) for s in (1, 2, 3)]
+    rgb = np.stack(planes, axis=-1).reshape(-1)
+    (tmp_path / "in.rgb").write_bytes(rgb.tobytes())
+    assert codec_mod.RGBUtils.main(["split", str(tmp_path / "in.rgb"), str(tmp_path / "p")]) == 0
+    for ext, p in zip((".red", ".green", ".blue"), planes):
+        assert (np.fromfile(str(tmp_path / "p") + ext, np.uint8) == p.reshape(-1)).all()
+    with make(codec_mod, W, H, 8) as c:
+        for ext, p in zip((".red", ".green", ".blue"), planes):
+            stream, nbits = c.encode_u8(p)
+            c.decode_u8(stream, F).tofile(str(tmp_path / "q") + ext)
+    assert codec_mod.RGBUtils.main(["mix", str(tmp_path / "q"), str(tmp_path / "out.rgb")]) == 0
+    out = np.fromfile(str(tmp_path / "out.rgb"), np.uint8)
+    assert out.size == rgb.size and np.abs(out.astype(int) - rgb.astype(int)).mean() < 6.0
