@@ -60,7 +60,7 @@ struct dct3d_ctx {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::string err;
     DevBuf frames, bits, q, status, ctrl, seg, seglist, fa, fb, zz, cmask, coo, coocnt;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // around encode_kernel / reconstruct_zz_kernel
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // around encode_kernel / reconstruct_coo_kernel
     bool ev_valid[2] = {false, false};
     Ctrl *h_ctrl = nullptr;          // pinned
     unsigned long long *h_u64 = nullptr;  // pinned scratch (4 entries)
@@ -258,7 +258,7 @@ int zero_stream(dct3d_ctx *ctx, void *d_stream, size_t cap, uint64_t start_bit, 
 
 
 template <int C>
-static int launch_reconstruct_zz(dct3d_ctx *ctx, const Layout &L, void *d_frames, cudaStream_t st)
+static int launch_reconstruct_coo(dct3d_ctx *ctx, const Layout &L, void *d_frames, cudaStream_t st)
 {
     auto kern = reconstruct_coo_kernel<C>;
     const int smem = CooSmem<C>::TOTAL;
@@ -444,7 +444,7 @@ long dct3d_get_stat(const dct3d_ctx *ctx, const char *key)
     if (!strcmp(key, "launches")) return ctx->launches;
     if (!strcmp(key, "tma")) return ctx->use_tma;
     if (!strcmp(key, "num_sms")) return ctx->num_sms;
-    // device time of the last encode_kernel / reconstruct_zz_kernel launch, nanoseconds (CUDA events on
+    // device time of the last encode_kernel / reconstruct_coo_kernel launch, nanoseconds (CUDA events on
     // the launching stream; waits for that launch to finish)
     for (int k = 0; k < 2; k++) {
         if (!strcmp(key, k == 0 ? "ns_encode_kernel" : "ns_reconstruct_kernel")) {
@@ -742,7 +742,7 @@ int dct3d_decode_u8_dev(dct3d_ctx *ctx, const void *d_stream, size_t nbytes, uin
     uint64_t end = 0;
     if ((rc = parse_common(ctx, d_stream, nbytes, start_bit, (size_t)L.ncubes, &end, st))) return rc;
     if (end_bit) *end_bit = end;
-    return C == 8 ? launch_reconstruct_zz<8>(ctx, L, d_frames, st) : launch_reconstruct_zz<4>(ctx, L, d_frames, st);
+    return C == 8 ? launch_reconstruct_coo<8>(ctx, L, d_frames, st) : launch_reconstruct_coo<4>(ctx, L, d_frames, st);
 }
 
 static int rgb_dev(dct3d_ctx *ctx, bool split, void *d_rgb, void *d_r, void *d_g, void *d_b, size_t nbytes, void *cuda_stream)

@@ -693,9 +693,9 @@ struct WordBase {
     }
 };
 
-// The CTA's staged window.  A thread reads at most its own 32 words, a 33-bit entry overhang, 15
-// more codes (seg_parse_kernel) and the reader's two-word look-ahead: always inside the window's
-// 32-word margin.  The index is clamped so that even a corrupt stream cannot read outside it.
+// The CTA's staged window.  A thread reads at most the 3 words of its lead-in walk, its own 32 words,
+// a 33-bit code running past them and the reader's two-word look-ahead: always inside the window (4 lead
+// words + 28 words of margin).  The index is clamped so that even a corrupt stream cannot read outside it.
 struct StagedSource : WordBase {
     const uint32_t *s;
     __device__ __forceinline__ uint32_t word(uint32_t j) const
@@ -785,11 +785,9 @@ struct DecParams {
     unsigned int *changed;              // fix-up flag
     unsigned int *err;                  // bit1 = malformed, bit2 = truncated
     unsigned long long *end_bit;        // out: first bit after the last code
-    int16_t *zzg;                       // zig-zag chunk scratch [cube][CS] (zz_scatter_kernel input)
-    uint32_t *cmask;                    // [cube] chunk masks (zz_scatter_kernel input)
     uint32_t *coo;                      // non-zero coefficients of the whole stream, in stream order: natural index << 16 | value
     unsigned long long *coo_start;      // [ncubes+1] first entry of every cube (CSR row pointers)
-    int16_t *qcubes;                    // natural-order cubes (zz_scatter_kernel)
+    int16_t *qcubes;                    // natural-order cubes out (coo_scatter_kernel)
     uint8_t *frames;
 };
 
