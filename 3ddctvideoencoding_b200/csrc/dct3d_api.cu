@@ -39,7 +39,7 @@ struct Ctrl {               // small device control block, zeroed before every l
     unsigned int ticket;
     unsigned int err;
     unsigned int changed;
-    unsigned int nwork;
+    unsigned int pad_;
     unsigned long long end_bit;
 };
 
@@ -631,12 +631,11 @@ static int parse_common(dct3d_ctx *ctx, const void *d_stream, size_t nbytes, uin
     P.seg_count = (unsigned int *)ctx->seg.p;
     P.seg_over = P.seg_count + n;
     P.seg_used = P.seg_over + n + 1;
-    P.seg_work = P.seg_used + n;
     P.seg_list = (uint4 *)ctx->seglist.p;
     P.seg_first = (unsigned long long *)((uint8_t *)ctx->seg.p + off_first);
     P.seg_nzfirst = P.seg_first + n + 1;
     Ctrl *dc = (Ctrl *)ctx->ctrl.p;
-    P.changed = &dc->changed; P.err = &dc->err; P.end_bit = &dc->end_bit; P.nwork = &dc->nwork;
+    P.changed = &dc->changed; P.err = &dc->err; P.end_bit = &dc->end_bit;
     P.coo = (uint32_t *)ctx->coo.p;
     P.coo_start = (unsigned long long *)ctx->coocnt.p;
     CU_CHECK(ctx, cudaMemsetAsync(ctx->ctrl.p, 0, sizeof(Ctrl), st));
@@ -644,18 +643,18 @@ static int parse_common(dct3d_ctx *ctx, const void *d_stream, size_t nbytes, uin
     const unsigned sb = kSegThreads, sg = (unsigned)((P.nseg + sb - 1) / sb);
     seg_scan_kernel<<<sg, sb, 0, st>>>(P);
     ctx->launches++;
+    unsigned int round = 0;
     auto fix_round = [&]() -> int {
-        CU_CHECK(ctx, cudaMemsetAsync(&dc->changed, 0, 8, st));   // changed + nwork
-        seg_check_kernel<<<(unsigned)((P.nseg + 255) / 256), 256, 0, st>>>(P);
-        seg_fix_kernel<<<(unsigned)std::min<unsigned long long>((P.nseg + 127) / 128, (unsigned long long)ctx->num_sms * 16), 128, 0, st>>>(P);
-        ctx->launches += 2;
+        seg_fix_kernel<<<(unsigned)((P.nseg + 127) / 128), 128, 0, st>>>(P, ++round);
+        ctx->launches++;
         return DCT3D_OK;
     };
+    bool redo = false;
     auto prefix_and_parse = [&]() -> int {
         const long long stiles = (long long)((P.nseg + kScanThreads * kScanItems - 1) / (kScanThreads * kScanItems));
         CU_CHECK(ctx, ctx->status.reserve((size_t)stiles * 16));
         CU_CHECK(ctx, cudaMemsetAsync(ctx->status.p, 0, (size_t)stiles * 16, st));
-        CU_CHECK(ctx, cudaMemsetAsync(&dc->ticket, 0, 4, st));
+        if (redo) CU_CHECK(ctx, cudaMemsetAsync(&dc->ticket, 0, 4, st));     // the first time the whole block is still zero
         const long long grid = std::min<long long>(stiles, (long long)ctx->num_sms * 8);
         seg_prefix_kernel<<<(unsigned)grid, kScanThreads, 0, st>>>(P, (unsigned long long *)ctx->status.p,
                                                                    (unsigned long long *)ctx->status.p + stiles, &dc->ticket);
@@ -665,18 +664,18 @@ static int parse_common(dct3d_ctx *ctx, const void *d_stream, size_t nbytes, uin
         CU_CHECK(ctx, cudaGetLastError());
         return DCT3D_OK;
     };
-    // Fix-up rounds re-scan only the segments whose entry overhang differs from the one assumed.  Two
-    // rounds are enqueued without looking (the first repairs ~1 segment in 7, the second normally finds
-    // nothing), the rest of the pipeline follows, and the host checks ONCE at the end whether the second
-    // round still changed something; only then (not seen on any tested content) it iterates to
-    // convergence and redoes prefix + parse.
+    // Fix-up rounds re-scan only the segments whose entry point was guessed wrong.  Two rounds are enqueued
+    // without looking (with the lead-in walk the first one already finds next to nothing), the rest of
+    // the pipeline follows, and the host checks ONCE at the end whether the second round still moved an
+    // overhang; only then (the constructed worst case) it iterates to convergence and redoes prefix + emit.
     if ((rc = fix_round()) || (rc = fix_round()) || (rc = prefix_and_parse())) return rc;
     CU_CHECK(ctx, cudaMemcpyAsync(ctx->h_u64, P.seg_first + n, 8, cudaMemcpyDeviceToHost, st));
     if ((rc = fetch_ctrl(ctx, st))) return rc;
-    if (ctx->h_ctrl->changed) {
-        for (unsigned long long round = 0; round <= P.nseg && ctx->h_ctrl->changed; round++) {
+    if (ctx->h_ctrl->changed == round) {
+        for (unsigned long long it = 0; it <= P.nseg && ctx->h_ctrl->changed == round; it++) {
             if ((rc = fix_round()) || (rc = fetch_ctrl(ctx, st))) return rc;
         }
+        redo = true;
         CU_CHECK(ctx, cudaMemsetAsync(&dc->err, 0, 4, st));
         if ((rc = prefix_and_parse())) return rc;
         CU_CHECK(ctx, cudaMemcpyAsync(ctx->h_u64, P.seg_first + n, 8, cudaMemcpyDeviceToHost, st));

@@ -778,11 +778,9 @@ struct DecParams {
     unsigned int *seg_over;             // [nseg+1] overhang INTO segment k (seg_over[0] = 0)
     unsigned int *seg_used;             // [nseg] entry overhang used for the current count
     uint4 *seg_list;                    // [nseg][kSegListVec] non-zero codes of each segment (sparsely touched)
-    unsigned int *seg_work;             // [nseg] worklist of segments to re-scan
-    unsigned int *nwork;
     unsigned long long *seg_first;      // [nseg+1] exclusive prefix of the code counts
     unsigned long long *seg_nzfirst;    // [nseg+1] exclusive prefix of the non-zero code counts
-    unsigned int *changed;              // fix-up flag
+    unsigned int *changed;              // number of the last fix-up round that moved an overhang
     unsigned int *err;                  // bit1 = malformed, bit2 = truncated
     unsigned long long *end_bit;        // out: first bit after the last code
     uint32_t *coo;                      // non-zero coefficients of the whole stream, in stream order: natural index << 16 | value
@@ -810,7 +808,7 @@ seg_scan_kernel(const DecParams P)
     // Guess the entry point: walk the last kLeadBits bits of the previous segment from an arbitrary
     // phase.  Exp-Golomb streams resynchronise within a few codes (every run of one-bits is a run of
     // complete codes), so the walk usually arrives at the segment's first code; the guess is verified
-    // against the predecessor's overhang by seg_check_kernel like any other.
+    // against the predecessor's overhang by seg_fix_kernel like any other.
     uint32_t entry = 0;
     if (k > 0 && seg0 < lim) {
         uint32_t nd, nx;
@@ -829,41 +827,35 @@ seg_scan_kernel(const DecParams P)
     P.seg_over[k + 1] = next > lim ? next - lim : 0u;
 }
 
-// Fix-up rounds: list the segments whose true entry point (the predecessor's overhang) differs from
-// the one they were scanned with, then re-scan only those (one in seven without the lead-in walk, far
-// fewer with it; almost none on the second round), until nothing changes.
-__global__ void seg_check_kernel(const DecParams P)
+// Fix-up rounds: every thread compares the entry point its segment was scanned with against the
+// predecessor's overhang and re-scans the segment on a mismatch (one in seven without the lead-in walk,
+// nearly none with it), until a round changes nothing.  `round` is stored in *changed by a thread that
+// moves an overhang, so the flag needs no reset between rounds.
+__global__ void __launch_bounds__(128)
+seg_fix_kernel(const DecParams P, unsigned int round)
 {
     const unsigned long long k = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
     if (k >= P.nseg) return;
-    if (P.seg_over[k] != P.seg_used[k]) P.seg_work[atomicAdd(P.nwork, 1u)] = (unsigned int)k;
-}
-
-__global__ void seg_fix_kernel(const DecParams P)
-{
-    const unsigned int nwork = *P.nwork;
-    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < nwork; i += gridDim.x * blockDim.x) {
-        const unsigned long long k = P.seg_work[i];
-        LocalSource src;                                       // the segment is fetched with independent loads, then walked
-        src.w0 = (P.start_bit >> 5) + k * kSegWords;
-        src.fill(P.words, P.nwords);
-        const unsigned int entry = P.seg_over[k];
-        const uint32_t seg0 = src.rel(P.start_bit + k * (unsigned long long)P.seg_bits);
-        const uint32_t eos = src.rel(P.nbits_total);
-        uint32_t lim = seg0 + P.seg_bits;
-        if (lim > eos) lim = eos;
-        uint32_t n = 0, next = 0, nz = 0;
-        unsigned int bad = 0;
-        SegListSink sink;
-        sink.dst = P.seg_list + seg_list_base(k);
-        sink.e0 = sink.e1 = sink.e2 = sink.e3 = 0u;
-        if (seg0 + entry >= lim) { n = 0; next = seg0 + entry; }
-        else if (!eg_scan_segment(src, seg0 + entry, lim, eos, n, next, &nz, sink)) { bad = 0x80000000u; n = 0; nz = 0; next = lim; }
-        P.seg_count[k] = n | (nz << 16) | bad;
-        P.seg_used[k] = entry;
-        const unsigned int over = next > lim ? next - lim : 0u;
-        if (P.seg_over[k + 1] != over) { P.seg_over[k + 1] = over; *P.changed = 1u; }
-    }
+    const unsigned int entry = P.seg_over[k];
+    if (entry == P.seg_used[k]) return;
+    LocalSource src;                                           // the segment is fetched with independent loads, then walked
+    src.w0 = (P.start_bit >> 5) + k * kSegWords;
+    src.fill(P.words, P.nwords);
+    const uint32_t seg0 = src.rel(P.start_bit + k * (unsigned long long)P.seg_bits);
+    const uint32_t eos = src.rel(P.nbits_total);
+    uint32_t lim = seg0 + P.seg_bits;
+    if (lim > eos) lim = eos;
+    uint32_t n = 0, next = 0, nz = 0;
+    unsigned int bad = 0;
+    SegListSink sink;
+    sink.dst = P.seg_list + seg_list_base(k);
+    sink.e0 = sink.e1 = sink.e2 = sink.e3 = 0u;
+    if (seg0 + entry >= lim) { n = 0; next = seg0 + entry; }
+    else if (!eg_scan_segment(src, seg0 + entry, lim, eos, n, next, &nz, sink)) { bad = 0x80000000u; n = 0; nz = 0; next = lim; }
+    P.seg_count[k] = n | (nz << 16) | bad;
+    P.seg_used[k] = entry;
+    const unsigned int over = next > lim ? next - lim : 0u;
+    if (P.seg_over[k + 1] != over) { P.seg_over[k + 1] = over; *P.changed = round; }
 }
 
 // Exclusive prefix sums over all segments of (a) the code counts and (b) the non-zero code counts:
