@@ -58,3 +58,28 @@ def test_levels_and_ratio_close_to_single_stream(driver):
         assert zlib.decompress(z) == data
         ref = zlib.compress(data, level)
         assert len(z) < 1.03 * len(ref) + 64      # the cuts cost little thanks to the carried dictionary
+
+
+def test_reference_cli_reads_our_container(driver, tmp_path):
+    """The reference's own decoder (unmodified C/decoder.c + inflate, built into oracle/_ref/codec_ref) must read a file
+    whose container was written by pdeflate: Exp-Golomb stream from the oracle, our container, the reference's decode."""
+    import importlib
+    import sys
+    ref = os.path.join(ROOT, "oracle", "_ref", "codec_ref")
+    if not os.path.exists(ref):
+        pytest.skip("oracle/_ref/codec_ref not built (needs /root/reference at build time)")
+    sys.path.insert(0, ROOT)
+    O = importlib.import_module("oracle.oracle")
+    O.build()
+    synth = importlib.import_module("3ddctvideoencoding_b200.synth")
+    W, H, F = 64, 48, 24
+    clip = synth.natural(W, H, F, 7)
+    stream, nbits = O.encode_u8(clip, 8, 1)             # C rounding flavour, as codec_ref itself would produce
+    z = run(driver, stream.tobytes(), 9, 4, 1024, 777)  # many small blocks: every cut is exercised
+    (tmp_path / "a.dct").write_bytes(z)
+    p = subprocess.run([ref, "decode", str(tmp_path / "a.dct"), str(tmp_path / "a.out"), str(W), str(H), str(F), "1"],
+                       capture_output=True, cwd=os.path.dirname(ref), timeout=300)
+    assert p.returncode == 0, p.stdout[-500:]
+    got = np.fromfile(str(tmp_path / "a.out"), np.uint8).reshape(F, H, W)
+    want = O.decode_u8(stream, W, H, F, 8)
+    assert np.abs(got.astype(int) - want.astype(int)).max() <= 1       # float kernels of the reference vs the fp64 oracle
