@@ -239,6 +239,26 @@ __device__ __forceinline__ void inv_yx_n(T (&a)[C][C])
 #pragma unroll
     for (int y = 0; y < C; y++) Dct1D<C, T>::template inv_n<1>(&a[y][0]);
 }
+// The same with the column transforms of the y pass (and, in inv_t_n_masked, of the t pass) skipped for
+// the k2 columns that are zero in every cube of the warp: bit x of colmask = column x holds a non-zero.
+// The inverse transform of an all-zero column is all zero, so the result is bit-identical; the branch is
+// warp-uniform.
+template <int C, typename T>
+__device__ __forceinline__ void inv_yx_n_masked(T (&a)[C][C], uint32_t colmask)
+{
+#pragma unroll
+    for (int x = 0; x < C; x++)
+        if ((colmask >> x) & 1u) Dct1D<C, T>::template inv_n<C>(&a[0][x]);
+#pragma unroll
+    for (int y = 0; y < C; y++) Dct1D<C, T>::template inv_n<1>(&a[y][0]);
+}
+template <int C, typename T>
+__device__ __forceinline__ void inv_t_n_masked(T (&b)[C][C], uint32_t colmask)
+{
+#pragma unroll
+    for (int x = 0; x < C; x++)
+        if ((colmask >> x) & 1u) Dct1D<C, T>::template inv_n<C>(&b[0][x]);
+}
 template <int C, typename T>
 __device__ __forceinline__ void fwd_t_g(T (&b)[C][C])
 {
@@ -1059,13 +1079,13 @@ __device__ __forceinline__ void build_dequant_table(float *tab, int tid)
 // truncate (Decoder.java:112, decoder.c:29), store the thread's frame plane.
 template <int C, bool ALL_SCALED = false, bool T_DONE = false>
 __device__ __forceinline__ void idct_store(float (&b)[C][C], uint8_t *xbuf, int cl, int r, bool valid, const Layout &L,
-                                           long long cube, uint8_t *__restrict__ frames)
+                                           long long cube, uint8_t *__restrict__ frames, uint32_t colmask = 0xffffffffu)
 {
     float a[C][C];
     // ALL_SCALED: b already carries S[k0] S[k1] S[k2]; otherwise S[k1] only and the t stage folds in S[k2]
     if (!T_DONE) { if (ALL_SCALED) inv_t_n<C, float>(b); else inv_t_g<C, float>(b); }
     Xch<C, float>::transpose(xbuf, cl, r, b, a);   // the exchange is its own inverse
-    inv_yx_n<C, float>(a);
+    if (T_DONE) inv_yx_n_masked<C, float>(a, colmask); else inv_yx_n<C, float>(a);
     if (!valid) return;
     const int per_slab = L.by * L.bx;
     const int slab = (int)(cube / per_slab);
@@ -1162,6 +1182,7 @@ reconstruct_coo_kernel(const Layout L, const uint32_t *__restrict__ coo, const u
         fetch_entries();                        // group g + stride
         fetch_rows(g + 2 * stride);
         // scatter this cube's entries (lane r of the cube takes entries r, r+C, r+2C, ...)
+        uint32_t colbits = 0;                   // k2 columns this lane scattered into (physical = swizzled position)
         {
             // the table loads of the prefetched entries are issued together (index 0 for an absent entry)
             uint32_t ix[PRE];
@@ -1172,7 +1193,7 @@ reconstruct_coo_kernel(const Layout L, const uint32_t *__restrict__ coo, const u
             for (int k = 0; k < PRE; k++) tv[k] *= (float)(int)(int16_t)(e[k] & 0xffffu);
 #pragma unroll
             for (int k = 0; k < PRE; k++)
-                if ((uint32_t)(r + k * C) < cnt) nat[ix[k]] = tv[k];
+                if ((uint32_t)(r + k * C) < cnt) { nat[ix[k]] = tv[k]; colbits |= 1u << (coo_swizzle<C>(ix[k]) & (C - 1)); }
         }
         // dense cubes: the rest of the list, four independent loads at a time
         for (uint32_t i = r + PRE * C; i < cnt; i += 4 * C) {
@@ -1183,6 +1204,9 @@ reconstruct_coo_kernel(const Layout L, const uint32_t *__restrict__ coo, const u
             for (int k = 0; k < 4; k++)
                 if (i + k * C < cnt) put(x[k]);
         }
+        if (cnt > (uint32_t)(PRE * C)) colbits = (1u << C) - 1u;   // a dense cube: no pruning, and no bookkeeping in its loop
+        // columns that are zero in all cubes of this pass skip their t and y transforms
+        const uint32_t colmask = __reduce_or_sync(0xffffffffu, colbits);
         __syncwarp();
         float b[C][C];
         // first halves of all rows, then second halves: the t pass of columns 0..3 starts while the
@@ -1196,7 +1220,7 @@ reconstruct_coo_kernel(const Layout L, const uint32_t *__restrict__ coo, const u
                 b[k0][k2] = v.x; b[k0][k2 + 1] = v.y; b[k0][k2 + 2] = v.z; b[k0][k2 + 3] = v.w;
             }
         }
-        inv_t_n<C, float>(b);
+        inv_t_n_masked<C, float>(b, colmask);
         // wipe what was scattered, after the t pass: by now every lane's row loads have long landed
         __syncwarp();
 #pragma unroll
@@ -1210,7 +1234,7 @@ reconstruct_coo_kernel(const Layout L, const uint32_t *__restrict__ coo, const u
             for (int k = 0; k < 4; k++)
                 if (i + k * C < cnt) nat[(x[k] >> 16) & (G::CS - 1)] = 0.0f;
         }
-        idct_store<C, true, true>(b, xbuf, cl, r, cube < L.ncubes, L, cube, frames);
+        idct_store<C, true, true>(b, xbuf, cl, r, cube < L.ncubes, L, cube, frames, colmask);
     }
 }
 
