@@ -49,6 +49,8 @@ struct dct3d_ctx {
     int device = 0, W = 0, H = 0, C = 8;
     int num_sms = 0;
     int use_tma = 1;
+    int precision = 32;              // option: 64 = the fused entry points compute in fp64 (Java parity)
+    int rounding = 0;                // option, fp64 mode: 0 = Math.round (floor(v+0.5)), 1 = C round()
     int debug = 0;
     int reuse_zeroed = 0;            // option: see dct3d_set_option
     const void *clean_ptr = nullptr; // stream buffer known to be zero beyond clean_dirty bytes
@@ -434,6 +436,12 @@ int dct3d_set_option(dct3d_ctx *ctx, const char *key, long value)
         return DCT3D_OK;
     }
     if (!strcmp(key, "debug")) { ctx->debug = (int)value; return DCT3D_OK; }
+    if (!strcmp(key, "precision")) {
+        if (value != 32 && value != 64) return fail(ctx, DCT3D_E_INVALID, "precision must be 32 or 64");
+        ctx->precision = (int)value;
+        return DCT3D_OK;
+    }
+    if (!strcmp(key, "rounding")) { ctx->rounding = value ? 1 : 0; return DCT3D_OK; }
     if (!strcmp(key, "reuse_zeroed")) { ctx->reuse_zeroed = value ? 1 : 0; ctx->clean_ptr = nullptr; return DCT3D_OK; }
     return fail(ctx, DCT3D_E_INVALID, "unknown option '%s'", key);
 }
@@ -459,6 +467,51 @@ long dct3d_get_stat(const dct3d_ctx *ctx, const char *key)
 }
 
 // ---- device-resident entry points -----------------------------------------------------------
+
+static unsigned ew_grid(dct3d_ctx *ctx, unsigned long long n)
+{
+    return (unsigned)std::min<unsigned long long>((n + 255) / 256, (unsigned long long)ctx->num_sms * 32);
+}
+
+// fp64 mode, forward half: u8 frames -> natural-order int16 cubes through the f64 transform seam
+static int quantize_f64(dct3d_ctx *ctx, const void *d_frames, int nslabs, void *d_q, cudaStream_t st)
+{
+    const int C = ctx->C;
+    const Layout L = make_layout(ctx->W, ctx->H, C, nslabs);
+    const unsigned long long n = (unsigned long long)L.ncubes * C * C * C;
+    if ((ctx->W * sizeof(double)) % 16) return fail(ctx, DCT3D_E_INVALID, "fp64 mode needs an even width");
+    CU_CHECK(ctx, ctx->fa.reserve(n * sizeof(double)));
+    CU_CHECK(ctx, ctx->fb.reserve(n * sizeof(double)));
+    u8_to_f64_kernel<<<ew_grid(ctx, n), 256, 0, st>>>((const uint8_t *)d_frames, (double *)ctx->fa.p, n);
+    ctx->launches++;
+    int rc = dct3d_forward_f64_dev(ctx, ctx->fa.p, ctx->fb.p, nslabs * C, st);
+    if (rc) return rc;
+    if (C == 8) quant_f64_kernel<8, true><<<ew_grid(ctx, n), 256, 0, st>>>(L, (double *)ctx->fb.p, (int16_t *)d_q, ctx->rounding);
+    else quant_f64_kernel<4, true><<<ew_grid(ctx, n), 256, 0, st>>>(L, (double *)ctx->fb.p, (int16_t *)d_q, ctx->rounding);
+    ctx->launches++;
+    CU_CHECK(ctx, cudaGetLastError());
+    return DCT3D_OK;
+}
+
+// fp64 mode, inverse half: natural-order int16 cubes -> u8 frames
+static int reconstruct_f64(dct3d_ctx *ctx, const void *d_q, int nslabs, void *d_frames, cudaStream_t st)
+{
+    const int C = ctx->C;
+    const Layout L = make_layout(ctx->W, ctx->H, C, nslabs);
+    const unsigned long long n = (unsigned long long)L.ncubes * C * C * C;
+    if ((ctx->W * sizeof(double)) % 16) return fail(ctx, DCT3D_E_INVALID, "fp64 mode needs an even width");
+    CU_CHECK(ctx, ctx->fa.reserve(n * sizeof(double)));
+    CU_CHECK(ctx, ctx->fb.reserve(n * sizeof(double)));
+    if (C == 8) quant_f64_kernel<8, false><<<ew_grid(ctx, n), 256, 0, st>>>(L, (double *)ctx->fa.p, (int16_t *)const_cast<void *>(d_q), 0);
+    else quant_f64_kernel<4, false><<<ew_grid(ctx, n), 256, 0, st>>>(L, (double *)ctx->fa.p, (int16_t *)const_cast<void *>(d_q), 0);
+    ctx->launches++;
+    int rc = dct3d_inverse_f64_dev(ctx, ctx->fa.p, ctx->fb.p, nslabs * C, st);
+    if (rc) return rc;
+    f64_to_u8_kernel<<<ew_grid(ctx, n), 256, 0, st>>>((const double *)ctx->fb.p, (uint8_t *)d_frames, n);
+    ctx->launches++;
+    CU_CHECK(ctx, cudaGetLastError());
+    return DCT3D_OK;
+}
 
 // Kernel 2 (bit packing) over ctx->zz / ctx->cmask.  P.L.ncubes must be set.
 static int run_pack_noreset(dct3d_ctx *ctx, EncParams &P, void *d_stream, size_t cap, uint64_t start_bit, uint64_t *end_bit, cudaStream_t st)
@@ -516,6 +569,15 @@ static int encode_common(dct3d_ctx *ctx, const void *d_frames, int nframes, void
     }
     if (nslabs == 0) { if (end_bit) *end_bit = start_bit; return DCT3D_OK; }
     if (!d_frames) return fail(ctx, DCT3D_E_INVALID, "null frame pointer");
+    if (ctx->precision == 64) {
+        // fp64 mode: u8 -> double, the f64 transform seam, the reference's quantiser in double, then the
+        // same zig-zag gather and bit packer as the stage entry point
+        if (emit_q) return quantize_f64(ctx, d_frames, nslabs, d_qcubes, st);
+        const size_t ncubes = (size_t)nslabs * (ctx->H / C) * (ctx->W / C);
+        CU_CHECK(ctx, ctx->q.reserve(ncubes * C * C * C * sizeof(int16_t)));
+        if ((rc = quantize_f64(ctx, d_frames, nslabs, ctx->q.p, st))) return rc;
+        return dct3d_eg_encode_i16_dev(ctx, ctx->q.p, ncubes, start_bit, d_stream, cap, end_bit, st);
+    }
     EncParams P;
     memset(&P, 0, sizeof P);
     P.L = make_layout(ctx->W, ctx->H, C, nslabs);
@@ -724,6 +786,7 @@ int dct3d_reconstruct_i16_dev(dct3d_ctx *ctx, const void *d_qcubes, int nframes,
     if (!d_qcubes || !d_frames) return fail(ctx, DCT3D_E_INVALID, "null pointer");
     const Layout L = make_layout(ctx->W, ctx->H, ctx->C, nslabs);
     cudaStream_t st = pick(ctx, cuda_stream);
+    if (ctx->precision == 64) return reconstruct_f64(ctx, d_qcubes, nslabs, d_frames, st);
     return ctx->C == 8 ? launch_reconstruct<8>(ctx, L, d_qcubes, d_frames, st) : launch_reconstruct<4>(ctx, L, d_qcubes, d_frames, st);
 }
 
@@ -739,6 +802,12 @@ int dct3d_decode_u8_dev(dct3d_ctx *ctx, const void *d_stream, size_t nbytes, uin
     const Layout L = make_layout(ctx->W, ctx->H, C, nslabs);
     cudaStream_t st = pick(ctx, cuda_stream);
     uint64_t end = 0;
+    if (ctx->precision == 64) {
+        CU_CHECK(ctx, ctx->q.reserve((size_t)L.ncubes * C * C * C * sizeof(int16_t)));
+        if ((rc = dct3d_eg_decode_i16_dev(ctx, d_stream, nbytes, start_bit, (size_t)L.ncubes, ctx->q.p, &end, st))) return rc;
+        if (end_bit) *end_bit = end;
+        return reconstruct_f64(ctx, ctx->q.p, nslabs, d_frames, st);
+    }
     if ((rc = parse_common(ctx, d_stream, nbytes, start_bit, (size_t)L.ncubes, &end, st))) return rc;
     if (end_bit) *end_bit = end;
     return C == 8 ? launch_reconstruct_coo<8>(ctx, L, d_frames, st) : launch_reconstruct_coo<4>(ctx, L, d_frames, st);

@@ -1405,6 +1405,49 @@ transform_kernel(const Layout L, const T *__restrict__ in, T *__restrict__ out)
 }
 
 // ------------------------------------------------------------------------------------------
+// fp64 mode (option "precision" = 64): the reference's Java flavour computes in double
+// (DCT.java:41-59, Encoder.java:82, Decoder.java:89,112); these element-wise kernels sit around the
+// f64 transform seam so that the quantised cubes match it without rounding-tie flips.
+// ------------------------------------------------------------------------------------------
+__global__ void u8_to_f64_kernel(const uint8_t *__restrict__ in, double *__restrict__ out, unsigned long long n)
+{
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n; i += gridDim.x * (unsigned long long)blockDim.x)
+        out[i] = (double)in[i];
+}
+
+// clamp happened in the inverse transform; (byte)(double) truncates (Decoder.java:112)
+__global__ void f64_to_u8_kernel(const double *__restrict__ in, uint8_t *__restrict__ out, unsigned long long n)
+{
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n; i += gridDim.x * (unsigned long long)blockDim.x)
+        out[i] = (uint8_t)(int)in[i];
+}
+
+// planar f64 coefficients [F][H][W] <-> natural-order int16 cubes [cube][k0][k1][k2].
+// QUANT: q = Math.round(c / d) = floor(c / d + 0.5) (Encoder.java:82; rounding 0) or C round(), ties away
+// from zero (encoder.c:53; rounding 1), d = max(1, 5(k0+k1+k2)).  Otherwise c = q * d (Decoder.java:89).
+template <int C, bool QUANT>
+__global__ void quant_f64_kernel(const Layout L, double *__restrict__ planar, int16_t *__restrict__ q, int rounding)
+{
+    constexpr int CS = C * C * C;
+    const unsigned long long n = (unsigned long long)L.ncubes * CS;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n; i += gridDim.x * (unsigned long long)blockDim.x) {
+        const unsigned long long cube = i / CS;
+        const int e = (int)(i % CS), k2 = e % C, k1 = (e / C) % C, k0 = e / (C * C);
+        const int per_slab = L.by * L.bx;
+        const int slab = (int)(cube / per_slab), rem = (int)(cube % per_slab), byi = rem / L.bx, bxi = rem % L.bx;
+        const size_t at = ((size_t)(slab * C + k0) * L.H + (byi * C + k1)) * L.W + (bxi * C + k2);
+        const double d = (double)quant_divisor(k0 + k1 + k2);
+        if (QUANT) {
+            const double v = planar[at] / d;
+            const double r = rounding ? (v < 0 ? -floor(-v + 0.5) : floor(v + 0.5)) : floor(v + 0.5);
+            q[i] = (int16_t)max(-32768.0, min(32767.0, r));
+        } else {
+            planar[at] = (double)q[i] * d;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Colour planes: the reference codes colour video as three gray streams and
 // converts with RGBUtils (RGBUtils.java:39-92 split, :94-131 mix): byte i of the raw RGB24 file
 // belongs to plane i % 3.  One thread moves 16 pixels: 3 x 16 bytes one way, 48 contiguous bytes the

@@ -70,6 +70,11 @@ void dct3d_host_free(void *p);
  * read back) is only wiped up to where that call wrote -- the caller promises not to have written
  * beyond it in between.
  * "debug" (1 = print per-stage diagnostics to stderr).
+ * "precision" (32 [default] or 64): with 64 the fused and stage entry points (encode_u8, decode_u8, quantize_u8,
+ * reconstruct_i16 and the streaming calls) compute in double like the Java reference (J/dct/DCT.java:41-59,
+ * J/Encoder.java:82, J/Decoder.java:89,112): quantised cubes then equal the fp64 oracle without rounding-tie
+ * flips, at a fraction of the fp32 path's speed.  "rounding" (fp64 mode only): 0 = Math.round = floor(v + 0.5)
+ * (J/Encoder.java:82), 1 = C round(), ties away from zero (C/encoder.c:53).
  * Statistics (dct3d_get_stat): "launches" = kernels launched by the context so far; "tma" = 1 when the
  * TMA path is active; "num_sms"; "ns_encode_kernel" / "ns_reconstruct_kernel" = duration in ns of the
  * last transform kernel of each direction, from CUDA events recorded around it on the launching stream. */

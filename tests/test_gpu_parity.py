@@ -474,3 +474,46 @@ def test_rgbutils_cli_and_colour_clip(codec_mod, synth, tmp_path):
     assert codec_mod.RGBUtils.main(["mix", str(tmp_path / "q"), str(tmp_path / "out.rgb")]) == 0
     out = np.fromfile(str(tmp_path / "out.rgb"), np.uint8)
     assert out.size == rgb.size and np.abs(out.astype(int) - rgb.astype(int)).mean() < 6.0
+
+
+# ---- fp64 mode (option "precision" = 64): the Java flavour's arithmetic, no tie flips -----------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,seed", [("natural", 1), ("noise", 2)])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_fp64_mode_matches_oracle_without_flips(codec_mod, oracle, synth, kind, seed, mode):
+    """In fp64 the quantiser sees the same values as the fp64 oracle to ~1e-12, so for the 8^3 transform (no exact
+    ties) the quantised cubes and therefore the whole Exp-Golomb stream are identical, in both rounding flavours
+    (J/Encoder.java:82 Math.round, C/encoder.c:53 round)."""
+    W, H, F = 128, 64, 16
+    clip = gen(synth, kind, W, H, F, seed)
+    ref = oracle.quantized_cubes(clip, 8, mode=mode)
+    ref_stream, ref_bits = oracle.encode_u8(clip, 8, mode)
+    with make(codec_mod, W, H, 8) as c:
+        c.set_option("precision", 64)
+        c.set_option("rounding", mode)
+        q = c.quantize_u8(clip).astype(np.int32)
+        assert int((q != ref).sum()) == 0
+        stream, nbits = c.encode_u8(clip)
+        assert nbits == ref_bits and stream.tobytes() == ref_stream[: nbits // 8 + 1].tobytes()
+        dec = c.decode_u8(stream, F)
+        want = oracle.decode_u8(ref_stream, W, H, F, 8)
+        # truncation after fp64 arithmetic in a different summation order: a pixel may differ by one only where
+        # the exact value is an integer to within 1e-9
+        assert np.abs(dec.astype(int) - want.astype(int)).max() <= 1
+        assert (dec != want).mean() < 1e-3
+        assert (c.reconstruct_i16(q.astype(np.int16), F) == dec).all()
+        c.set_option("precision", 32)
+        q32 = c.quantize_u8(clip).astype(np.int32)
+        assert np.abs(q32 - q).max() <= 1           # and the fp32 path differs from it only by tie flips
+
+
+@pytest.mark.gpu
+def test_fp64_mode_cube4_flips_only_at_exact_ties(codec_mod, oracle, synth):
+    W, H, F = 64, 32, 8
+    clip = gen(synth, "natural", W, H, F, 4)
+    ref, coef = oracle.quantized_cubes(clip, 4, mode=0, want_coef=True)
+    with make(codec_mod, W, H, 4) as c:
+        c.set_option("precision", 64)
+        q = c.quantize_u8(clip).astype(np.int32)
+    exact, near = classify_flips(q, ref, coef, oracle, 4)
+    assert near == 0                                # the 4^3 basis is rational: only exact ties can differ (DESIGN.md 6)
