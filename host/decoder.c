@@ -7,6 +7,7 @@
  * sequence + writeCubes (:229-295) are ONE call, dct3d_stream_decode, which reports
  * DCT3D_E_NEED_MORE while the buffered input does not yet hold the whole slab.
  */
+#include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -14,6 +15,37 @@
 
 #include "../include/dct3d.h"
 #include "codec.h"
+
+/* Output side of the slab pipeline: the frames of slab i are written by this thread while the main thread
+ * inflates and decodes slab i+1 into the other page-locked buffer (replaces the blocking fwrite of
+ * writeCubes' caller, decoder.c:294-295). */
+typedef struct {
+    FILE *out;
+    unsigned char *buf[2];
+    size_t bytes;
+    int filled[2], stop, failed;       /* filled[b]: buffer b holds a slab that is not on disk yet */
+    pthread_mutex_t mu;
+    pthread_cond_t cv;
+} slab_writer;
+
+static void *slab_writer_main(void *arg)
+{
+    slab_writer *w = (slab_writer *)arg;
+    int b = 0;
+    for (;;) {
+        pthread_mutex_lock(&w->mu);
+        while (!w->filled[b] && !w->stop) pthread_cond_wait(&w->cv, &w->mu);
+        if (!w->filled[b]) { pthread_mutex_unlock(&w->mu); return NULL; }
+        pthread_mutex_unlock(&w->mu);
+        const int bad = fwrite(w->buf[b], 1, w->bytes, w->out) != w->bytes;
+        pthread_mutex_lock(&w->mu);
+        if (bad) w->failed = 1;
+        w->filled[b] = 0;
+        pthread_cond_broadcast(&w->cv);
+        pthread_mutex_unlock(&w->mu);
+        b ^= 1;
+    }
+}
 
 int decode(char *inputFileName, char *outputFileName, int width, int height, int framesToDecode, int platformIndex)
 {
@@ -25,8 +57,18 @@ int decode(char *inputFileName, char *outputFileName, int width, int height, int
     size_t cap = 2 * bufferSize + 64, have = 0;                  /* inflated, not yet consumed */
     /* page-locked buffers on both sides of the GPU call */
     unsigned char *expGolombCodedData = (unsigned char *)dct3d_host_alloc(cap);
-    unsigned char *frames = (unsigned char *)dct3d_host_alloc(bufferSize);
-    if (!zlibCompressedData || !expGolombCodedData || !frames) { printf("Error allocating host buffers\n"); return 1; }
+    slab_writer writer;
+    memset(&writer, 0, sizeof writer);
+    writer.out = outputFile;
+    writer.bytes = bufferSize;
+    writer.buf[0] = (unsigned char *)dct3d_host_alloc(bufferSize);
+    writer.buf[1] = (unsigned char *)dct3d_host_alloc(bufferSize);
+    if (!zlibCompressedData || !expGolombCodedData || !writer.buf[0] || !writer.buf[1]) { printf("Error allocating host buffers\n"); return 1; }
+    pthread_mutex_init(&writer.mu, NULL);
+    pthread_cond_init(&writer.cv, NULL);
+    pthread_t writerThread;
+    pthread_create(&writerThread, NULL, slab_writer_main, &writer);
+    int cur = 0;                                                 /* buffer the next slab is decoded into */
 
     z_stream zlibStream;
     memset(&zlibStream, 0, sizeof zlibStream);
@@ -43,6 +85,11 @@ int decode(char *inputFileName, char *outputFileName, int width, int height, int
     int framesRead = 0, eof = 0, inflated_all = 0;
     uint64_t bitpos = 0;
     while (framesRead < framesToDecode) {
+        /* the buffer must be back from the writer before it is decoded into again */
+        pthread_mutex_lock(&writer.mu);
+        while (writer.filled[cur]) pthread_cond_wait(&writer.cv, &writer.mu);
+        pthread_mutex_unlock(&writer.mu);
+        unsigned char *frames = writer.buf[cur];
         int rc = have ? dct3d_stream_decode(ctx, expGolombCodedData, have, &bitpos, DCT_BLOCK_DEPTH, frames) : DCT3D_E_NEED_MORE;
         if (rc == DCT3D_E_NEED_MORE) {
             if (inflated_all) { printf("Input ended before all frames were decoded\n"); return 1; }
@@ -70,8 +117,12 @@ int decode(char *inputFileName, char *outputFileName, int width, int height, int
             continue;
         }
         if (rc != DCT3D_OK) { printf("Error decoding slab: %s\n", dct3d_last_error(ctx)); return 1; }
-        /* Writing the resulting pixels to the output file */
-        fwrite(frames, 1, bufferSize, outputFile);
+        /* Writing the resulting pixels to the output file (handed to the writer thread) */
+        pthread_mutex_lock(&writer.mu);
+        writer.filled[cur] = 1;
+        pthread_cond_broadcast(&writer.cv);
+        pthread_mutex_unlock(&writer.mu);
+        cur ^= 1;
         framesRead += DCT_BLOCK_DEPTH;
         /* drop the consumed bytes, keep the partial byte's bit position */
         const size_t consumed = (size_t)(bitpos / 8);
@@ -81,11 +132,17 @@ int decode(char *inputFileName, char *outputFileName, int width, int height, int
         printf("Frames processed: %d\n", framesRead);
     }
     inflateEnd(&zlibStream);
+    pthread_mutex_lock(&writer.mu);
+    writer.stop = 1;
+    pthread_cond_broadcast(&writer.cv);
+    pthread_mutex_unlock(&writer.mu);
+    pthread_join(writerThread, NULL);
+    if (writer.failed) { printf("Error writing output\n"); return 1; }
     fflush(outputFile);
     fclose(outputFile);
     fclose(inputFile);
     dct3d_destroy(ctx);
-    free(zlibCompressedData); dct3d_host_free(expGolombCodedData); dct3d_host_free(frames);
+    free(zlibCompressedData); dct3d_host_free(expGolombCodedData); dct3d_host_free(writer.buf[0]); dct3d_host_free(writer.buf[1]);
     printf("Decoding process completed");
     return 0;
 }
