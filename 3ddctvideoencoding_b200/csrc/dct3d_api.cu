@@ -61,7 +61,7 @@ struct dct3d_ctx {
     cudaStream_t aux = nullptr;      // side stream: the stream wipe of the fused encoder runs beside kernel 1
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::string err;
-    DevBuf frames, bits, q, status, ctrl, seg, seglist, fa, fb, zz, cmask, coo, coocnt;
+    DevBuf frames, bits, q, ctrl, seg, seglist, fa, fb, zz, cmask, coo, coocnt;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // around encode_kernel / reconstruct_coo_kernel
     bool ev_valid[2] = {false, false};
     Ctrl *h_ctrl = nullptr;          // pinned
@@ -222,12 +222,18 @@ int launch_encode(dct3d_ctx *ctx, const EncParams &P, const CUtensorMap &tm, cud
 }
 
 // zero the control block and the look-back status array
+// The control block and the look-back status words share one allocation (control block first), so that
+// one memset resets both.
+constexpr size_t kCtrlBytes = 64;
+static_assert(sizeof(Ctrl) <= kCtrlBytes, "control block grew");
+
+unsigned long long *status_words(dct3d_ctx *ctx) { return (unsigned long long *)((uint8_t *)ctx->ctrl.p + kCtrlBytes); }
+
 int reset_ctrl(dct3d_ctx *ctx, long long ntiles, cudaStream_t st)
 {
-    CU_CHECK(ctx, ctx->ctrl.reserve(sizeof(Ctrl)));
-    CU_CHECK(ctx, ctx->status.reserve((size_t)std::max<long long>(ntiles, 1) * 8));
-    CU_CHECK(ctx, cudaMemsetAsync(ctx->ctrl.p, 0, sizeof(Ctrl), st));
-    CU_CHECK(ctx, cudaMemsetAsync(ctx->status.p, 0, (size_t)std::max<long long>(ntiles, 1) * 8, st));
+    const size_t bytes = kCtrlBytes + (size_t)std::max<long long>(ntiles, 1) * 8;
+    CU_CHECK(ctx, ctx->ctrl.reserve(bytes));
+    CU_CHECK(ctx, cudaMemsetAsync(ctx->ctrl.p, 0, bytes, st));
     return DCT3D_OK;
 }
 
@@ -401,7 +407,7 @@ void dct3d_destroy(dct3d_ctx *ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    for (DevBuf *b : {&ctx->frames, &ctx->bits, &ctx->q, &ctx->status, &ctx->ctrl, &ctx->seg, &ctx->seglist, &ctx->fa, &ctx->fb, &ctx->zz, &ctx->cmask, &ctx->coo, &ctx->coocnt}) b->release();
+    for (DevBuf *b : {&ctx->frames, &ctx->bits, &ctx->q, &ctx->ctrl, &ctx->seg, &ctx->seglist, &ctx->fa, &ctx->fb, &ctx->zz, &ctx->cmask, &ctx->coo, &ctx->coocnt}) b->release();
     for (int i = 0; i < 4; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->h_ctrl) cudaFreeHost(ctx->h_ctrl);
     if (ctx->h_u64) cudaFreeHost(ctx->h_u64);
@@ -522,7 +528,7 @@ static int run_pack_noreset(dct3d_ctx *ctx, EncParams &P, void *d_stream, size_t
     P.out_words = (uint32_t *)d_stream;
     P.cap_bits = (unsigned long long)(cap / 4) * 32;
     P.start_bit = start_bit;
-    P.tile_status = (unsigned long long *)ctx->status.p;
+    P.tile_status = status_words(ctx);
     P.ticket = &dc->ticket; P.err = &dc->err; P.end_bit = &dc->end_bit;
     int &occ = ctx->occ_cache[4];
     if (occ == 0) {
@@ -585,7 +591,7 @@ static int encode_common(dct3d_ctx *ctx, const void *d_frames, int nframes, void
     P.qcubes = (int16_t *)d_qcubes;
     P.use_tma = ctx->use_tma && !((uintptr_t)d_frames & 15);
     P.debug = ctx->debug;
-    CU_CHECK(ctx, ctx->ctrl.reserve(sizeof(Ctrl)));
+    CU_CHECK(ctx, ctx->ctrl.reserve(kCtrlBytes + (size_t)((P.L.ncubes + kPackThreads - 1) / kPackThreads) * 8));   // final size: the pointer below stays valid
     P.err = &((Ctrl *)ctx->ctrl.p)->err;
     if (!emit_q) {
         CU_CHECK(ctx, ctx->zz.reserve((size_t)P.L.ncubes * C * C * C * sizeof(int16_t)));
@@ -687,7 +693,8 @@ static int parse_common(dct3d_ctx *ctx, const void *d_stream, size_t nbytes, uin
     const size_t off_first = ((4 * n + 1) * 4 + 7) & ~(size_t)7;
     CU_CHECK(ctx, ctx->seg.reserve(off_first + 2 * (n + 1) * 8));
     CU_CHECK(ctx, ctx->seglist.reserve(((n + 31) / 32) * 32 * kSegListVec * sizeof(uint4)));   // dense-addressed, only the heads are touched
-    CU_CHECK(ctx, ctx->ctrl.reserve(sizeof(Ctrl)));
+    const long long stiles = (long long)((P.nseg + kScanThreads * kScanItems - 1) / (kScanThreads * kScanItems));
+    CU_CHECK(ctx, ctx->ctrl.reserve(kCtrlBytes + (size_t)stiles * 16));
     CU_CHECK(ctx, ctx->coo.reserve(ncubes * CS * sizeof(uint32_t) + 2048));   // worst case: every coefficient non-zero, + the tail of the last segment's list
     CU_CHECK(ctx, ctx->coocnt.reserve((ncubes + 1) * 8));
     P.seg_count = (unsigned int *)ctx->seg.p;
@@ -700,8 +707,7 @@ static int parse_common(dct3d_ctx *ctx, const void *d_stream, size_t nbytes, uin
     P.changed = &dc->changed; P.err = &dc->err; P.end_bit = &dc->end_bit;
     P.coo = (uint32_t *)ctx->coo.p;
     P.coo_start = (unsigned long long *)ctx->coocnt.p;
-    CU_CHECK(ctx, cudaMemsetAsync(ctx->ctrl.p, 0, sizeof(Ctrl), st));
-    CU_CHECK(ctx, cudaMemsetAsync(P.seg_over, 0, 4, st));
+    CU_CHECK(ctx, cudaMemsetAsync(ctx->ctrl.p, 0, kCtrlBytes + (size_t)stiles * 16, st));   // control block + both status arrays of the prefix
     const unsigned sb = kSegThreads, sg = (unsigned)((P.nseg + sb - 1) / sb);
     seg_scan_kernel<<<sg, sb, 0, st>>>(P);
     ctx->launches++;
@@ -713,13 +719,12 @@ static int parse_common(dct3d_ctx *ctx, const void *d_stream, size_t nbytes, uin
     };
     bool redo = false;
     auto prefix_and_parse = [&]() -> int {
-        const long long stiles = (long long)((P.nseg + kScanThreads * kScanItems - 1) / (kScanThreads * kScanItems));
-        CU_CHECK(ctx, ctx->status.reserve((size_t)stiles * 16));
-        CU_CHECK(ctx, cudaMemsetAsync(ctx->status.p, 0, (size_t)stiles * 16, st));
-        if (redo) CU_CHECK(ctx, cudaMemsetAsync(&dc->ticket, 0, 4, st));     // the first time the whole block is still zero
+        if (redo) {                                                          // the first time everything is still zero
+            CU_CHECK(ctx, cudaMemsetAsync(status_words(ctx), 0, (size_t)stiles * 16, st));
+            CU_CHECK(ctx, cudaMemsetAsync(&dc->ticket, 0, 4, st));
+        }
         const long long grid = std::min<long long>(stiles, (long long)ctx->num_sms * 8);
-        seg_prefix_kernel<<<(unsigned)grid, kScanThreads, 0, st>>>(P, (unsigned long long *)ctx->status.p,
-                                                                   (unsigned long long *)ctx->status.p + stiles, &dc->ticket);
+        seg_prefix_kernel<<<(unsigned)grid, kScanThreads, 0, st>>>(P, status_words(ctx), status_words(ctx) + stiles, &dc->ticket);
         const unsigned pg = (unsigned)std::min<unsigned long long>((P.nseg + kEmitThreads - 1) / kEmitThreads, (unsigned long long)ctx->num_sms * 12);
         if (C == 8) seg_emit_kernel<8><<<pg, kEmitThreads, 0, st>>>(P); else seg_emit_kernel<4><<<pg, kEmitThreads, 0, st>>>(P);
         ctx->launches += 2;

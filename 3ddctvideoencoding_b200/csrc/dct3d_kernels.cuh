@@ -845,6 +845,7 @@ seg_scan_kernel(const DecParams P)
     P.seg_count[k] = n | (nz << 16) | bad;
     P.seg_used[k] = entry;
     P.seg_over[k + 1] = next > lim ? next - lim : 0u;
+    if (k == 0) P.seg_over[0] = 0u;              // the stream's first code starts at its first bit
 }
 
 // Fix-up rounds: every thread compares the entry point its segment was scanned with against the
