@@ -949,12 +949,11 @@ seg_prefix_kernel(const DecParams P, unsigned long long *status_codes, unsigned 
 // Segment lists -> rows of a CSR matrix of the cubes.  A warp owns 32 consecutive segments; every lane
 // knows its segment's first code index and the rank of its first non-zero code in the whole stream, so
 // entry i of segment s goes to coo[rank_s + i] as (list index space of the coefficient << 16 | value).
-// The copy is ENTRY-parallel: the warp walks the concatenation of its 32 lists 32 entries at a time
-// (a lane finds its entry's segment by a shuffle binary search over the prefix of the list lengths), so
-// sparse and dense content keep all lanes busy and the stores are contiguous.  Row pointers: each lane
-// bisects its own (sorted) list for every cube whose first code lies in its segment.  No bit is parsed a
-// second time; only the one thread that holds the clip's last code re-walks its segment to report where
-// the stream ends.
+// The copy is ENTRY-parallel: the warp takes the 32 lists one after the other (four in flight), a lane per
+// entry, with the segment's parameters broadcast by shuffle, so the stores are contiguous and sparse and
+// dense content keep the lanes busy alike.  Row pointers: each lane bisects its own (sorted) list for every
+// cube whose first code lies in its segment.  No bit is parsed a second time; only the one thread that
+// holds the clip's last code re-walks its segment to report where the stream ends.
 constexpr int kEmitThreads = 128;
 
 template <int C>
@@ -986,30 +985,29 @@ seg_emit_kernel(const DecParams P)
         const unsigned long long wbase = (kw >> 5) * (unsigned long long)(kSegListVec * 32 * 4);
         auto entry = [&](int s, uint32_t i) { return __ldg(lists + wbase + (unsigned)s * 4u + (i >> 2) * 128u + (i & 3u)); };
 
-        // ---- entries: warp-wide, 32 at a time -----------------------------------------------------
-        uint32_t off = cnt;                                      // exclusive prefix of the list lengths
+        // ---- entries: the warp copies one segment's list after the other, a lane per entry, four segments
+        // in flight; contiguous stores, and no search for the segment an entry belongs to
+        auto emit_one = [&](uint32_t e, uint32_t sp, unsigned long long dst) {
+            const uint32_t rel = e >> 17;
+            P.coo[dst] = ((uint32_t)s_lin[(sp + rel) & (G::CS - 1)] << 16) | ((uint32_t)eg_unmap(e & 0x1ffffu) & 0xffffu);
+        };
+        for (int s0 = 0; s0 < 32; s0 += 4) {
+            uint32_t sc[4], sp[4], e[4];
+            unsigned long long sz[4];
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, off, d); if (lane >= d) off += o; }
-        const uint32_t total = __shfl_sync(0xffffffffu, off, 31);
-        off -= cnt;
-        const unsigned long long dst0 = zr - off;                // coo index of this segment's entry i is dst0 + off + i
-#pragma unroll 8
-        for (uint32_t j0 = 0; j0 < total; j0 += 32) {
-            const uint32_t j = j0 + lane;
-            int s = 0;
+            for (int q = 0; q < 4; q++) {
+                sc[q] = __shfl_sync(0xffffffffu, cnt, s0 + q);
+                sp[q] = __shfl_sync(0xffffffffu, pos0, s0 + q);
+                sz[q] = __shfl_sync(0xffffffffu, zr, s0 + q);
+            }
 #pragma unroll
-            for (int step = 16; step > 0; step >>= 1) {
-                const uint32_t o = __shfl_sync(0xffffffffu, off, (s + step) & 31);
-                if (s + step < 32 && o <= j) s += step;
-            }
-            const uint32_t so = __shfl_sync(0xffffffffu, off, s);
-            const uint32_t sp = __shfl_sync(0xffffffffu, pos0, s);
-            const unsigned long long sd = __shfl_sync(0xffffffffu, dst0, s);
-            if (j < total) {
-                const uint32_t e = entry(s, j - so);
-                const uint32_t rel = e >> 17;
-                P.coo[sd + j] = ((uint32_t)s_lin[(sp + rel) & (G::CS - 1)] << 16) | ((uint32_t)eg_unmap(e & 0x1ffffu) & 0xffffu);
-            }
+            for (int q = 0; q < 4; q++) e[q] = (uint32_t)lane < sc[q] ? entry(s0 + q, lane) : 0u;
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                if ((uint32_t)lane < sc[q]) emit_one(e[q], sp[q], sz[q] + lane);
+#pragma unroll
+            for (int q = 0; q < 4; q++)                              // lists longer than a warp: dense content
+                for (uint32_t i = 32 + lane; i < sc[q]; i += 32) emit_one(entry(s0 + q, i), sp[q], sz[q] + i);
         }
 
         // ---- row pointers: this lane's cubes ------------------------------------------------------
