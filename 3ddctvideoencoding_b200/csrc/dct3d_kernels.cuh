@@ -713,16 +713,12 @@ struct WordBase {
     }
 };
 
-// The CTA's staged window.  A thread reads at most the 3 words of its lead-in walk, its own 32 words,
-// a 33-bit code running past them and the reader's two-word look-ahead: always inside the window (4 lead
-// words + 28 words of margin).  The index is clamped so that even a corrupt stream cannot read outside it.
+// The CTA's staged window.  The scan only looks at bit positions below its segment's end (plus 16 for the
+// second half of a 33-bit code), and a look reads two words: with the 4 lead words in front and 28 words of
+// margin behind the last segment every index is inside the window, whatever the stream holds.
 struct StagedSource : WordBase {
     const uint32_t *s;
-    __device__ __forceinline__ uint32_t word(uint32_t j) const
-    {
-        j = min(j, (uint32_t)kStageN - 1u);
-        return s[j + (j >> 5)];
-    }
+    __device__ __forceinline__ uint32_t word(uint32_t j) const { return s[j + (j >> 5)]; }
 };
 
 // Plain global reads (fix-up kernel: scattered segments).

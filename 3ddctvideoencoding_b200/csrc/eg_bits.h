@@ -303,29 +303,46 @@ struct NullNzSink {
 // `limit` starts (stream segments for index discovery).  Returns false on a malformed code
 // (zero padding after the last code of the stream is not an error).  With STOP the scan ends after
 // stop_after codes instead (next_start = first bit after them).
+// The 32 stream bits that start at bit `pos` (relative to the source's base), MSB first.  The scan keeps
+// no window state: every look at the stream is two word reads and one funnel shift.
+template <typename Source>
+EG_HD uint32_t eg_fetch32(const Source &src, uint32_t pos)
+{
+    const uint32_t i = pos >> 5;
+    return fsl(src.word(i), src.word(i + 1), (int)(pos & 31u));
+}
+
 template <typename Source, typename NzSink = NullNzSink, bool STOP = false>
 EG_HD bool eg_scan_segment(const Source &src, uint32_t start, uint32_t limit, uint32_t end_of_stream,
                            uint32_t &ncodes, uint32_t &next_start, uint32_t *nonzero = nullptr, NzSink sink = NzSink(),
                            uint32_t stop_after = 0)
 {
-    BitReader<Source> br(src, start);
-    uint32_t n = 0, nz = 0;
-    while (br.pos < limit) {
-        br.refill();
-        uint32_t ones = (uint32_t)clz32(~br.hi);
-        const uint32_t room = limit - br.pos;
+    uint32_t pos = start, n = 0, nz = 0;
+    while (pos < limit) {
+        // one iteration = a run of one-bits (zero coefficients) + one longer code
+        uint32_t w = eg_fetch32(src, pos);
+        uint32_t ones = (uint32_t)clz32(~w);
+        const uint32_t room = limit - pos;
         if (ones > room) ones = room;
         if (STOP && ones > stop_after - n) ones = stop_after - n;
         n += ones;
-        br.skip((int)ones);
-        if (br.pos >= limit || (STOP && n >= stop_after)) break;
-        br.refill();
-        if (br.hi >> 31) continue;
-        uint32_t m;
-        const uint32_t at = br.pos;
-        if (!br.take_code(m)) {
-            if (at + 17 >= end_of_stream || clz32(br.hi) + at >= end_of_stream) { br.pos = limit > at ? limit : at; break; }
+        pos += ones;
+        if (pos >= limit || (STOP && n >= stop_after)) break;
+        w = eg_fetch32(src, pos);
+        if (w >> 31) continue;                                  // the run goes on
+        const int z = clz32(w);
+        if (z > 16) {                                           // no such code: zero padding at the end of the stream, or damage
+            if (pos + 17 >= end_of_stream || (uint32_t)z + pos >= end_of_stream) { if (pos < limit) pos = limit; break; }
             return false;
+        }
+        uint32_t m;
+        if (z < 16) {
+            const int len = 2 * z + 1;
+            m = w >> (32 - len);
+            pos += (uint32_t)len;
+        } else {                                                // 33 bits: 16 zeros, then m in 17 bits
+            m = eg_fetch32(src, pos + 16) >> 15;
+            pos += 33;
         }
         sink.push(nz, (n << 17) | m);
         n++;
@@ -334,7 +351,7 @@ EG_HD bool eg_scan_segment(const Source &src, uint32_t start, uint32_t limit, ui
     }
     sink.flush(nz);
     ncodes = n;
-    next_start = br.pos;
+    next_start = pos;
     if (nonzero) *nonzero = nz;
     return true;
 }
