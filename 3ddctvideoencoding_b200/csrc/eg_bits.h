@@ -320,8 +320,13 @@ EG_HD bool eg_scan_segment(const Source &src, uint32_t start, uint32_t limit, ui
     uint32_t pos = start, n = 0, nz = 0;
     while (pos < limit) {
         // one iteration = a run of one-bits (zero coefficients) + one longer code
-        uint32_t w = eg_fetch32(src, pos);
+        // the run is measured on 64 bits at once: most runs of zero coefficients end inside them
+        const uint32_t wi = pos >> 5;
+        const int wb = (int)(pos & 31u);
+        const uint32_t a1 = src.word(wi + 1);
+        uint32_t w = fsl(src.word(wi), a1, wb);
         uint32_t ones = (uint32_t)clz32(~w);
+        if (ones == 32u) ones += (uint32_t)clz32(~fsl(a1, src.word(wi + 2), wb));
         const uint32_t room = limit - pos;
         if (ones > room) ones = room;
         if (STOP && ones > stop_after - n) ones = stop_after - n;
