@@ -1,24 +1,32 @@
 // dct3d_kernels.cuh -- CUDA kernels (sm_100a) for the 3D-DCT codec hot path.
 //
 // Design (see DESIGN.md for the full account):
-//   * A "tile" is 32 consecutive cubes of the stream order.  Pixels arrive as TMA boxes of
-//     128 px x 1 row x C frames (one op per row, SWIZZLE_128B) straight from the planar frame
-//     stack -- this is what replaces the host-side u8 -> float cube reshuffle readCubes /
-//     writeCubes (reference 3d-DCT-video-encoding-OpenCL/encoder.c:10-45, decoder.c:10-46).
+//   * encode_kernel: a warp transforms a "unit" of 32 px x C rows x C frames (32/C cubes) per pass.
+//     The unit arrives by ONE TMA box {32, C frames, C rows} (SWIZZLE_32B) straight from the planar
+//     frame stack into the warp's private double buffer, completing on the warp's own mbarrier: no
+//     CTA-wide barrier in the loop.  This is what replaces the host-side u8 -> float cube reshuffle
+//     readCubes / writeCubes (reference 3d-DCT-video-encoding-OpenCL/encoder.c:10-45, decoder.c:10-46).
 //   * Transform: C threads own one cube.  Thread t first holds the CxC plane of frame t in
 //     registers and runs the 1D butterflies along x and y, the cube is then transposed through
 //     a swizzled shared-memory exchange so that thread j holds all (k0, k2) for row-frequency
-//     k1 = j, and the butterflies along t follow.  24 -> 13.5 flops/sample vs the naive form.
+//     k1 = j, and the butterflies along t follow.  ~12 flop-instructions per sample (un-normalised
+//     butterflies, scales folded into the t pass and the quantiser) vs 24 for the matrix form.
 //   * The quantiser is one FFMA per coefficient (reciprocal table per lane + magic rounding).
 //   * In that layout the elements a thread owns on one diagonal k0+k2 are CONTIGUOUS in the
 //     reference's zig-zag order (CubeUtils.c:17-42: slices of constant x+y+z, y outer, z middle),
-//     so the zig-zag reorder is 64 STS.U16 with per-lane base registers and immediate offsets.
-//   * Entropy stage: one lane of warp 0 per cube (32 cubes in flight): count pass, warp scan,
-//     decoupled look-back across tiles for the global bit offset, write pass straight to the
-//     global stream (plain stores inside a cube, OR-merge for the two boundary words).
-//     The bitstream never visits the host (reference: ExpGolomb.c:32-64 on one host thread).
-//   * Decode mirrors it: stream index discovery (segment scan + fix-up), one thread per cube
-//     parse, then dequantise + inverse butterflies + clamp + truncate to u8.
+//     so the zig-zag reorder is a predicated STS.U16 per non-zero with per-lane base registers and
+//     immediate offsets; the non-zero 16-coefficient chunks go to a sparsely touched scratch.
+//   * eg_pack_kernel: one thread per cube: count pass, block scan, decoupled look-back across tiles
+//     for the global bit offset, write pass straight to the global stream (plain stores inside a
+//     cube, OR-merge for the two boundary words).  The bitstream never visits the host
+//     (reference: ExpGolomb.c:32-64 on one host thread).
+//   * Decode: index discovery over 1024-bit segments (seg_scan_kernel with a lead-in walk that
+//     guesses every entry point, keeping the non-zero codes it decodes; seg_fix_kernel; two prefix
+//     sums), seg_emit_kernel turns the segment lists into CSR rows of the cubes, and
+//     reconstruct_coo_kernel scatters the dequantised non-zeros into a float cube, runs the inverse
+//     butterflies (skipping all-zero columns), clamps, truncates and stores u8 rows.
+//   * transform_kernel: the f32 / f64 transform seams; rgb_planes_kernel: RGBUtils split / mix;
+//     quant_f64_kernel and friends: the fp64 mode.
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
