@@ -11,7 +11,7 @@
  * this restatement is pinned against (a) the known-answer vectors generated
  * from the reference's own CubeUtils.c / ExpGolomb.c (SURVEY.md App. C,
  * committed under tests/golden/) and (b) the reference's unmodified C sources
- * compiled into oracle/_ref/ by oracle/Makefile (tests/test_oracle_vs_ref.py).
+ * compiled into oracle/_ref/ by oracle/Makefile (the test_ref_*_live tests of tests/test_oracle.py).
  *
  * Every function cites the reference file:line it restates.  Paths:
  *   J/ = 3d-DCT-video-encoding/src/br/jpiccoli/video/
