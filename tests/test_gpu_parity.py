@@ -517,3 +517,37 @@ def test_fp64_mode_cube4_flips_only_at_exact_ties(codec_mod, oracle, synth):
         q = c.quantize_u8(clip).astype(np.int32)
     exact, near = classify_flips(q, ref, coef, oracle, 4)
     assert near == 0                                # the 4^3 basis is rational: only exact ties can differ
+
+
+@pytest.mark.gpu
+def test_randomised_shapes_and_contents(codec_mod, oracle):
+    """40 seeded random clips: odd cube counts per row (partial warp units, TMA on and off), every content mix.
+    For each: the fused stream equals the oracle's Exp-Golomb coding of the cubes the quantise entry point
+    returns, index discovery recovers exactly those cubes, and the fused decode equals the staged one."""
+    rng = np.random.default_rng(2026)
+    for it in range(40):
+        cube = 8 if it % 5 else 4
+        W = cube * int(rng.integers(1, 41))
+        H = cube * int(rng.integers(1, 13))
+        F = cube * int(rng.integers(1, 4)) + int(rng.integers(0, cube))      # trailing frames are ignored
+        kind = it % 4
+        if kind == 0:
+            clip = rng.integers(0, 256, (F, H, W), dtype=np.uint8)
+        elif kind == 1:
+            clip = np.full((F, H, W), int(rng.integers(0, 256)), np.uint8)
+        elif kind == 2:
+            clip = (128 + 100 * np.sin(np.arange(W) / 7.0)[None, None, :] * np.cos(np.arange(F) / 3.0)[:, None, None]
+                    + rng.normal(0, 3, (F, H, W))).clip(0, 255).astype(np.uint8)
+        else:
+            clip = np.zeros((F, H, W), np.uint8)
+            clip[rng.random((F, H, W)) < 0.01] = 255
+        Fe = F - F % cube
+        with make(codec_mod, W, H, cube) as c:
+            stream, nbits = c.encode_u8(clip)
+            q = c.quantize_u8(clip)
+            ref, ref_bits = oracle.eg_encode_cubes(q.astype(np.int32), cube, cap=5 * q.size + 64)
+            assert nbits == ref_bits and stream.tobytes() == ref[: nbits // 8 + 1].tobytes(), (it, W, H, F, cube)
+            qd, end = c.eg_decode_i16(stream, q.shape[0])
+            assert end == nbits and (qd == q).all(), (it, W, H, F, cube)
+            dec = c.decode_u8(stream, F)
+            assert dec.shape == (Fe, H, W) and (dec == c.reconstruct_i16(q, Fe)).all(), (it, W, H, F, cube)
