@@ -17,6 +17,8 @@ SYMBOLS = {
     "dct3d_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_int, C.c_int]),
     "dct3d_destroy": (None, [_vp]),
     "dct3d_last_error": (C.c_char_p, [_vp]),
+    "dct3d_eg_locate": (C.c_int, [_vp, _vp, C.c_size_t, C.c_uint64, C.c_size_t, C.POINTER(C.c_uint64)]),
+    "dct3d_eg_locate_dev": (C.c_int, [_vp, _vp, C.c_size_t, C.c_uint64, C.c_size_t, C.POINTER(C.c_uint64), _vp]),
     "dct3d_rgb_split": (C.c_int, [_vp, _vp, C.c_size_t, _vp, _vp, _vp]),
     "dct3d_rgb_mix": (C.c_int, [_vp, _vp, _vp, _vp, C.c_size_t, _vp]),
     "dct3d_rgb_split_dev": (C.c_int, [_vp, _vp, C.c_size_t, _vp, _vp, _vp, _vp]),

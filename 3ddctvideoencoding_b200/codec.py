@@ -202,6 +202,13 @@ class Codec:
         self._check(self.L.dct3d_eg_decode_i16(self.h, _ptr(s), s.size, start_bit, ncubes, _ptr(q), C.byref(end)))
         return q.reshape(-1, self.cube, self.cube, self.cube), end.value
 
+    def eg_locate(self, stream, ncubes: int, start_bit: int = 0) -> int:
+        """Bit position right after the first `ncubes` cubes of the stream (index discovery only, nothing is decoded)."""
+        s = np.ascontiguousarray(stream, np.uint8)
+        end = C.c_uint64()
+        self._check(self.L.dct3d_eg_locate(self.h, _ptr(s), s.size, start_bit, ncubes, C.byref(end)))
+        return end.value
+
     # -- device-resident (torch tensors or raw device addresses) ------------------------------------------
     def encode_u8_dev(self, d_frames, nframes: int, d_stream, cap: int, start_bit: int = 0, stream=0, want_end=True):
         end = C.c_uint64()

@@ -672,7 +672,7 @@ int dct3d_eg_encode_i16_dev(dct3d_ctx *ctx, const void *d_qcubes, size_t ncubes,
 
 // Index discovery + emit: stream -> CSR lists of the cubes' non-zero coefficients (ctx->coo, ctx->coocnt).
 static int parse_common(dct3d_ctx *ctx, const void *d_stream, size_t nbytes, uint64_t start_bit, size_t ncubes,
-                        uint64_t *end_bit, cudaStream_t st)
+                        uint64_t *end_bit, cudaStream_t st, bool locate_only = false)
 {
     int rc;
     const int C = ctx->C, CS = C * C * C;
@@ -695,8 +695,11 @@ static int parse_common(dct3d_ctx *ctx, const void *d_stream, size_t nbytes, uin
     CU_CHECK(ctx, ctx->seglist.reserve(((n + 31) / 32) * 32 * kSegListVec * sizeof(uint4)));   // dense-addressed, only the heads are touched
     const long long stiles = (long long)((P.nseg + kScanThreads * kScanItems - 1) / (kScanThreads * kScanItems));
     CU_CHECK(ctx, ctx->ctrl.reserve(kCtrlBytes + (size_t)stiles * 16));
-    CU_CHECK(ctx, ctx->coo.reserve(ncubes * CS * sizeof(uint32_t) + 2048));   // worst case: every coefficient non-zero, + the tail of the last segment's list
-    CU_CHECK(ctx, ctx->coocnt.reserve((ncubes + 1) * 8));
+    if (!locate_only) {
+        CU_CHECK(ctx, ctx->coo.reserve(ncubes * CS * sizeof(uint32_t) + 2048));   // worst case: every coefficient non-zero, + the tail of the last segment's list
+        CU_CHECK(ctx, ctx->coocnt.reserve((ncubes + 1) * 8));
+    }
+    P.locate_only = locate_only ? 1 : 0;
     P.seg_count = (unsigned int *)ctx->seg.p;
     P.seg_over = P.seg_count + n;
     P.seg_used = P.seg_over + n + 1;
@@ -779,6 +782,15 @@ int dct3d_eg_decode_i16_dev(dct3d_ctx *ctx, const void *d_stream, size_t nbytes,
     ctx->launches++;
     CU_CHECK(ctx, cudaGetLastError());
     return DCT3D_OK;
+}
+
+int dct3d_eg_locate_dev(dct3d_ctx *ctx, const void *d_stream, size_t nbytes, uint64_t start_bit, size_t ncubes,
+                        uint64_t *end_bit, void *cuda_stream)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (ncubes == 0) { if (end_bit) *end_bit = start_bit; return DCT3D_OK; }
+    return parse_common(ctx, d_stream, nbytes, start_bit, ncubes, end_bit, pick(ctx, cuda_stream), true);
 }
 
 int dct3d_reconstruct_i16_dev(dct3d_ctx *ctx, const void *d_qcubes, int nframes, void *d_frames, void *cuda_stream)
@@ -1079,6 +1091,21 @@ int dct3d_eg_encode_i16(dct3d_ctx *ctx, const int16_t *qcubes, size_t ncubes, ui
     SYNC(ctx);
     if (end_bit) *end_bit = end;
     return DCT3D_OK;
+}
+
+int dct3d_eg_locate(dct3d_ctx *ctx, const uint8_t *stream, size_t nbytes, uint64_t start_bit, size_t ncubes, uint64_t *end_bit)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (ncubes == 0) { if (end_bit) *end_bit = start_bit; return DCT3D_OK; }
+    if (!stream) return fail(ctx, DCT3D_E_INVALID, "null pointer");
+    const size_t padded = ((nbytes + 3) & ~(size_t)3) + 8;
+    CU_CHECK(ctx, ctx->bits.reserve(padded));
+    CU_CHECK(ctx, cudaMemsetAsync((uint8_t *)ctx->bits.p + (nbytes & ~(size_t)3), 0, padded - (nbytes & ~(size_t)3), ctx->stream));
+    H2D(ctx, ctx->bits.p, stream, nbytes);
+    rc = dct3d_eg_locate_dev(ctx, ctx->bits.p, nbytes, start_bit, ncubes, end_bit, nullptr);
+    if (rc == DCT3D_E_NEED_MORE) return fail(ctx, DCT3D_E_STREAM, "Exp-Golomb stream truncated: %s", ctx->err.c_str());
+    return rc;
 }
 
 int dct3d_eg_decode_i16(dct3d_ctx *ctx, const uint8_t *stream, size_t nbytes, uint64_t start_bit,

@@ -809,6 +809,7 @@ struct DecParams {
     unsigned long long *end_bit;        // out: first bit after the last code
     uint32_t *coo;                      // non-zero coefficients of the whole stream, in stream order: natural index << 16 | value
     unsigned long long *coo_start;      // [ncubes+1] first entry of every cube (CSR row pointers)
+    int locate_only;                    // seg_emit_kernel: only report where the clip ends (dct3d_eg_locate)
     int16_t *qcubes;                    // natural-order cubes out (coo_scatter_kernel)
     uint8_t *frames;
 };
@@ -989,6 +990,16 @@ seg_emit_kernel(const DecParams P)
         const unsigned long long wbase = (kw >> 5) * (unsigned long long)(kSegListVec * 32 * 4);
         auto entry = [&](int s, uint32_t i) { return __ldg(lists + wbase + (unsigned)s * 4u + (i >> 2) * 128u + (i & 3u)); };
 
+        // first entry with rel >= bound (the list is sorted by rel)
+        auto lower_bound = [&](uint32_t bound) {
+            uint32_t lo = 0, up = cnt;
+            while (lo < up) {
+                const uint32_t mid = (lo + up) >> 1;
+                if ((entry(lane, mid) >> 17) < bound) lo = mid + 1; else up = mid;
+            }
+            return lo;
+        };
+        if (!P.locate_only) {
         // ---- entries: the warp copies one segment's list after the other, a lane per entry, four segments
         // in flight; contiguous stores, and no search for the segment an entry belongs to
         auto emit_one = [&](uint32_t e, uint32_t sp, unsigned long long dst) {
@@ -1015,22 +1026,14 @@ seg_emit_kernel(const DecParams P)
         }
 
         // ---- row pointers: this lane's cubes ------------------------------------------------------
-        // first entry with rel >= bound (the list is sorted by rel)
-        auto lower_bound = [&](uint32_t bound) {
-            uint32_t lo = 0, up = cnt;
-            while (lo < up) {
-                const uint32_t mid = (lo + up) >> 1;
-                if ((entry(lane, mid) >> 17) < bound) lo = mid + 1; else up = mid;
-            }
-            return lo;
-        };
         if (active) {
             unsigned long long cube = cur / G::CS + (pos0 ? 1 : 0);       // next cube to start at or after `cur`
             for (uint32_t nb = pos0 ? (uint32_t)G::CS - pos0 : 0u; nb < span; nb += G::CS)
                 P.coo_start[cube++] = zr + (nb ? lower_bound(nb) : 0u);
         }
+        }
         if (last) {
-            P.coo_start[P.L.ncubes] = zr + lower_bound(span);
+            if (!P.locate_only) P.coo_start[P.L.ncubes] = zr + lower_bound(span);
             // where does the clip end?  re-walk this one segment up to its last code
             LocalSource src;
             src.w0 = (P.start_bit >> 5) + k * kSegWords;

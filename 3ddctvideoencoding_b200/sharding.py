@@ -63,3 +63,20 @@ def gather_bit_counts(nbits: int, group=None) -> list[int]:
     out = [torch.zeros_like(mine) for _ in range(world)]
     dist.all_gather(out, mine, group=group)
     return [int(t.item()) for t in out]
+
+
+def decode_range(codec, stream, nslabs: int, rank: int, world: int, cubes_per_slab: int, start_bits=None):
+    """Rank `rank` decodes its slab range of ONE concatenated stream (the reference's file layout).
+
+    The stream carries no index, so the range's first bit has to come from somewhere: `start_bits` (the
+    exclusive prefix of the encoder ranks' bit counts, `bit_offsets`) when the encoder's side information is at
+    hand, otherwise `codec.eg_locate`, which runs index discovery over the stream up to the range's first cube
+    (SURVEY.md 8e).  Returns (frames of the range, start bit used)."""
+    lo, hi = slab_range(nslabs, rank, world)
+    if hi == lo:
+        return np.zeros((0, codec.height, codec.width), np.uint8), 0
+    start = int(start_bits[rank]) if start_bits is not None else codec.eg_locate(stream, lo * cubes_per_slab)
+    s = np.ascontiguousarray(stream, np.uint8)
+    byte0 = start // 8                     # the library takes a bit offset below 8 plus whole bytes
+    q, _ = codec.eg_decode_i16(s[byte0:], (hi - lo) * cubes_per_slab, start % 8)
+    return codec.reconstruct_i16(q, (hi - lo) * codec.cube), start

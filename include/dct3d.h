@@ -144,6 +144,12 @@ int dct3d_eg_encode_i16(dct3d_ctx *ctx, const int16_t *qcubes, size_t ncubes, ui
 int dct3d_eg_decode_i16(dct3d_ctx *ctx, const uint8_t *stream, size_t nbytes, uint64_t start_bit,
                         size_t ncubes, int16_t *qcubes, uint64_t *end_bit);
 
+/* Finds where the first `ncubes` cubes of the stream end (*end_bit) without decoding them: index discovery only.
+ * The stream has no index (J/ExpGolombReader.java:19-63 is the only way the reference knows a code boundary), so
+ * this is how a GPU that decodes a later slab range learns its start bit when the encoder's bit counts are not at
+ * hand. */
+int dct3d_eg_locate(dct3d_ctx *ctx, const uint8_t *stream, size_t nbytes, uint64_t start_bit, size_t ncubes, uint64_t *end_bit);
+
 /* ---- device-resident variants ------------------------------------------------------------
  * All pointers are device pointers on the context's GPU; `cuda_stream` is a cudaStream_t (NULL =
  * the context's own stream, which is non-blocking: it does not synchronise with the legacy default
@@ -168,6 +174,8 @@ int dct3d_eg_encode_i16_dev(dct3d_ctx *ctx, const void *d_qcubes, size_t ncubes,
                             void *d_stream, size_t cap, uint64_t *end_bit, void *cuda_stream);
 int dct3d_eg_decode_i16_dev(dct3d_ctx *ctx, const void *d_stream, size_t nbytes, uint64_t start_bit,
                             size_t ncubes, void *d_qcubes, uint64_t *end_bit, void *cuda_stream);
+int dct3d_eg_locate_dev(dct3d_ctx *ctx, const void *d_stream, size_t nbytes, uint64_t start_bit, size_t ncubes,
+                        uint64_t *end_bit, void *cuda_stream);
 
 /* ---- colour planes (the reference codes colour video as three gray streams) --------------------
  * RGBUtils split / mix (J/RGBUtils.java:39-92 and :94-131): byte i of a raw RGB24 buffer belongs to

@@ -551,3 +551,27 @@ def test_randomised_shapes_and_contents(codec_mod, oracle):
             assert end == nbits and (qd == q).all(), (it, W, H, F, cube)
             dec = c.decode_u8(stream, F)
             assert dec.shape == (Fe, H, W) and (dec == c.reconstruct_i16(q, Fe)).all(), (it, W, H, F, cube)
+
+
+@pytest.mark.gpu
+def test_locate_and_sharded_decode_without_side_information(codec_mod, oracle, synth):
+    """SURVEY.md 8e, decode side: a rank that decodes a later slab range of the one concatenated stream finds its
+    first bit by index discovery alone (dct3d_eg_locate), and its frames equal the one-shot decode's."""
+    sh = pkg("sharding")
+    W, H, F = 128, 64, 48
+    clip = gen(synth, "natural", W, H, F, 11)
+    with make(codec_mod, W, H, 8) as c:
+        stream, nbits = c.encode_u8(clip)
+        whole = c.decode_u8(stream, F)
+        nslabs, cps = F // 8, (W // 8) * (H // 8)
+        # every slab boundary, against the oracle's sequential reader
+        q = c.quantize_u8(clip).astype(np.int32)
+        for s in range(nslabs + 1):
+            _, want = oracle.eg_encode_cubes(q[: s * cps], 8, cap=5 * q.size + 64) if s else (None, 0)
+            assert c.eg_locate(stream, s * cps) == want
+        assert c.eg_locate(stream, nslabs * cps) == nbits
+        for world in (2, 3, 4):
+            parts = [sh.decode_range(c, stream, nslabs, r, world, cps)[0] for r in range(world)]
+            assert (np.concatenate(parts) == whole).all()
+        with pytest.raises(codec_mod.Dct3dError):
+            c.eg_locate(stream, nslabs * cps + 1)           # more cubes than the stream holds
