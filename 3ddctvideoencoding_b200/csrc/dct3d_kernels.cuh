@@ -1380,14 +1380,17 @@ transform_kernel(const Layout L, const T *__restrict__ in, T *__restrict__ out)
         };
         T a[C][C], b[C][C];
         if (!INVERSE) {
+            // t pass first (thread = row y holds [t][x]): the C threads of a cube then load one contiguous
+            // run per frame, the same access shape as the inverse direction, which scattered row loads by
+            // frame do not reach (5.5 vs 6.0 TB/s); the transform is separable, so the order is free
 #pragma unroll
-            for (int y = 0; y < C; y++) load_row<C, T>(in + addr(r, y, 0), a[y], valid);
-            fwd_xy<C, T>(a);
-            Xch<C, T>::transpose(smem + warp * Xch<C, T>::WARP_BYTES, cl, r, a, b);
+            for (int t = 0; t < C; t++) load_row<C, T>(in + addr(t, r, 0), b[t], valid);
             fwd_t<C, T>(b);
+            Xch<C, T>::transpose(smem + warp * Xch<C, T>::WARP_BYTES, cl, r, b, a);   // thread = k0 holds [y][x]
+            fwd_xy<C, T>(a);
             if (valid) {
 #pragma unroll
-                for (int k0 = 0; k0 < C; k0++) store_row<C, T>(out + addr(k0, r, 0), b[k0]);
+                for (int k1 = 0; k1 < C; k1++) store_row<C, T>(out + addr(r, k1, 0), a[k1]);
             }
         } else {
 #pragma unroll
