@@ -23,6 +23,20 @@ SYMBOLS = {
     "dct3d_rgb_mix": (C.c_int, [_vp, _vp, _vp, _vp, C.c_size_t, _vp]),
     "dct3d_rgb_split_dev": (C.c_int, [_vp, _vp, C.c_size_t, _vp, _vp, _vp, _vp]),
     "dct3d_rgb_mix_dev": (C.c_int, [_vp, _vp, _vp, _vp, C.c_size_t, _vp, _vp]),
+    "dct3d_encode_u8_range": (C.c_int, [_vp, _vp, C.c_int, _u64p]),
+    "dct3d_encode_u8_place": (C.c_int, [_vp, C.c_uint64, C.c_int, _vp, C.c_size_t, C.POINTER(C.c_uint8)]),
+    "dct3d_decode_u8_range": (C.c_int, [_vp, _vp, C.c_size_t, C.c_uint64, C.c_uint64, C.c_int, _vp, _u64p]),
+    "dct3d_stream_shift_dev": (C.c_int, [_vp, _vp, C.c_uint64, C.c_uint, _vp, C.c_size_t, _vp]),
+    "dct3d_host_register": (C.c_int, [_vp, C.c_size_t]),
+    "dct3d_host_unregister": (C.c_int, [_vp]),
+    "dct3d_multi_create": (C.c_int, [C.POINTER(_vp), C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, C.c_int]),
+    "dct3d_multi_destroy": (None, [_vp]),
+    "dct3d_multi_last_error": (C.c_char_p, [_vp]),
+    "dct3d_multi_set_option": (C.c_int, [_vp, C.c_char_p, C.c_long]),
+    "dct3d_multi_context": (C.c_void_p, [_vp, C.c_int]),
+    "dct3d_multi_encode_u8": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_size_t, _u64p, _szp, _u64p]),
+    "dct3d_multi_locate": (C.c_int, [_vp, _vp, C.c_size_t, C.c_int, _u64p]),
+    "dct3d_multi_decode_u8": (C.c_int, [_vp, _vp, C.c_size_t, C.c_int, _vp, _u64p]),
     "dct3d_host_alloc": (C.c_void_p, [C.c_size_t]),
     "dct3d_host_free": (None, [_vp]),
     "dct3d_set_option": (C.c_int, [_vp, C.c_char_p, C.c_long]),

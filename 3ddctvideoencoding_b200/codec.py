@@ -109,6 +109,36 @@ class Codec:
         self._check(self.L.dct3d_decode_u8(self.h, _ptr(s), s.size, nframes, _ptr(out)))
         return out
 
+    # -- sharded coding: a slab range per GPU / process, placed into the clip's one stream -------------
+    def encode_u8_range(self, frames) -> int:
+        """Phase 1: code the frames from bit 0 into the context's device buffer; returns the bit count."""
+        fr = frames if not isinstance(frames, np.ndarray) else np.ascontiguousarray(frames, np.uint8)
+        F = (fr.size if isinstance(fr, np.ndarray) else fr.numel()) // (self.width * self.height)
+        nbits = C.c_uint64()
+        self._check(self.L.dct3d_encode_u8_range(self.h, _ptr(fr), F, C.byref(nbits)))
+        return nbits.value
+
+    def encode_u8_place(self, start_bit: int, last: bool, stream, cap: int | None = None) -> int:
+        """Phase 2: move the coded range to global bit `start_bit` of the host buffer `stream`; returns the range's
+        first byte when it is shared with the predecessor (to be OR-ed in by the caller), else 0."""
+        fb = C.c_uint8(0)
+        cap = cap if cap is not None else (stream.size if isinstance(stream, np.ndarray) else stream.numel())
+        self._check(self.L.dct3d_encode_u8_place(self.h, start_bit, 1 if last else 0, _ptr(stream), cap, C.byref(fb)))
+        return fb.value
+
+    def decode_u8_range(self, stream, start_bit: int, nframes: int, end_bit_hint: int = 0, out=None, nbytes: int | None = None):
+        """Decode `nframes` frames whose first code starts at bit `start_bit` of `stream`; returns (frames, end bit)."""
+        s = stream if not isinstance(stream, np.ndarray) else np.ascontiguousarray(stream, np.uint8)
+        nbytes = nbytes if nbytes is not None else (s.size if isinstance(s, np.ndarray) else s.numel())
+        if out is None:
+            out = np.zeros((self._nframes_eff(nframes), self.height, self.width), np.uint8)
+        end = C.c_uint64()
+        self._check(self.L.dct3d_decode_u8_range(self.h, _ptr(s), nbytes, start_bit, end_bit_hint, nframes, _ptr(out), C.byref(end)))
+        return out, end.value
+
+    def stream_shift_dev(self, d_src, nbits: int, phase: int, d_dst, cap: int, stream=0):
+        self._check(self.L.dct3d_stream_shift_dev(self.h, _ptr(d_src), nbits, phase, _ptr(d_dst), cap, stream))
+
     # -- streaming ------------------------------------------------------------------------------
     def stream_begin(self):
         self._check(self.L.dct3d_stream_begin(self.h))
@@ -263,6 +293,73 @@ class Codec:
 
     def rgb_mix_dev(self, d_r, d_g, d_b, npixels: int, d_rgb, stream=0):
         self._check(self.L.dct3d_rgb_mix_dev(self.h, _ptr(d_r), _ptr(d_g), _ptr(d_b), npixels, _ptr(d_rgb), stream))
+
+
+class MultiCodec:
+    """Several GPUs in one process (dct3d_multi_*): contiguous slab ranges, one stream."""
+
+    def __init__(self, width: int, height: int, cube: int = 8, devices=None, ndevices: int | None = None):
+        self.L = _lib.load()
+        self.width, self.height, self.cube = width, height, cube
+        devs = list(devices) if devices is not None else list(range(ndevices or 1))
+        self.n = len(devs)
+        arr = (C.c_int * self.n)(*devs)
+        h = C.c_void_p()
+        rc = self.L.dct3d_multi_create(C.byref(h), arr, self.n, width, height, cube)
+        if rc != _lib.OK:
+            raise Dct3dError(rc, (self.L.dct3d_last_error(None) or b"").decode())
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.dct3d_multi_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc: int):
+        if rc != _lib.OK:
+            raise Dct3dError(rc, (self.L.dct3d_multi_last_error(self.h) or b"").decode())
+
+    def set_option(self, key: str, value: int):
+        self._check(self.L.dct3d_multi_set_option(self.h, key.encode(), value))
+
+    def encode_u8(self, frames, out=None, cap: int | None = None):
+        """-> (stream bytes, nbits, start bit of every range [n+1])."""
+        fr = frames if not isinstance(frames, np.ndarray) else np.ascontiguousarray(frames, np.uint8)
+        size = fr.size if isinstance(fr, np.ndarray) else fr.numel()
+        F = size // (self.width * self.height)
+        if out is None:
+            cap = cap or (size // 2 + 4096)
+            out = np.zeros(cap, np.uint8)
+        cap = cap or (out.size if isinstance(out, np.ndarray) else out.numel())
+        nbits, nbytes = C.c_uint64(), C.c_size_t()
+        starts = (C.c_uint64 * (self.n + 1))()
+        self._check(self.L.dct3d_multi_encode_u8(self.h, _ptr(fr), F, _ptr(out), cap, C.byref(nbits), C.byref(nbytes), starts))
+        return out[: nbytes.value], nbits.value, list(starts)
+
+    def locate(self, stream, nframes: int):
+        s = stream if not isinstance(stream, np.ndarray) else np.ascontiguousarray(stream, np.uint8)
+        starts = (C.c_uint64 * (self.n + 1))()
+        self._check(self.L.dct3d_multi_locate(self.h, _ptr(s), s.size if isinstance(s, np.ndarray) else s.numel(), nframes, starts))
+        return list(starts)
+
+    def decode_u8(self, stream, nframes: int, range_start_bits=None, out=None):
+        s = stream if not isinstance(stream, np.ndarray) else np.ascontiguousarray(stream, np.uint8)
+        nbytes = s.size if isinstance(s, np.ndarray) else s.numel()
+        if out is None:
+            out = np.zeros((nframes - nframes % self.cube, self.height, self.width), np.uint8)
+        sb = None
+        if range_start_bits is not None:
+            sb = (C.c_uint64 * (self.n + 1))(*[int(x) for x in range_start_bits])
+        self._check(self.L.dct3d_multi_decode_u8(self.h, _ptr(s), nbytes, nframes, _ptr(out), sb))
+        return out
 
 
 def list_devices() -> str:

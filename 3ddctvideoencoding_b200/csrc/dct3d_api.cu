@@ -7,7 +7,10 @@
 #include <string.h>
 
 #include <algorithm>
+#include <condition_variable>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/dct3d.h"
@@ -69,6 +72,19 @@ struct dct3d_ctx {
     // streaming state
     uint8_t carry_byte = 0;
     int carry_bits = 0;
+    // pipelined host-buffer paths (dct3d_encode_u8 / dct3d_decode_u8 and the range calls)
+    int chunk_frames = 0;            // option: frames per pipeline chunk (0 = about 32 MB of pixels)
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    std::vector<cudaEvent_t> pev;    // event pool (no timing)
+    DevBuf ring[3];                  // frame chunks in flight
+    DevBuf chain;                    // u64 bit positions between chunks + the chain's error word
+    DevBuf bits2;                    // a range's stream moved to its phase (dct3d_encode_u8_place)
+    unsigned long long *h_chain = nullptr;   // pinned mirror of the chain slots
+    size_t h_chain_n = 0;
+    uint8_t *h_byte = nullptr;       // pinned scratch (the first byte of a placed range)
+    uint64_t range_bits = 0;         // bit count of the range held in `bits` (dct3d_encode_u8_range)
+    bool range_valid = false;
+    long chunks_last = 0;            // statistics: pipeline chunks of the last host-buffer call
 };
 
 namespace {
@@ -119,9 +135,11 @@ void build_zz(int C, std::vector<int> &lin)
 }
 
 bool g_tables_ready[64] = {false};
+std::mutex g_tables_mu;
 
 int upload_tables(dct3d_ctx *ctx)
 {
+    std::lock_guard<std::mutex> lock(g_tables_mu);          // contexts may be created concurrently (one per host thread)
     if (ctx->device < 64 && g_tables_ready[ctx->device]) return DCT3D_OK;
     ZzTables t;
     memset(&t, 0, sizeof t);
@@ -157,16 +175,15 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
 
 EncodeTiledFn get_encode_tiled()
 {
-    static EncodeTiledFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
+    // function-local static: initialised once, thread-safe (contexts are created from several host threads)
+    static const EncodeTiledFn fn = []() -> EncodeTiledFn {
         void *p = nullptr;
         cudaDriverEntryPointQueryResult q;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
             q == cudaDriverEntryPointSuccess)
-            fn = (EncodeTiledFn)p;
-    }
+            return (EncodeTiledFn)p;
+        return nullptr;
+    }();
     return fn;
 }
 
@@ -266,7 +283,7 @@ int zero_stream(dct3d_ctx *ctx, void *d_stream, size_t cap, uint64_t start_bit, 
 
 
 template <int C>
-static int launch_reconstruct_coo(dct3d_ctx *ctx, const Layout &L, void *d_frames, cudaStream_t st)
+static int launch_reconstruct_coo(dct3d_ctx *ctx, const Layout &L, void *d_frames, cudaStream_t st, long long cube_base = 0)
 {
     auto kern = reconstruct_coo_kernel<C>;
     const int smem = CooSmem<C>::TOTAL;
@@ -278,7 +295,7 @@ static int launch_reconstruct_coo(dct3d_ctx *ctx, const Layout &L, void *d_frame
     const long long groups = (L.ncubes + Geo<C>::CPW - 1) / Geo<C>::CPW;
     const long long grid = std::min<long long>((groups + kWarps - 1) / kWarps, (long long)ctx->num_sms * std::max(occ, 1));
     cudaEventRecord(ctx->ev[2], st);
-    kern<<<(unsigned)grid, kThreads, smem, st>>>(L, (const uint32_t *)ctx->coo.p, (const unsigned long long *)ctx->coocnt.p, (uint8_t *)d_frames);
+    kern<<<(unsigned)grid, kThreads, smem, st>>>(L, (const uint32_t *)ctx->coo.p, (const unsigned long long *)ctx->coocnt.p, (uint8_t *)d_frames, cube_base);
     cudaEventRecord(ctx->ev[3], st);
     ctx->ev_valid[1] = true;
     ctx->launches++;
@@ -395,6 +412,9 @@ int dct3d_create(dct3d_ctx **out, int device, int width, int height, int cube)
         for (int i = 0; i < 4 && e == cudaSuccess; i++) e = cudaEventCreate(&ctx->ev[i]);
         if (e == cudaSuccess) e = cudaMallocHost((void **)&ctx->h_ctrl, sizeof(Ctrl));
         if (e == cudaSuccess) e = cudaMallocHost((void **)&ctx->h_u64, 4 * sizeof(unsigned long long));
+        if (e == cudaSuccess) e = cudaMallocHost((void **)&ctx->h_byte, 16);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking);
         if (e != cudaSuccess) rc = fail(ctx, DCT3D_E_CUDA, "context setup failed: %s", cudaGetErrorString(e));
     }
     if (rc == DCT3D_OK) rc = upload_tables(ctx);
@@ -407,7 +427,13 @@ void dct3d_destroy(dct3d_ctx *ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    for (DevBuf *b : {&ctx->frames, &ctx->bits, &ctx->q, &ctx->ctrl, &ctx->seg, &ctx->seglist, &ctx->fa, &ctx->fb, &ctx->zz, &ctx->cmask, &ctx->coo, &ctx->coocnt}) b->release();
+    for (DevBuf *b : {&ctx->frames, &ctx->bits, &ctx->q, &ctx->ctrl, &ctx->seg, &ctx->seglist, &ctx->fa, &ctx->fb, &ctx->zz, &ctx->cmask, &ctx->coo, &ctx->coocnt,
+                      &ctx->ring[0], &ctx->ring[1], &ctx->ring[2], &ctx->chain, &ctx->bits2}) b->release();
+    for (cudaEvent_t e : ctx->pev) cudaEventDestroy(e);
+    if (ctx->h_chain) cudaFreeHost(ctx->h_chain);
+    if (ctx->h_byte) cudaFreeHost(ctx->h_byte);
+    if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
+    if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
     for (int i = 0; i < 4; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->h_ctrl) cudaFreeHost(ctx->h_ctrl);
     if (ctx->h_u64) cudaFreeHost(ctx->h_u64);
@@ -448,6 +474,11 @@ int dct3d_set_option(dct3d_ctx *ctx, const char *key, long value)
         return DCT3D_OK;
     }
     if (!strcmp(key, "rounding")) { ctx->rounding = value ? 1 : 0; return DCT3D_OK; }
+    if (!strcmp(key, "chunk_frames")) {
+        if (value < 0 || value % ctx->C) return fail(ctx, DCT3D_E_INVALID, "chunk_frames must be a non-negative multiple of the cube edge");
+        ctx->chunk_frames = (int)value;
+        return DCT3D_OK;
+    }
     if (!strcmp(key, "reuse_zeroed")) { ctx->reuse_zeroed = value ? 1 : 0; ctx->clean_ptr = nullptr; return DCT3D_OK; }
     return fail(ctx, DCT3D_E_INVALID, "unknown option '%s'", key);
 }
@@ -458,6 +489,7 @@ long dct3d_get_stat(const dct3d_ctx *ctx, const char *key)
     if (!strcmp(key, "launches")) return ctx->launches;
     if (!strcmp(key, "tma")) return ctx->use_tma;
     if (!strcmp(key, "num_sms")) return ctx->num_sms;
+    if (!strcmp(key, "chunks")) return ctx->chunks_last;
     // device time of the last encode_kernel / reconstruct_coo_kernel launch, nanoseconds (CUDA events on
     // the launching stream; waits for that launch to finish)
     for (int k = 0; k < 2; k++) {
@@ -519,8 +551,17 @@ static int reconstruct_f64(dct3d_ctx *ctx, const void *d_q, int nslabs, void *d_
     return DCT3D_OK;
 }
 
+// Bit positions chained on the device: the pipelined host-buffer encoder codes a clip as consecutive slab ranges
+// without visiting the host in between (the rule of expGolomb_freeBuffer, C/ExpGolomb.c:112-122, kept on the GPU).
+struct Chain {
+    const unsigned long long *d_start = nullptr;   // the packer reads its start bit here ...
+    unsigned long long *d_end = nullptr;           // ... and leaves its end bit here
+    unsigned int *d_err = nullptr;                 // sticky error word of the whole chain (not reset per call)
+};
+
 // Kernel 2 (bit packing) over ctx->zz / ctx->cmask.  P.L.ncubes must be set.
-static int run_pack_noreset(dct3d_ctx *ctx, EncParams &P, void *d_stream, size_t cap, uint64_t start_bit, uint64_t *end_bit, cudaStream_t st)
+static int run_pack_noreset(dct3d_ctx *ctx, EncParams &P, void *d_stream, size_t cap, uint64_t start_bit, uint64_t *end_bit, cudaStream_t st,
+                            const Chain *chain = nullptr)
 {
     int rc;
     const long long ptiles = (P.L.ncubes + kPackThreads - 1) / kPackThreads;
@@ -530,6 +571,7 @@ static int run_pack_noreset(dct3d_ctx *ctx, EncParams &P, void *d_stream, size_t
     P.start_bit = start_bit;
     P.tile_status = status_words(ctx);
     P.ticket = &dc->ticket; P.err = &dc->err; P.end_bit = &dc->end_bit;
+    if (chain) { P.start_bit_dev = chain->d_start; P.end_bit = chain->d_end; P.err = chain->d_err; }
     int &occ = ctx->occ_cache[4];
     if (occ == 0) {
         if (ctx->C == 8) CU_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, eg_pack_kernel<8>, kPackThreads, 0));
@@ -559,7 +601,7 @@ static int run_pack(dct3d_ctx *ctx, EncParams &P, void *d_stream, size_t cap, ui
 }
 
 static int encode_common(dct3d_ctx *ctx, const void *d_frames, int nframes, void *d_stream, size_t cap,
-                         uint64_t start_bit, uint64_t *end_bit, void *cuda_stream, void *d_qcubes)
+                         uint64_t start_bit, uint64_t *end_bit, void *cuda_stream, void *d_qcubes, const Chain *chain = nullptr)
 {
     int rc = bind(ctx);
     if (rc) return rc;
@@ -575,6 +617,9 @@ static int encode_common(dct3d_ctx *ctx, const void *d_frames, int nframes, void
     }
     if (nslabs == 0) { if (end_bit) *end_bit = start_bit; return DCT3D_OK; }
     if (!d_frames) return fail(ctx, DCT3D_E_INVALID, "null frame pointer");
+    if ((uintptr_t)d_frames % (size_t)C) return fail(ctx, DCT3D_E_INVALID, "frame buffer must be aligned to the cube edge (%d bytes)", C);
+    if (emit_q && ((uintptr_t)d_qcubes & 15)) return fail(ctx, DCT3D_E_INVALID, "cube buffer must be 16-byte aligned");
+    if (chain && ctx->precision == 64) return fail(ctx, DCT3D_E_INVALID, "chained ranges are an fp32-path feature");
     if (ctx->precision == 64) {
         // fp64 mode: u8 -> double, the f64 transform seam, the reference's quantiser in double, then the
         // same zig-zag gather and bit packer as the stage entry point
@@ -592,7 +637,7 @@ static int encode_common(dct3d_ctx *ctx, const void *d_frames, int nframes, void
     P.use_tma = ctx->use_tma && !((uintptr_t)d_frames & 15);
     P.debug = ctx->debug;
     CU_CHECK(ctx, ctx->ctrl.reserve(kCtrlBytes + (size_t)((P.L.ncubes + kPackThreads - 1) / kPackThreads) * 8));   // final size: the pointer below stays valid
-    P.err = &((Ctrl *)ctx->ctrl.p)->err;
+    P.err = chain ? chain->d_err : &((Ctrl *)ctx->ctrl.p)->err;
     if (!emit_q) {
         CU_CHECK(ctx, ctx->zz.reserve((size_t)P.L.ncubes * C * C * C * sizeof(int16_t)));
         CU_CHECK(ctx, ctx->cmask.reserve((size_t)P.L.ncubes * 4));
@@ -616,6 +661,10 @@ static int encode_common(dct3d_ctx *ctx, const void *d_frames, int nframes, void
     // again only partially by run_pack: keep one reset, done by run_pack, and run kernel 1 after it
     const long long ptiles = (P.L.ncubes + kPackThreads - 1) / kPackThreads;
     if ((rc = reset_ctrl(ctx, ptiles, st))) return rc;
+    if (chain) {                                                   // the caller wiped the whole stream buffer once
+        rc = C == 8 ? launch_encode<8, MODE_ZZ>(ctx, P, tm, st) : launch_encode<4, MODE_ZZ>(ctx, P, tm, st);
+        return rc ? rc : run_pack_noreset(ctx, P, d_stream, cap, 0, nullptr, st, chain);
+    }
     // The wipe of the stream buffer only has to precede kernel 2: it is forked onto the side stream
     // (after whatever the caller's stream did to the buffer before) and joined in front of the packer,
     // so it runs beside kernel 1, which leaves DRAM 80% idle.
@@ -652,6 +701,7 @@ int dct3d_eg_encode_i16_dev(dct3d_ctx *ctx, const void *d_qcubes, size_t ncubes,
     if ((rc = zero_stream(ctx, d_stream, cap, start_bit, st))) return rc;
     if (ncubes == 0) { if (end_bit) *end_bit = start_bit; return DCT3D_OK; }
     if (!d_qcubes) return fail(ctx, DCT3D_E_INVALID, "null cube pointer");
+    if ((uintptr_t)d_qcubes & 15) return fail(ctx, DCT3D_E_INVALID, "cube buffer must be 16-byte aligned");
     const int C = ctx->C;
     EncParams P;
     memset(&P, 0, sizeof P);
@@ -754,7 +804,8 @@ static int parse_common(dct3d_ctx *ctx, const void *d_stream, size_t nbytes, uin
     if (ctx->h_u64[0] < (unsigned long long)ncubes * CS)
         return fail(ctx, DCT3D_E_NEED_MORE, "stream holds %llu codes, %llu needed", ctx->h_u64[0], (unsigned long long)ncubes * CS);
     if (ctx->h_ctrl->err & 2u) return fail(ctx, DCT3D_E_STREAM, "malformed Exp-Golomb code in stream");
-    if (ctx->h_ctrl->err & 4u) return fail(ctx, DCT3D_E_STREAM, "Exp-Golomb stream truncated");
+    if (ctx->h_ctrl->end_bit > P.nbits_total)        // cannot happen with the scan's end-of-stream rule; kept as a guard
+        return fail(ctx, DCT3D_E_NEED_MORE, "the last code runs past the end of the buffered stream");
     if (end_bit) *end_bit = ctx->h_ctrl->end_bit;
     return DCT3D_OK;
 }
@@ -766,6 +817,7 @@ int dct3d_eg_decode_i16_dev(dct3d_ctx *ctx, const void *d_stream, size_t nbytes,
     if (rc) return rc;
     if (ncubes == 0) { if (end_bit) *end_bit = start_bit; return DCT3D_OK; }
     if (!d_qcubes) return fail(ctx, DCT3D_E_INVALID, "null cube pointer");
+    if ((uintptr_t)d_qcubes & 15) return fail(ctx, DCT3D_E_INVALID, "cube buffer must be 16-byte aligned");
     cudaStream_t st = pick(ctx, cuda_stream);
     if ((rc = parse_common(ctx, d_stream, nbytes, start_bit, ncubes, end_bit, st))) return rc;
     DecParams P;
@@ -801,6 +853,8 @@ int dct3d_reconstruct_i16_dev(dct3d_ctx *ctx, const void *d_qcubes, int nframes,
     const int nslabs = nframes / ctx->C;
     if (nslabs == 0) return DCT3D_OK;
     if (!d_qcubes || !d_frames) return fail(ctx, DCT3D_E_INVALID, "null pointer");
+    if (((uintptr_t)d_qcubes & 15) || (uintptr_t)d_frames % (size_t)ctx->C)
+        return fail(ctx, DCT3D_E_INVALID, "cube buffer must be 16-byte aligned and the frame buffer aligned to the cube edge");
     const Layout L = make_layout(ctx->W, ctx->H, ctx->C, nslabs);
     cudaStream_t st = pick(ctx, cuda_stream);
     if (ctx->precision == 64) return reconstruct_f64(ctx, d_qcubes, nslabs, d_frames, st);
@@ -816,6 +870,7 @@ int dct3d_decode_u8_dev(dct3d_ctx *ctx, const void *d_stream, size_t nbytes, uin
     const int C = ctx->C, nslabs = nframes / C;
     if (nslabs == 0) { if (end_bit) *end_bit = start_bit; return DCT3D_OK; }
     if (!d_frames) return fail(ctx, DCT3D_E_INVALID, "null frame pointer");
+    if ((uintptr_t)d_frames % (size_t)C) return fail(ctx, DCT3D_E_INVALID, "frame buffer must be aligned to the cube edge (%d bytes)", C);
     const Layout L = make_layout(ctx->W, ctx->H, C, nslabs);
     cudaStream_t st = pick(ctx, cuda_stream);
     uint64_t end = 0;
@@ -903,6 +958,176 @@ int dct3d_inverse_f64_dev(dct3d_ctx *c, const void *i, void *o, int nframes, voi
 
 // ---- host-buffer entry points ---------------------------------------------------------------
 
+// ---- pipelined host-buffer paths ---------------------------------------------------------------
+// dct3d_encode_u8 / dct3d_decode_u8 move a clip as a pipeline of slab-range chunks (about 32 MB of pixels each): the
+// H2D copy of chunk i+1 runs beside the kernels of chunk i and beside the D2H copy of what chunk i-1 produced, on three
+// streams.  The chunks of one call still form ONE stream: the bit position is chained on the device (Chain above).
+
+static cudaEvent_t pipe_event(dct3d_ctx *ctx, size_t i)
+{
+    while (ctx->pev.size() <= i) {
+        cudaEvent_t e = nullptr;
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        ctx->pev.push_back(e);
+    }
+    return ctx->pev[i];
+}
+
+static int chunk_slabs(const dct3d_ctx *ctx, int nslabs)
+{
+    const size_t slab = (size_t)ctx->W * ctx->H * ctx->C;
+    const size_t k = ctx->chunk_frames ? (size_t)ctx->chunk_frames / ctx->C : (((size_t)32 << 20) + slab - 1) / slab;
+    return (int)std::min<size_t>(std::max<size_t>(k, 1), (size_t)std::max(nslabs, 1));
+}
+
+static void pipe_quiesce(dct3d_ctx *ctx)
+{
+    cudaStreamSynchronize(ctx->s_h2d);
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->s_d2h);
+}
+
+constexpr int kRing = 3;
+
+// Codes host frames into ctx->bits from bit 0.  With `out` the finished bytes flow back to the host beside the following
+// chunks and out[0 .. *nbits/8] is the complete stream; without it the stream stays on the device (dct3d_encode_u8_range).
+static int pipe_encode(dct3d_ctx *ctx, const uint8_t *frames, int nframes, size_t dcap, uint8_t *out, size_t cap, uint64_t *nbits)
+{
+    int rc;
+    const int C = ctx->C, nslabs = nframes / C;
+    const size_t slab_bytes = (size_t)ctx->W * ctx->H * C;
+    cudaStream_t st = ctx->stream;
+    ctx->range_valid = false;
+    CU_CHECK(ctx, ctx->bits.reserve(dcap));
+    const int K = chunk_slabs(ctx, nslabs), nchunks = nslabs ? (nslabs + K - 1) / K : 0;
+    ctx->chunks_last = nchunks;
+    if (nchunks <= 1 || ctx->precision == 64) {
+        // one shot: a single chunk, or the fp64 mode (whose packer is not chained)
+        const size_t n = slab_bytes * nslabs;
+        CU_CHECK(ctx, ctx->ring[0].reserve(n + 16));
+        if (n) H2D(ctx, ctx->ring[0].p, frames, n);
+        uint64_t end = 0;
+        if ((rc = dct3d_encode_u8_dev(ctx, ctx->ring[0].p, nframes, ctx->bits.p, dcap, 0, &end, nullptr))) return rc;
+        if (out) {
+            const size_t nb = (size_t)(end / 8) + 1;
+            if (nb > cap) return fail(ctx, DCT3D_E_OVERFLOW, "stream needs %zu bytes, buffer has %zu", nb, cap);
+            D2H(ctx, out, ctx->bits.p, nb);
+        }
+        SYNC(ctx);
+        *nbits = end;
+        return DCT3D_OK;
+    }
+    // ---- set-up: everything the chunks share is sized for the largest chunk before the first launch, so that no later
+    // reserve() can free a buffer under a running kernel
+    const size_t cubes_chunk = (size_t)K * (ctx->H / C) * (ctx->W / C);
+    for (int b = 0; b < kRing; b++) CU_CHECK(ctx, ctx->ring[b].reserve((size_t)K * slab_bytes + 16));
+    CU_CHECK(ctx, ctx->zz.reserve(cubes_chunk * C * C * C * sizeof(int16_t)));
+    CU_CHECK(ctx, ctx->cmask.reserve(cubes_chunk * 4));
+    CU_CHECK(ctx, ctx->ctrl.reserve(kCtrlBytes + ((cubes_chunk + kPackThreads - 1) / kPackThreads) * 8));
+    const size_t nslots = (size_t)nchunks + 2;                   // bit position before every chunk and after the last; error word
+    CU_CHECK(ctx, ctx->chain.reserve(nslots * 8));
+    if (ctx->h_chain_n < nslots) {
+        if (ctx->h_chain) cudaFreeHost(ctx->h_chain);
+        ctx->h_chain = nullptr; ctx->h_chain_n = 0;
+        CU_CHECK(ctx, cudaMallocHost((void **)&ctx->h_chain, (nslots + 64) * 8));
+        ctx->h_chain_n = nslots + 64;
+    }
+    unsigned long long *d_chain = (unsigned long long *)ctx->chain.p;
+    unsigned int *d_err = (unsigned int *)(d_chain + nchunks + 1);
+    auto ev = [&](int i, int what) { return pipe_event(ctx, (size_t)3 * i + what); };   // 0: chunk on the device, 1: chunk coded, 2: its end bit on the host
+    if (!ev(nchunks - 1, 2)) return fail(ctx, DCT3D_E_CUDA, "cudaEventCreate failed");
+    CU_CHECK(ctx, cudaMemsetAsync(ctx->chain.p, 0, nslots * 8, st));
+    if ((rc = zero_stream(ctx, ctx->bits.p, dcap, 0, st))) return rc;
+
+    size_t sent = 0;
+    auto drain = [&](int j, bool last) -> int {                  // bytes that chunk j completed go home
+        CU_CHECK(ctx, cudaEventSynchronize(ev(j, 2)));
+        const size_t full = (size_t)(ctx->h_chain[j + 1] / 8), give = last ? full + 1 : full;
+        if (give > cap) return fail(ctx, DCT3D_E_OVERFLOW, "stream needs %zu bytes, buffer has %zu", give, cap);
+        if (give > sent) CU_CHECK(ctx, cudaMemcpyAsync(out + sent, (const uint8_t *)ctx->bits.p + sent, give - sent, cudaMemcpyDeviceToHost, ctx->s_d2h));
+        sent = std::max(sent, give);
+        return DCT3D_OK;
+    };
+    auto run = [&]() -> int {
+        for (int i = 0; i < nchunks; i++) {
+            const int s0 = i * K, ns = std::min(K, nslabs - s0), b = i % kRing;
+            if (i >= kRing) CU_CHECK(ctx, cudaStreamWaitEvent(ctx->s_h2d, ev(i - kRing, 1), 0));
+            CU_CHECK(ctx, cudaMemcpyAsync(ctx->ring[b].p, frames + (size_t)s0 * slab_bytes, (size_t)ns * slab_bytes, cudaMemcpyHostToDevice, ctx->s_h2d));
+            CU_CHECK(ctx, cudaEventRecord(ev(i, 0), ctx->s_h2d));
+            CU_CHECK(ctx, cudaStreamWaitEvent(st, ev(i, 0), 0));
+            const Chain ch{d_chain + i, d_chain + i + 1, d_err};
+            if ((rc = encode_common(ctx, ctx->ring[b].p, ns * C, ctx->bits.p, dcap, 0, nullptr, st, nullptr, &ch))) return rc;
+            CU_CHECK(ctx, cudaEventRecord(ev(i, 1), st));
+            CU_CHECK(ctx, cudaStreamWaitEvent(ctx->s_d2h, ev(i, 1), 0));
+            CU_CHECK(ctx, cudaMemcpyAsync(ctx->h_chain + i + 1, d_chain + i + 1, i == nchunks - 1 ? 16 : 8, cudaMemcpyDeviceToHost, ctx->s_d2h));   // the last one brings the error word along
+            CU_CHECK(ctx, cudaEventRecord(ev(i, 2), ctx->s_d2h));
+            if (out && i >= 1 && (rc = drain(i - 1, false))) return rc;
+        }
+        CU_CHECK(ctx, cudaEventSynchronize(ev(nchunks - 1, 2)));
+        const unsigned int err = (unsigned int)ctx->h_chain[nchunks + 1];
+        if (err & 16u) return fail(ctx, DCT3D_E_CUDA, "TMA tile load timed out");
+        if (err & 8u) return fail(ctx, DCT3D_E_CUDA, "tile look-back timed out");
+        if (err & 1u) return fail(ctx, DCT3D_E_OVERFLOW, "stream buffer of %zu bytes is too small", dcap);
+        if (out && (rc = drain(nchunks - 1, true))) return rc;
+        CU_CHECK(ctx, cudaStreamSynchronize(ctx->s_d2h));
+        return DCT3D_OK;
+    };
+    rc = run();
+    if (rc) { pipe_quiesce(ctx); ctx->clean_ptr = nullptr; return rc; }
+    *nbits = ctx->h_chain[nchunks];
+    if (ctx->bits.p == ctx->clean_ptr) ctx->clean_dirty = (size_t)(*nbits / 8) + 1;
+    return DCT3D_OK;
+}
+
+// Decodes `nframes` frames from a host stream whose bit `start_bit` is the first bit of the first cube; the parsed lists
+// cover the whole range, the inverse transform runs chunk by chunk beside the D2H copies of the frames.
+static int pipe_decode(dct3d_ctx *ctx, const uint8_t *stream, size_t nbytes, uint64_t start_bit, int nframes, uint8_t *frames, uint64_t *end_bit)
+{
+    int rc;
+    const int C = ctx->C, nslabs = nframes / C;
+    const size_t slab_bytes = (size_t)ctx->W * ctx->H * C;
+    cudaStream_t st = ctx->stream;
+    ctx->range_valid = false;
+    ctx->clean_ptr = nullptr;                                    // ctx->bits is about to hold foreign bytes
+    const size_t padded = ((nbytes + 3) & ~(size_t)3) + 8;
+    CU_CHECK(ctx, ctx->bits.reserve(padded));
+    CU_CHECK(ctx, cudaMemsetAsync((uint8_t *)ctx->bits.p + (nbytes & ~(size_t)3), 0, padded - (nbytes & ~(size_t)3), st));
+    H2D(ctx, ctx->bits.p, stream, nbytes);
+    const int K = chunk_slabs(ctx, nslabs), nchunks = (nslabs + K - 1) / K;
+    ctx->chunks_last = nchunks;
+    if (nchunks <= 1 || ctx->precision == 64) {
+        const size_t n = slab_bytes * nslabs;
+        CU_CHECK(ctx, ctx->ring[0].reserve(n + 16));
+        if ((rc = dct3d_decode_u8_dev(ctx, ctx->bits.p, nbytes, start_bit, nframes, ctx->ring[0].p, end_bit, nullptr))) return rc;
+        D2H(ctx, frames, ctx->ring[0].p, n);
+        SYNC(ctx);
+        return DCT3D_OK;
+    }
+    for (int b = 0; b < kRing; b++) CU_CHECK(ctx, ctx->ring[b].reserve((size_t)K * slab_bytes + 16));
+    auto ev = [&](int i, int what) { return pipe_event(ctx, (size_t)2 * i + what); };   // 0: chunk reconstructed, 1: chunk on the host
+    if (!ev(nchunks - 1, 1)) return fail(ctx, DCT3D_E_CUDA, "cudaEventCreate failed");
+    const Layout L = make_layout(ctx->W, ctx->H, C, nslabs);
+    if ((rc = parse_common(ctx, ctx->bits.p, nbytes, start_bit, (size_t)L.ncubes, end_bit, st))) return rc;
+    auto run = [&]() -> int {
+        for (int i = 0; i < nchunks; i++) {
+            const int s0 = i * K, ns = std::min(K, nslabs - s0), b = i % kRing;
+            if (i >= kRing) CU_CHECK(ctx, cudaStreamWaitEvent(st, ev(i - kRing, 1), 0));
+            const Layout Lc = make_layout(ctx->W, ctx->H, C, ns);
+            const long long base = (long long)s0 * L.by * L.bx;
+            if ((rc = C == 8 ? launch_reconstruct_coo<8>(ctx, Lc, ctx->ring[b].p, st, base) : launch_reconstruct_coo<4>(ctx, Lc, ctx->ring[b].p, st, base))) return rc;
+            CU_CHECK(ctx, cudaEventRecord(ev(i, 0), st));
+            CU_CHECK(ctx, cudaStreamWaitEvent(ctx->s_d2h, ev(i, 0), 0));
+            CU_CHECK(ctx, cudaMemcpyAsync(frames + (size_t)s0 * slab_bytes, ctx->ring[b].p, (size_t)ns * slab_bytes, cudaMemcpyDeviceToHost, ctx->s_d2h));
+            CU_CHECK(ctx, cudaEventRecord(ev(i, 1), ctx->s_d2h));
+        }
+        CU_CHECK(ctx, cudaStreamSynchronize(ctx->s_d2h));
+        return DCT3D_OK;
+    };
+    rc = run();
+    if (rc) pipe_quiesce(ctx);
+    return rc;
+}
+
 static size_t frame_bytes(const dct3d_ctx *ctx, int nframes) { return (size_t)ctx->W * ctx->H * (size_t)(nframes - nframes % ctx->C); }
 
 int dct3d_encode_u8(dct3d_ctx *ctx, const uint8_t *frames, int nframes, uint8_t *stream, size_t cap,
@@ -912,44 +1137,336 @@ int dct3d_encode_u8(dct3d_ctx *ctx, const uint8_t *frames, int nframes, uint8_t 
     if (rc) return rc;
     if ((rc = check_frames(ctx, nframes))) return rc;
     if (!stream || cap == 0) return fail(ctx, DCT3D_E_INVALID, "null stream buffer");
-    const size_t n = frame_bytes(ctx, nframes);
-    if (n && !frames) return fail(ctx, DCT3D_E_INVALID, "null frame pointer");
+    if (frame_bytes(ctx, nframes) && !frames) return fail(ctx, DCT3D_E_INVALID, "null frame pointer");
     // device stream capacity: the caller's cap, rounded up to words, plus slack
     const size_t dcap = ((cap + 3) & ~(size_t)3) + 64;
-    CU_CHECK(ctx, ctx->frames.reserve(n + 16));
-    CU_CHECK(ctx, ctx->bits.reserve(dcap));
-    if (n) H2D(ctx, ctx->frames.p, frames, n);
     uint64_t end = 0;
-    if ((rc = dct3d_encode_u8_dev(ctx, ctx->frames.p, nframes, ctx->bits.p, dcap, 0, &end, nullptr))) return rc;
-    const size_t nb = (size_t)(end / 8) + 1;
-    if (nb > cap) return fail(ctx, DCT3D_E_OVERFLOW, "stream needs %zu bytes, buffer has %zu", nb, cap);
-    D2H(ctx, stream, ctx->bits.p, nb);
-    SYNC(ctx);
+    if ((rc = pipe_encode(ctx, frames, nframes, dcap, stream, cap, &end))) return rc;
     if (nbits) *nbits = end;
-    if (nbytes) *nbytes = nb;
+    if (nbytes) *nbytes = (size_t)(end / 8) + 1;
     return DCT3D_OK;
 }
 
 int dct3d_decode_u8(dct3d_ctx *ctx, const uint8_t *stream, size_t nbytes, int nframes, uint8_t *frames)
 {
+    return dct3d_decode_u8_range(ctx, stream, nbytes, 0, 0, nframes, frames, nullptr);
+}
+
+int dct3d_decode_u8_range(dct3d_ctx *ctx, const uint8_t *stream, size_t nbytes, uint64_t start_bit, uint64_t end_bit_hint,
+                          int nframes, uint8_t *frames, uint64_t *end_bit)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if ((rc = check_frames(ctx, nframes))) return rc;
+    if (frame_bytes(ctx, nframes) == 0) { if (end_bit) *end_bit = start_bit; return DCT3D_OK; }
+    if (!stream || !frames) return fail(ctx, DCT3D_E_INVALID, "null pointer");
+    const size_t byte0 = (size_t)(start_bit / 8);
+    size_t upto = nbytes;
+    if (end_bit_hint) {
+        if (end_bit_hint < start_bit) return fail(ctx, DCT3D_E_INVALID, "end bit hint before the start bit");
+        upto = std::min<size_t>(nbytes, (size_t)(end_bit_hint / 8) + 1);
+    }
+    if (byte0 >= upto) return fail(ctx, DCT3D_E_STREAM, "Exp-Golomb stream truncated: no data at the start bit");
+    uint64_t end = 0;
+    rc = pipe_decode(ctx, stream + byte0, upto - byte0, start_bit % 8, nframes, frames, &end);
+    if (rc == DCT3D_E_NEED_MORE) return fail(ctx, DCT3D_E_STREAM, "Exp-Golomb stream truncated: %s", ctx->err.c_str());
+    if (rc) return rc;
+    if (end_bit) *end_bit = (uint64_t)byte0 * 8 + end;
+    return DCT3D_OK;
+}
+
+// ---- sharded encode: a slab range per GPU, placed into the clip's one stream -------------------------
+
+int dct3d_encode_u8_range(dct3d_ctx *ctx, const uint8_t *frames, int nframes, uint64_t *nbits)
+{
     int rc = bind(ctx);
     if (rc) return rc;
     if ((rc = check_frames(ctx, nframes))) return rc;
     const size_t n = frame_bytes(ctx, nframes);
-    if (n == 0) return DCT3D_OK;
-    if (!stream || !frames) return fail(ctx, DCT3D_E_INVALID, "null pointer");
-    const size_t padded = ((nbytes + 3) & ~(size_t)3) + 8;
-    CU_CHECK(ctx, ctx->bits.reserve(padded));
-    CU_CHECK(ctx, ctx->frames.reserve(n + 16));
-    CU_CHECK(ctx, cudaMemsetAsync((uint8_t *)ctx->bits.p + (nbytes & ~(size_t)3), 0, padded - (nbytes & ~(size_t)3), ctx->stream));
-    H2D(ctx, ctx->bits.p, stream, nbytes);
+    if (n && !frames) return fail(ctx, DCT3D_E_INVALID, "null frame pointer");
+    // worst case of the codec's own output on u8 input is about 2.6 bytes per sample; start at 1/2 and grow on overflow
+    size_t dcap = std::max<size_t>(ctx->bits.cap > 64 ? ctx->bits.cap - 64 : 0, n / 2 + 4096) & ~(size_t)3;
     uint64_t end = 0;
-    rc = dct3d_decode_u8_dev(ctx, ctx->bits.p, nbytes, 0, nframes, ctx->frames.p, &end, nullptr);
-    if (rc == DCT3D_E_NEED_MORE) return fail(ctx, DCT3D_E_STREAM, "Exp-Golomb stream truncated: %s", ctx->err.c_str());
+    for (;;) {
+        rc = pipe_encode(ctx, frames, nframes, dcap, nullptr, 0, &end);
+        if (rc != DCT3D_E_OVERFLOW || dcap >= 4 * n + 4096) break;
+        dcap = std::min(dcap * 4, 4 * n + 4096) & ~(size_t)3;
+    }
     if (rc) return rc;
-    D2H(ctx, frames, ctx->frames.p, n);
-    SYNC(ctx);
+    ctx->range_bits = end;
+    ctx->range_valid = true;
+    if (nbits) *nbits = end;
     return DCT3D_OK;
+}
+
+int dct3d_stream_shift_dev(dct3d_ctx *ctx, const void *d_src, uint64_t nbits, unsigned phase, void *d_dst, size_t cap, void *cuda_stream)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (!d_src || !d_dst) return fail(ctx, DCT3D_E_INVALID, "null pointer");
+    if (((uintptr_t)d_src | (uintptr_t)d_dst) & 3) return fail(ctx, DCT3D_E_INVALID, "stream buffers must be 4-byte aligned");
+    if (phase > 7) return fail(ctx, DCT3D_E_INVALID, "phase must be 0..7");
+    const unsigned long long src_words = (nbits + 31) / 32, dst_words = (nbits + phase + 31) / 32 + 1;   // + one zero word of slack
+    if ((size_t)dst_words * 4 > cap) return fail(ctx, DCT3D_E_OVERFLOW, "shifted stream needs %llu bytes, buffer has %zu", dst_words * 4, cap);
+    stream_shift_kernel<<<ew_grid(ctx, dst_words), 256, 0, pick(ctx, cuda_stream)>>>((const uint32_t *)d_src, src_words, (uint32_t *)d_dst, dst_words, (int)phase);
+    ctx->launches++;
+    CU_CHECK(ctx, cudaGetLastError());
+    return DCT3D_OK;
+}
+
+int dct3d_encode_u8_place(dct3d_ctx *ctx, uint64_t start_bit, int last, uint8_t *stream, size_t cap, uint8_t *first_byte)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (!ctx->range_valid) return fail(ctx, DCT3D_E_INVALID, "no coded range to place (call dct3d_encode_u8_range first)");
+    if (!stream) return fail(ctx, DCT3D_E_INVALID, "null stream buffer");
+    if (first_byte) *first_byte = 0;
+    const unsigned phase = (unsigned)(start_bit % 8);
+    const size_t byte0 = (size_t)(start_bit / 8);
+    const uint64_t n = ctx->range_bits, endp = phase + n;        // bits of the placed range, counted from byte0
+    if (n == 0) {                                                // an empty range owns no byte, except the stream's closing one
+        if (last && phase == 0) { if (byte0 >= cap) return fail(ctx, DCT3D_E_OVERFLOW, "stream buffer too small"); stream[byte0] = 0; }
+        return DCT3D_OK;
+    }
+    const uint8_t *src = (const uint8_t *)ctx->bits.p;
+    if (phase) {
+        const size_t need = (size_t)((endp + 31) / 32 + 1) * 4;
+        CU_CHECK(ctx, ctx->bits2.reserve(need));
+        if ((rc = dct3d_stream_shift_dev(ctx, ctx->bits.p, n, phase, ctx->bits2.p, ctx->bits2.cap, nullptr))) return rc;
+        src = (const uint8_t *)ctx->bits2.p;
+    }
+    // bytes first..lastb of the placed range go straight to their place; the first one is shared with the predecessor
+    // when phase != 0 and is handed to the caller instead; the byte after the last bit is written only if the range has
+    // bits in it or closes the stream (otherwise it belongs to the successor, which starts there at phase 0)
+    const size_t first = phase ? 1 : 0;
+    const size_t lastb = (endp % 8 != 0 || last) ? (size_t)(endp / 8) : (size_t)(endp / 8) - 1;
+    if (byte0 + lastb + 1 > cap) return fail(ctx, DCT3D_E_OVERFLOW, "stream needs %zu bytes, buffer has %zu", byte0 + lastb + 1, cap);
+    if (lastb >= first) D2H(ctx, stream + byte0 + first, src + first, lastb - first + 1);
+    if (phase) D2H(ctx, ctx->h_byte, src, 1);
+    SYNC(ctx);
+    if (phase) {
+        if (!first_byte) return fail(ctx, DCT3D_E_INVALID, "the range starts inside a byte: first_byte must not be null");
+        *first_byte = ctx->h_byte[0];
+    }
+    return DCT3D_OK;
+}
+
+int dct3d_host_register(void *p, size_t bytes)
+{
+    if (!p || !bytes) return fail(nullptr, DCT3D_E_INVALID, "null buffer");
+    cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(nullptr, DCT3D_E_CUDA, "cudaHostRegister failed: %s", cudaGetErrorString(e)); }
+    return DCT3D_OK;
+}
+
+int dct3d_host_unregister(void *p)
+{
+    if (p && cudaHostUnregister(p) != cudaSuccess) { cudaGetLastError(); return fail(nullptr, DCT3D_E_CUDA, "cudaHostUnregister failed"); }
+    return DCT3D_OK;
+}
+
+// ---- several GPUs in one process: contiguous slab ranges, one host thread per GPU ----------------------------------
+// Every slab is an independent key-frame group (reference README.md:10, slab loop C/encoder.c:203-278); the only coupling
+// is the stream's bit position.  GPU g codes slabs [g n/G, (g+1) n/G) from bit 0 of its own buffer, the G bit counts are
+// prefix-summed on the host, and every GPU moves its bits to its phase and copies them to their place in the caller's
+// one stream; the host ORs the G-1 shared boundary bytes.  No collective.
+
+struct dct3d_multi {
+    std::vector<dct3d_ctx *> ctx;
+    int W = 0, H = 0, C = 8;
+    std::string err;
+};
+
+namespace {
+
+int mfail(dct3d_multi *m, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    if (m) m->err = buf;
+    return code;
+}
+
+class HostBarrier {
+    std::mutex mu;
+    std::condition_variable cv;
+    int n, waiting = 0;
+    unsigned long gen = 0;
+public:
+    explicit HostBarrier(int count) : n(count) {}
+    void wait()
+    {
+        std::unique_lock<std::mutex> lk(mu);
+        const unsigned long g = gen;
+        if (++waiting == n) { waiting = 0; gen++; cv.notify_all(); }
+        else cv.wait(lk, [&] { return gen != g; });
+    }
+};
+
+void slab_range(int nslabs, int g, int G, int &lo, int &hi)
+{
+    lo = (int)((long long)g * nslabs / G);
+    hi = (int)((long long)(g + 1) * nslabs / G);
+}
+
+// first failure of the per-GPU calls, with the failing context's message
+int first_failure(dct3d_multi *m, const std::vector<int> &rcs)
+{
+    for (size_t g = 0; g < rcs.size(); g++)
+        if (rcs[g]) return mfail(m, rcs[g], "GPU %d: %s", m->ctx[g]->device, m->ctx[g]->err.c_str());
+    return DCT3D_OK;
+}
+
+}  // namespace
+
+int dct3d_multi_create(dct3d_multi **out, const int *devices, int ndevices, int width, int height, int cube)
+{
+    if (!out) return mfail(nullptr, DCT3D_E_INVALID, "null output pointer");
+    *out = nullptr;
+    if (ndevices <= 0 || ndevices > 64) return mfail(nullptr, DCT3D_E_INVALID, "device count %d out of range", ndevices);
+    dct3d_multi *m = new dct3d_multi();
+    m->W = width; m->H = height; m->C = cube;
+    for (int i = 0; i < ndevices; i++) {
+        dct3d_ctx *c = nullptr;
+        const int rc = dct3d_create(&c, devices ? devices[i] : i, width, height, cube);
+        if (rc) { const std::string keep = g_last_error; dct3d_multi_destroy(m); g_last_error = keep; return rc; }
+        m->ctx.push_back(c);
+    }
+    *out = m;
+    return DCT3D_OK;
+}
+
+void dct3d_multi_destroy(dct3d_multi *m)
+{
+    if (!m) return;
+    for (dct3d_ctx *c : m->ctx) dct3d_destroy(c);
+    delete m;
+}
+
+const char *dct3d_multi_last_error(const dct3d_multi *m) { return m ? m->err.c_str() : g_last_error.c_str(); }
+
+int dct3d_multi_set_option(dct3d_multi *m, const char *key, long value)
+{
+    if (!m) return mfail(nullptr, DCT3D_E_INVALID, "null context");
+    for (dct3d_ctx *c : m->ctx) {
+        const int rc = dct3d_set_option(c, key, value);
+        if (rc) return mfail(m, rc, "%s", c->err.c_str());
+    }
+    return DCT3D_OK;
+}
+
+dct3d_ctx *dct3d_multi_context(dct3d_multi *m, int index)
+{
+    return (m && index >= 0 && index < (int)m->ctx.size()) ? m->ctx[index] : nullptr;
+}
+
+int dct3d_multi_encode_u8(dct3d_multi *m, const uint8_t *frames, int nframes, uint8_t *stream, size_t cap,
+                          uint64_t *nbits, size_t *nbytes, uint64_t *range_start_bits)
+{
+    if (!m) return mfail(nullptr, DCT3D_E_INVALID, "null context");
+    if (nframes < 0) return mfail(m, DCT3D_E_INVALID, "negative frame count");
+    if (!stream || cap == 0) return mfail(m, DCT3D_E_INVALID, "null stream buffer");
+    const int G = (int)m->ctx.size(), C = m->C, nslabs = nframes / C;
+    const size_t slab_bytes = (size_t)m->W * m->H * C;
+    if (nslabs && !frames) return mfail(m, DCT3D_E_INVALID, "null frame pointer");
+    if (G == 1) {                                                // one GPU: its finished bytes stream home beside the coding
+        uint64_t nb = 0;
+        const int rc = dct3d_encode_u8(m->ctx[0], frames, nframes, stream, cap, &nb, nbytes);
+        if (rc) return mfail(m, rc, "%s", m->ctx[0]->err.c_str());
+        if (nbits) *nbits = nb;
+        if (range_start_bits) { range_start_bits[0] = 0; range_start_bits[1] = nb; }
+        return DCT3D_OK;
+    }
+    std::vector<uint64_t> bits(G, 0), start(G + 1, 0);
+    std::vector<int> rcs(G, 0);
+    std::vector<uint8_t> fb(G, 0);
+    HostBarrier bar(G);
+    auto work = [&](int g) {
+        int lo, hi;
+        slab_range(nslabs, g, G, lo, hi);
+        rcs[g] = dct3d_encode_u8_range(m->ctx[g], frames + (size_t)lo * slab_bytes, (hi - lo) * C, &bits[g]);
+        bar.wait();                                              // every GPU's bit count is known
+        for (int j = 0; j < G; j++) if (rcs[j]) return;
+        uint64_t b = 0;
+        for (int j = 0; j < g; j++) b += bits[j];
+        rcs[g] = dct3d_encode_u8_place(m->ctx[g], b, g == G - 1, stream, cap, &fb[g]);
+    };
+    std::vector<std::thread> th;
+    for (int g = 1; g < G; g++) th.emplace_back(work, g);
+    work(0);
+    for (auto &t : th) t.join();
+    int rc = first_failure(m, rcs);
+    if (rc) return rc;
+    for (int g = 0; g < G; g++) start[g + 1] = start[g] + bits[g];
+    for (int g = 1; g < G; g++)                                  // the byte a range shares with its predecessor
+        if (start[g] % 8) stream[start[g] / 8] |= fb[g];
+    if (nbits) *nbits = start[G];
+    if (nbytes) *nbytes = (size_t)(start[G] / 8) + 1;
+    if (range_start_bits) for (int g = 0; g <= G; g++) range_start_bits[g] = start[g];
+    return DCT3D_OK;
+}
+
+int dct3d_multi_locate(dct3d_multi *m, const uint8_t *stream, size_t nbytes, int nframes, uint64_t *range_start_bits)
+{
+    if (!m || !range_start_bits) return mfail(m, DCT3D_E_INVALID, "null argument");
+    const int G = (int)m->ctx.size(), C = m->C, nslabs = nframes / C;
+    const size_t cubes_per_slab = (size_t)(m->W / C) * (m->H / C);
+    std::vector<int> rcs(G, 0);
+    std::vector<uint64_t> sb(G + 1, 0);
+    // every GPU g > 0 finds the first bit of its own range: index discovery over the stream in front of it
+    auto work = [&](int g) {
+        int lo, hi;
+        slab_range(nslabs, g, G, lo, hi);
+        if (lo == 0) { sb[g] = 0; return; }
+        rcs[g] = dct3d_eg_locate(m->ctx[g], stream, nbytes, 0, (size_t)lo * cubes_per_slab, &sb[g]);
+    };
+    std::vector<std::thread> th;
+    for (int g = 2; g < G; g++) th.emplace_back(work, g);
+    if (G > 1) work(1);
+    for (auto &t : th) t.join();
+    int rc = first_failure(m, rcs);
+    if (rc) return rc;
+    sb[G] = 0;                                                   // unknown: the last range ends where the clip ends
+    for (int g = 0; g <= G; g++) range_start_bits[g] = sb[g];
+    return DCT3D_OK;
+}
+
+int dct3d_multi_decode_u8(dct3d_multi *m, const uint8_t *stream, size_t nbytes, int nframes, uint8_t *frames,
+                          const uint64_t *range_start_bits)
+{
+    if (!m) return mfail(nullptr, DCT3D_E_INVALID, "null context");
+    if (nframes < 0) return mfail(m, DCT3D_E_INVALID, "negative frame count");
+    const int G = (int)m->ctx.size(), C = m->C, nslabs = nframes / C;
+    if (nslabs == 0) return DCT3D_OK;
+    if (!stream || !frames) return mfail(m, DCT3D_E_INVALID, "null pointer");
+    const size_t slab_bytes = (size_t)m->W * m->H * C;
+    std::vector<uint64_t> sb(G + 1, 0);
+    if (range_start_bits) {
+        for (int g = 0; g <= G; g++) sb[g] = range_start_bits[g];
+    } else if (G > 1) {
+        const int rc = dct3d_multi_locate(m, stream, nbytes, nframes, sb.data());
+        if (rc) return rc;
+    }
+    std::vector<int> rcs(G, 0);
+    auto work = [&](int g) {
+        int lo, hi;
+        slab_range(nslabs, g, G, lo, hi);
+        if (hi == lo) return;
+        // the range's last bit when known (the next non-empty range's first): bounds the H2D copy of the stream
+        uint64_t hint = 0;
+        for (int j = g + 1; j <= G && !hint; j++) hint = sb[j];
+        rcs[g] = dct3d_decode_u8_range(m->ctx[g], stream, nbytes, sb[g], hint > sb[g] ? hint : 0, (hi - lo) * C,
+                                       frames + (size_t)lo * slab_bytes, nullptr);
+    };
+    std::vector<std::thread> th;
+    for (int g = 1; g < G; g++) th.emplace_back(work, g);
+    work(0);
+    for (auto &t : th) t.join();
+    return first_failure(m, rcs);
 }
 
 int dct3d_stream_begin(dct3d_ctx *ctx)

@@ -66,6 +66,8 @@ struct EncParams {
     uint32_t *out_words;            // stream as 32-bit words (memory byte order)
     unsigned long long cap_bits;    // capacity of out_words in bits
     unsigned long long start_bit;
+    const unsigned long long *start_bit_dev;   // when set, the start bit is read from device memory instead (written by the
+                                               // previous call's packer: slab ranges chained without a host round trip)
     unsigned long long *tile_status;  // [ntiles], zeroed: flag<<62 | inclusive bit count
     unsigned int *ticket;             // zeroed
     unsigned int *err;                // zeroed; bit0 = overflow
@@ -649,6 +651,7 @@ eg_pack_kernel(const EncParams P)
     __shared__ long long s_tile;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long ntiles = (P.L.ncubes + kPackThreads - 1) / kPackThreads;
+    const unsigned long long start_bit = P.start_bit_dev ? *P.start_bit_dev : P.start_bit;
     for (;;) {
         if (tid == 0) s_tile = (long long)atomicAdd(P.ticket, 1u);
         __syncthreads();
@@ -677,7 +680,7 @@ eg_pack_kernel(const EncParams P)
             }
             if (lane < kPackThreads / 32) s_wsum[lane] = wi - w;          // exclusive warp offsets
             const uint32_t total = __shfl_sync(0xffffffffu, wi, 31);
-            const unsigned long long off = tile_lookback(P.tile_status, tile, total, P.start_bit, lane, P.err);
+            const unsigned long long off = tile_lookback(P.tile_status, tile, total, start_bit, lane, P.err);
             if (lane == 0) {
                 s_off = off;
                 if (tile == ntiles - 1) *P.end_bit = off + total;
@@ -694,6 +697,23 @@ eg_pack_kernel(const EncParams P)
             }
         }
         __syncthreads();                        // s_tile / s_wsum / s_off are reused
+    }
+}
+
+// Placement of a slab range's stream inside the clip's one stream (the rule of ExpGolomb.c:112-130 with
+// encoder.c:263-271): a GPU codes its range from bit 0 of its own buffer; once the bit counts of the ranges before it are
+// known, its bits move to phase = (global start bit) % 8, so that the host only has to copy whole bytes to byte
+// (global start bit) / 8 and OR the one byte the range shares with its predecessor.  dst bit (phase + i) = src bit i;
+// the first `phase` bits of dst are zero.  src must be zero beyond its last bit (it is: the packer's buffer is wiped).
+__global__ void __launch_bounds__(256)
+stream_shift_kernel(const uint32_t *__restrict__ src, unsigned long long src_words, uint32_t *__restrict__ dst,
+                    unsigned long long dst_words, int phase)
+{
+    for (unsigned long long j = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; j < dst_words;
+         j += gridDim.x * (unsigned long long)blockDim.x) {
+        const uint32_t cur = j < src_words ? bswap32(__ldg(src + j)) : 0u;
+        const uint32_t prev = (j > 0 && j - 1 < src_words) ? bswap32(__ldg(src + j - 1)) : 0u;
+        dst[j] = bswap32(__funnelshift_r(cur, prev, phase));      // (prev:cur) >> phase, low word
     }
 }
 
@@ -805,7 +825,7 @@ struct DecParams {
     unsigned long long *seg_first;      // [nseg+1] exclusive prefix of the code counts
     unsigned long long *seg_nzfirst;    // [nseg+1] exclusive prefix of the non-zero code counts
     unsigned int *changed;              // number of the last fix-up round that moved an overhang
-    unsigned int *err;                  // bit1 = malformed, bit2 = truncated
+    unsigned int *err;                  // bit1 = malformed (a truncated stream shows as too few codes: DCT3D_E_NEED_MORE)
     unsigned long long *end_bit;        // out: first bit after the last code
     uint32_t *coo;                      // non-zero coefficients of the whole stream, in stream order: natural index << 16 | value
     unsigned long long *coo_start;      // [ncubes+1] first entry of every cube (CSR row pointers)
@@ -1133,9 +1153,12 @@ struct CooSmem {
 
 template <int C>
 __global__ void __launch_bounds__(kThreads, 4)
-reconstruct_coo_kernel(const Layout L, const uint32_t *__restrict__ coo, const unsigned long long *__restrict__ coo_start,
-                       uint8_t *__restrict__ frames)
+reconstruct_coo_kernel(const Layout L, const uint32_t *__restrict__ coo, const unsigned long long *__restrict__ coo_start_all,
+                       uint8_t *__restrict__ frames, const long long cube_base)
 {
+    // cube_base: the launch reconstructs cubes [cube_base, cube_base + L.ncubes) of the parsed stream into a frame buffer
+    // that starts at the first of them (a whole number of slabs): the pipelined decoder's chunks
+    const unsigned long long *__restrict__ coo_start = coo_start_all + cube_base;
     using G = Geo<C>;
     using S = CooSmem<C>;
     constexpr int PRE = 3;                                          // prefetched entries per lane

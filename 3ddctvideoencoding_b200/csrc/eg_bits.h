@@ -91,6 +91,11 @@ EG_HD void load_chunk(const int16_t *zz, int c, uint32_t (&w)[8])
     w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
 }
 
+// The largest code number an int16 coefficient maps to: v = -32768 -> m = 65537, the only 33-bit code.
+// (m = 65536 would be v = +32768, every other 17-bit m lies beyond int16: such streams are malformed here;
+// the reference reads them as full ints, ExpGolombReader.java:19-63.)
+constexpr uint32_t kEgMaxCode = 65537u;
+
 // v -> m (>= 1).  v > 0: 2v ; v <= 0: 1 - 2v.
 EG_HD uint32_t eg_map(int v) { const int t = 2 * v; return (uint32_t)(v > 0 ? t : 1 - t); }
 // m -> v
@@ -258,6 +263,7 @@ struct BitReader {
         } else {                          // 33 bits: 16 zeros, a one, 16 more bits
             refill();                     // navail may be exactly 32 here
             m = (hi << 1) | (lo >> 31);
+            if (m != kEgMaxCode) return false;   // the only 17-bit code number an int16 cube can hold (v = -32768)
             skip(32);
             skip(1);
         }
@@ -340,15 +346,18 @@ EG_HD bool eg_scan_segment(const Source &src, uint32_t start, uint32_t limit, ui
             if (pos + 17 >= end_of_stream || (uint32_t)z + pos >= end_of_stream) { if (pos < limit) pos = limit; break; }
             return false;
         }
+        // a code that runs past the end of the stream is not a code yet: the caller sees fewer codes than it
+        // needs (DCT3D_E_NEED_MORE / truncated) instead of a value read from the zero padding
+        const uint32_t len = z < 16 ? 2u * (uint32_t)z + 1u : 33u;
+        if (pos + len > end_of_stream) { pos = limit; break; }
         uint32_t m;
         if (z < 16) {
-            const int len = 2 * z + 1;
             m = w >> (32 - len);
-            pos += (uint32_t)len;
         } else {                                                // 33 bits: 16 zeros, then m in 17 bits
             m = eg_fetch32(src, pos + 16) >> 15;
-            pos += 33;
+            if (m != kEgMaxCode) return false;                  // would not fit the codec's int16 cubes
         }
+        pos += len;
         sink.push(nz, (n << 17) | m);
         n++;
         nz++;

@@ -11,6 +11,8 @@ placed at byte B_g/8 shifted right by B_g%8 bits, OR-ing the shared boundary byt
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 
@@ -53,6 +55,89 @@ def concatenate(parts, nbits_per_rank) -> tuple[np.ndarray, int]:
     return out, total
 
 
+def shift_to_phase(part: np.ndarray, nbits: int, phase: int) -> np.ndarray:
+    """Host model of stream_shift_kernel: bit (phase + i) of the result = bit i of `part`, the first `phase` bits
+    zero; (phase + nbits) // 8 + 1 bytes."""
+    out = np.zeros((phase + nbits) // 8 + 1, np.uint8)
+    place(out, np.asarray(part, np.uint8), nbits, phase)
+    return out
+
+
+def place_shifted(dst: np.ndarray, shifted: np.ndarray, start_bit: int, nbits: int, last: bool) -> int:
+    """Host model of dct3d_encode_u8_place: whole bytes of a range already at phase start_bit % 8 are COPIED (not
+    OR-ed) to byte start_bit // 8 onwards.  The first byte is skipped and returned when the range starts inside a byte
+    (the caller ORs it in once the predecessor's bytes have landed); the byte after the last bit is written only when
+    the range has bits in it or closes the stream."""
+    phase, byte0 = start_bit % 8, start_bit // 8
+    if nbits == 0:
+        if last and phase == 0:
+            dst[byte0] = 0
+        return 0
+    endp = phase + nbits
+    first = 1 if phase else 0
+    lastb = endp // 8 if (endp % 8 or last) else endp // 8 - 1
+    if lastb >= first:
+        dst[byte0 + first:byte0 + lastb + 1] = shifted[first:lastb + 1]
+    return int(shifted[0]) if phase else 0
+
+
+def concatenate_two_phase(parts, nbits_per_rank) -> tuple[np.ndarray, int]:
+    """The placement the GPUs perform: shift every part to its phase, copy whole bytes, OR the shared
+    boundary bytes afterwards.  The destination starts as garbage to show that every byte is written exactly once."""
+    offs = bit_offsets(nbits_per_rank)
+    total = offs[-1]
+    out = np.full(total // 8 + 1, 0xA5, np.uint8)
+    n = len(parts)
+    firsts = []
+    for g, (part, nb) in enumerate(zip(parts, nbits_per_rank)):
+        sh = shift_to_phase(np.asarray(part, np.uint8), int(nb), offs[g] % 8)
+        firsts.append(place_shifted(out, sh, offs[g], int(nb), g == n - 1))
+    for g in range(1, n):
+        if offs[g] % 8:
+            out[offs[g] // 8] |= firsts[g]
+    return out, total
+
+
+class SharedStream:
+    """The clip's one stream as a shared-memory mapping that every rank (process) places its range into."""
+
+    def __init__(self, name: str, nbytes: int, create: bool):
+        import mmap
+        self.path = os.path.join("/dev/shm", name)
+        flags = os.O_RDWR | (os.O_CREAT if create else 0)
+        fd = os.open(self.path, flags, 0o600)
+        try:
+            if create:
+                os.ftruncate(fd, nbytes)
+            self.mm = mmap.mmap(fd, nbytes)
+        finally:
+            os.close(fd)
+        self.array = np.frombuffer(self.mm, np.uint8)
+        self.nbytes = nbytes
+
+    def unlink(self):
+        try:
+            os.unlink(self.path)
+        except OSError:
+            pass
+
+
+def sharded_encode(codec, frames, shared: np.ndarray, rank: int, world: int, group=None):
+    """One rank's part of a multi-process encode: phase 1 on the GPU, all_gather of the bit counts, phase 2 straight
+    into the shared stream, then the boundary byte.  Returns the exclusive prefix of the bit counts (world + 1)."""
+    import torch.distributed as dist
+    nbits = codec.encode_u8_range(frames)
+    counts = gather_bit_counts(nbits, group) if world > 1 else [nbits]
+    offs = bit_offsets(counts)
+    fb = codec.encode_u8_place(offs[rank], rank == world - 1, shared, shared.size if isinstance(shared, np.ndarray) else shared.numel())
+    if world > 1:
+        dist.barrier(group)                 # the predecessor's bytes have landed
+        if offs[rank] % 8:
+            shared[offs[rank] // 8] |= fb
+        dist.barrier(group)
+    return offs
+
+
 def gather_bit_counts(nbits: int, group=None) -> list[int]:
     """All ranks learn every rank's bit count (torch.distributed; eight scalars at most)."""
     import torch
@@ -76,7 +161,6 @@ def decode_range(codec, stream, nslabs: int, rank: int, world: int, cubes_per_sl
     if hi == lo:
         return np.zeros((0, codec.height, codec.width), np.uint8), 0
     start = int(start_bits[rank]) if start_bits is not None else codec.eg_locate(stream, lo * cubes_per_slab)
-    s = np.ascontiguousarray(stream, np.uint8)
-    byte0 = start // 8                     # the library takes a bit offset below 8 plus whole bytes
-    q, _ = codec.eg_decode_i16(s[byte0:], (hi - lo) * cubes_per_slab, start % 8)
-    return codec.reconstruct_i16(q, (hi - lo) * codec.cube), start
+    hint = int(start_bits[rank + 1]) if start_bits is not None and len(start_bits) > rank + 1 else 0
+    frames, _ = codec.decode_u8_range(stream, start, (hi - lo) * codec.cube, hint)
+    return frames, start

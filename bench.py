@@ -1,21 +1,32 @@
 #!/usr/bin/env python
-"""bench.py -- 1080p grayscale encode+decode throughput of the 3D-DCT codec hot path.
+"""bench.py -- encode+decode throughput of the 3D-DCT codec hot path (BASELINE.json metric).
 
-    python bench.py --gpus N --steps K --warmup W            # our CUDA path (libdct3d.so)
-    python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port)
+    python bench.py --gpus N --steps K --warmup W [--config c1|c2|c3|c4|c5]   # our CUDA path (libdct3d.so)
+    python bench.py --impl reference --steps K --warmup W                     # the reference's CPU path (oracle port)
 
-One step = one pass of the hot path (u8 frames -> Exp-Golomb stream -> u8 frames) over
-BASELINE.json configs[1]: 1920x1080 grayscale, 256 frames, 8x8x8 cubes, synthetic "natural"
-clip (SURVEY.md 8d generator).  `value` is whole-job frames/s with the frames resident in HBM
-(CUDA events on the launching stream, max over ranks); `e2e` is the same metric through the
-host-buffer C ABI (dct3d_encode_u8 / dct3d_decode_u8) with pinned host memory, H2D/D2H inside the
-timed region.  Multi-GPU: one process per GPU (torchrun), each rank codes its own 256-frame slab
-range (slabs are independent key-frame groups), no data-path collective -> weak scaling.
+One step = one pass of the hot path (u8 frames -> Exp-Golomb stream -> u8 frames) over the configuration's clip:
+
+    c2 (default) 1920x1080 gray, 256 frames PER GPU, 8x8x8 cubes   BASELINE configs[1]; weak scaling over N
+    c1           640x480, 64 frames                                 configs[0], the reference's own CPU-runnable case
+    c3           3840x2160, 1024 frames, sharded over the N GPUs    configs[2]; strong scaling
+    c4           c2 with 4x4x4 cubes                                configs[3]
+    c5           1920x1080, 4096 frames, sharded over the N GPUs    configs[4]; strong scaling
+
+With N > 1 (torchrun, one process per GPU) the ranks code ONE clip: rank g owns the contiguous slab range g of it
+(slabs are independent key-frame groups), codes it from bit 0, the N bit counts are all-gathered and prefix-summed, and
+every rank moves its bits to its phase of the clip's ONE stream (stream_shift_kernel) and decodes its range from that
+global bit position.  No data-path collective.  `value` is whole-job frames/s with the frames resident in HBM (CUDA
+events on the launching stream, max over ranks; the all_gather of the N scalars and the shift are inside the timed
+region); `e2e` is the same through the host-buffer C ABI with pinned host memory, H2D/D2H inside the timed region: the
+ranks place their ranges straight into one shared-memory stream (dct3d_encode_u8_range / _place) and decode their
+ranges from it (dct3d_decode_u8_range); at N = 1 these are dct3d_encode_u8 / dct3d_decode_u8.  The SHA-256 of that
+stream is printed: it is the same for every N of a strong-scaling configuration.
 """
 from __future__ import annotations
 
 import argparse
 import ctypes as C
+import hashlib
 import importlib
 import json
 import os
@@ -30,8 +41,20 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 PKG = "3ddctvideoencoding_b200"
-METRIC = "1080p gray encode+decode frames/s"
 UNIT = "frames/s"
+
+CONFIGS = {
+    #      W     H     frames cube  scaling   BASELINE.json configs[] index
+    "c1": (640, 480, 64, 8, "strong", 0),
+    "c2": (1920, 1080, 256, 8, "weak", 1),
+    "c3": (3840, 2160, 1024, 8, "strong", 2),
+    "c4": (1920, 1080, 256, 4, "weak", 3),
+    "c5": (1920, 1080, 4096, 8, "strong", 4),
+}
+
+
+def metric_name(W, H):
+    return "1080p gray encode+decode frames/s" if (W, H) == (1920, 1080) else f"{W}x{H} gray encode+decode frames/s"
 
 
 def peaks():
@@ -40,6 +63,19 @@ def peaks():
         d = json.load(open(p))
         return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(kernel: str):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/traffic.json, written by
+    profiles/summarize.py from the --set full export); None when no capture of that kernel is committed."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None, None
+    d = json.load(open(p))
+    for k, v in d.get("kernels", {}).items():
+        if kernel.startswith(k):
+            return float(v["dram_bytes"]), d.get("source")
+    return None, d.get("source")
 
 
 class ClockSampler:
@@ -77,41 +113,54 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def synth_clip_torch(W, H, F, seed, device):
-    """The SURVEY.md 8d 'natural' generator, evaluated on the GPU (same formula, torch RNG)."""
+def synth_slabs_torch(W, H, cube, slab_lo, slab_hi, seed, device, kind="natural", out=None):
+    """The SURVEY.md 8d 'natural' generator on the GPU, seeded PER SLAB: any rank regenerates any slab of the clip
+    bit for bit, so the clip (and its stream) does not depend on how many ranks share it."""
     import torch
-    g = torch.Generator(device=device)
-    g.manual_seed(seed)
-    t = torch.arange(F, device=device, dtype=torch.float32)[:, None, None]
+    n = slab_hi - slab_lo
+    if out is None:
+        out = torch.empty((n * cube, H, W), dtype=torch.uint8, device=device)
     y = torch.arange(H, device=device, dtype=torch.float32)[None, :, None]
     x = torch.arange(W, device=device, dtype=torch.float32)[None, None, :]
-    out = torch.empty((F, H, W), dtype=torch.uint8, device=device)
-    step = 32
-    for f0 in range(0, F, step):
-        tt = t[f0:f0 + step]
-        v = 128.0 + 60.0 * torch.sin((x + 3.0 * tt) / 37.0) + 50.0 * torch.cos((y - 2.0 * tt) / 23.0)
+    g = torch.Generator(device=device)
+    for s in range(slab_lo, slab_hi):
+        g.manual_seed(seed * 1000003 + s)
+        o = out[(s - slab_lo) * cube:(s - slab_lo + 1) * cube]
+        if kind == "noise":
+            o.copy_(torch.randint(0, 256, o.shape, generator=g, device=device, dtype=torch.uint8))
+            continue
+        t = torch.arange(s * cube, (s + 1) * cube, device=device, dtype=torch.float32)[:, None, None]
+        v = 128.0 + 60.0 * torch.sin((x + 3.0 * t) / 37.0) + 50.0 * torch.cos((y - 2.0 * t) / 23.0)
         v = v + 6.0 * torch.randn(v.shape, generator=g, device=device)
-        out[f0:f0 + step] = v.round().clamp(0, 255).to(torch.uint8)
+        o.copy_(v.round().clamp(0, 255).to(torch.uint8))
     return out
 
 
-def cpu_baseline_sample(W, H, frames, threads):
-    """Times the oracle's Java-structured port (oracle/dct3d_oracle.c) on `frames` frames."""
+# ---------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's Java algorithm (the one place bench.py executes oracle/)
+# ---------------------------------------------------------------------------------------------------------
+def cpu_piece(clip, cube, threads):
+    """Times the oracle's Java-structured port (oracle/dct3d_oracle.c) on `clip`; returns (t_enc, t_dec, stream, frames)."""
     from oracle import oracle as O
-    synth = importlib.import_module(PKG + ".synth")
-    clip = synth.natural(W, H, frames, 1)
+    F, H, W = clip.shape
     t0 = time.perf_counter()
-    stream, bits = O.java_encode_u8(clip, 8, threads)
+    stream, bits = O.java_encode_u8(clip, cube, threads)
     t1 = time.perf_counter()
-    O.java_decode_u8(stream, W, H, frames, 8, threads)
+    dec = O.java_decode_u8(stream, W, H, F, cube, threads)
     t2 = time.perf_counter()
-    return frames / (t2 - t0), t1 - t0, t2 - t1, bits
+    return t1 - t0, t2 - t1, stream, dec
+
+
+def sample_slabs(nslabs: int, want: int = 4):
+    """First, two in the middle, last (at least 4 slabs of the headline configuration)."""
+    if nslabs <= want:
+        return list(range(nslabs))
+    return sorted({0, nslabs // 3, (2 * nslabs) // 3, nslabs - 1})
 
 
 def ref_c_host_sample(W, H):
     """Times the reference's own C host code (encoder.c / decoder.c / ExpGolomb.c / CubeUtils.c compiled unmodified
     into oracle/_ref/codec_ref, its four OpenCL kernels executed by the CPU shim oracle/ref_shim.c) on one slab."""
-    import subprocess
     import tempfile
     exe = os.path.join(ROOT, "oracle", "_ref", "codec_ref")
     if not os.path.exists(exe):
@@ -139,34 +188,86 @@ def run_reference(args):
         return 0
     from oracle import oracle as O
     O.build()
+    synth = importlib.import_module(PKG + ".synth")
     cores = os.cpu_count() or 1
-    W, H = args.width, args.height
-    sample = 8
+    W, H, F, cube, scaling, idx = config_of(args)
+    # a bounded sample of the workload per step: SAMPLE slabs spread over the clip (slabs are independent, the whole clip
+    # scales linearly); config c1 is small enough to run in full
+    nslabs = F // cube
+    slabs = list(range(nslabs)) if args.config == "c1" else sample_slabs(nslabs, args.ref_slabs)
+    pieces = [slab_numpy(W, H, cube, s, 1) for s in slabs]   # the clip is seeded per slab: any slab can be made alone
     vals = []
     for i in range(args.warmup + args.steps):
-        fps, te, td, _ = cpu_baseline_sample(W, H, sample, cores)
+        te = td = 0.0
+        for p in pieces:
+            a, b, _, _ = cpu_piece(p, cube, cores)
+            te += a
+            td += b
         if i >= args.warmup:
-            vals.append((fps, te, td))
-    fps = float(np.mean([v[0] for v in vals]))
+            vals.append((te, td))
+    te = float(np.mean([v[0] for v in vals]))
+    td = float(np.mean([v[1] for v in vals]))
+    frames = len(slabs) * cube
+    fps = frames / (te + td)
     line = {
-        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * sample / fps, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": metric_name(W, H), "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * (te + td), "higher_is_better": True, "scaling": scaling,
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{W}x{H} gray, 256 frames, 8x8x8 cubes (BASELINE configs[1])", "cube": 8,
-                   "note": "no JVM in the image: the Java Encoder/Decoder is timed as the oracle's C restatement of its "
-                           "algorithm (grouped-coefficient DCT on all cores, single-threaded quantise/Exp-Golomb)"},
+        "config": workload_config(args, max(1, args.gpus)),
+        "note": "no JVM in the image: the Java Encoder/Decoder is timed as the oracle's C restatement of its "
+                "algorithm (grouped-coefficient DCT on all cores, single-threaded quantise/Exp-Golomb)",
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{sample} frames (1 slab) of the workload per step, encode+decode"},
+                         "sample": f"{frames} frames ({len(slabs)} slabs: {slabs}) of the workload per step, encode+decode"},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "encode_s_per_slab": float(np.mean([v[1] for v in vals])), "decode_s_per_slab": float(np.mean([v[2] for v in vals])),
+        "encode_s_per_slab": te / len(slabs), "decode_s_per_slab": td / len(slabs),
         # the other flavour of the reference, for the record: slower than the Java algorithm, so the port above is the
         # conservative denominator
-        "ref_c_host": ref_c_host_sample(W, H),
+        "ref_c_host": ref_c_host_sample(W, H) if not args.no_ref_c else None,
     }
     print(json.dumps(line))
     return 0
 
 
+def slab_numpy(W, H, cube, slab, seed):
+    """One slab of the SURVEY.md 8d natural clip on the CPU (numpy RNG, seeded per slab)."""
+    rng = np.random.default_rng(seed * 1000003 + slab)
+    t = np.arange(slab * cube, (slab + 1) * cube, dtype=np.float64)[:, None, None]
+    y = np.arange(H, dtype=np.float64)[None, :, None]
+    x = np.arange(W, dtype=np.float64)[None, None, :]
+    g = 128.0 + 60.0 * np.sin((x + 3.0 * t) / 37.0) + 50.0 * np.cos((y - 2.0 * t) / 23.0)
+    g = g + rng.normal(0.0, 6.0, size=(cube, H, W))
+    return np.clip(np.rint(g), 0, 255).astype(np.uint8)
+
+
+def l2_note(bytes_per_gpu):
+    if bytes_per_gpu > 126e6:
+        return "inputs (%.0f MB per GPU) larger than the 126 MB L2, no flush needed" % (bytes_per_gpu / 1e6)
+    return "inputs (%.0f MB per GPU) FIT the 126 MB L2: a parity configuration, not a bench line" % (bytes_per_gpu / 1e6)
+
+
+def config_of(args):
+    W, H, F, cube, scaling, idx = CONFIGS[args.config]
+    if args.width:
+        W = args.width
+    if args.height:
+        H = args.height
+    if args.frames:
+        F = args.frames
+    return W, H, F, cube, scaling, idx
+
+
+def workload_config(args, world):
+    W, H, F, cube, scaling, idx = config_of(args)
+    total = F * world if scaling == "weak" else F
+    per = f"{F} frames per GPU" if scaling == "weak" else f"{F} frames sharded over the GPUs"
+    return {"workload": f"{W}x{H} gray, {per}, {cube}x{cube}x{cube} cubes (BASELINE configs[{idx}])", "name": args.config,
+            "cube": cube, "total_frames": total,
+            "l2": l2_note(W * H * (F if scaling == "weak" else F / world))}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -178,32 +279,65 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device; libdct3d has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    gloo = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        gloo = dist.new_group(backend="gloo")                   # host-side scalars of the e2e path
 
     importlib.import_module(PKG + ".build").build()
     codec = importlib.import_module(PKG + ".codec")
-    W, H, F, cube = args.width, args.height, args.frames, 8
-    N = W * H * F
+    sh = importlib.import_module(PKG + ".sharding")
+    W, H, F, cube, scaling, idx = config_of(args)
+    total_frames = F * world if scaling == "weak" else F
+    nslabs = total_frames // cube
+    lo, hi = sh.slab_range(nslabs, rank, world)
+    Fr = (hi - lo) * cube                                       # this rank's frames
+    N = W * H * Fr
     c = codec.Codec(W, H, cube, device=local)
     if args.tma is not None:
         c.set_option("tma", args.tma)
     c.set_option("reuse_zeroed", 1)     # the stream buffer is reused every step: wipe only what the last step wrote
-    frames = synth_clip_torch(W, H, F, 1 + rank, dev)
+    frames = synth_slabs_torch(W, H, cube, lo, hi, 1, dev)
     cap = N // 2 + 4096
-    d_stream = torch.zeros(cap, dtype=torch.uint8, device=dev)
+    d_part = torch.zeros(cap, dtype=torch.uint8, device=dev)    # this rank's bits, coded from bit 0
+    d_placed = torch.zeros(cap + 64, dtype=torch.uint8, device=dev) if world > 1 else None   # ... moved to their phase
     d_out = torch.empty_like(frames)
     # a real (non-NULL) stream: NULL would mean "the context's own stream" to libdct3d, invisible to torch events
     tstream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(tstream)
     st = tstream.cuda_stream
     assert st != 0
+    h_cnt = torch.zeros(1, dtype=torch.int64).pin_memory()
+    d_cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+    d_all = torch.zeros(world, dtype=torch.int64, device=dev)
+    h_all = torch.zeros(world, dtype=torch.int64).pin_memory()
 
-    def step():
-        end = c.encode_u8_dev(frames, F, d_stream, cap, 0, st)
-        nbytes = end // 8 + 1
-        c.decode_u8_dev(d_stream, nbytes, F, d_out, 0, st)
-        return end
+    def gather_counts(end):
+        """The one exchange step: N scalars."""
+        h_cnt[0] = end
+        d_cnt.copy_(h_cnt, non_blocking=True)
+        dist.all_gather_into_tensor(d_all, d_cnt)
+        h_all.copy_(d_all, non_blocking=True)
+        tstream.synchronize()
+        return [int(v) for v in h_all.tolist()]
+
+    def step(events=None, i=0):
+        if events:
+            events[3 * i].record()
+        end = c.encode_u8_dev(frames, Fr, d_part, cap, 0, st)
+        if world > 1:
+            offs = sh.bit_offsets(gather_counts(end))
+            phase = offs[rank] % 8
+            c.stream_shift_dev(d_part, end, phase, d_placed, cap + 64, st)
+            src, nbytes = d_placed, (phase + end) // 8 + 1
+        else:
+            offs, phase, src, nbytes = [0, end], 0, d_part, end // 8 + 1
+        if events:
+            events[3 * i + 1].record()
+        c.decode_u8_dev(src, nbytes, Fr, d_out, phase, st)
+        if events:
+            events[3 * i + 2].record()
+        return end, offs
 
     def barrier():
         if world > 1:
@@ -215,10 +349,14 @@ def run_ours(args):
     sampler = ClockSampler(local) if rank == 0 else None
     t_w = time.perf_counter()
     nwarm = 0
-    while nwarm < max(args.warmup, 3) or time.perf_counter() - t_w < 1.5:
-        nbits = step()
+    while True:
+        nbits, offs = step()
         nwarm += 1
-    S = nbits // 8 + 1
+        go = torch.tensor([1 if (nwarm < max(args.warmup, 3) or time.perf_counter() - t_w < 1.5) else 0], device=dev)
+        if world > 1:
+            dist.all_reduce(go, op=dist.ReduceOp.MAX)            # the ranks must agree on the number of warm-up steps
+        if not int(go.item()):
+            break
     launches0 = c.stat("launches")
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3 * args.steps)]
     k_enc, k_rec = [], []
@@ -227,11 +365,7 @@ def run_ours(args):
     e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e_start.record()
     for i in range(args.steps):
-        ev[3 * i].record()
-        end = c.encode_u8_dev(frames, F, d_stream, cap, 0, st)
-        ev[3 * i + 1].record()
-        c.decode_u8_dev(d_stream, end // 8 + 1, F, d_out, 0, st)
-        ev[3 * i + 2].record()
+        step(ev, i)
         k_enc.append(c.stat("ns_encode_kernel"))     # the step has already synchronised (decode returns its end bit)
         k_rec.append(c.stat("ns_reconstruct_kernel"))
     e_end.record()
@@ -243,12 +377,22 @@ def run_ours(args):
     dec_ms = float(np.mean([ev[3 * i + 1].elapsed_time(ev[3 * i + 2]) for i in range(args.steps)]))
     launches = c.stat("launches") - launches0
     kenc_ms, krec_ms = float(np.mean(k_enc)) * 1e-6, float(np.mean(k_rec)) * 1e-6
+    device_roundtrip_ok = True
+
+    t = torch.tensor([total_ms, enc_ms, dec_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, enc_ms_max, dec_ms_max = [float(v) for v in t.tolist()]
+    ms_per_step = total_ms / args.steps
+    value = total_frames / (ms_per_step * 1e-3)
+    total_bits = offs[-1]
+    S_total = total_bits // 8 + 1
 
     # the HBM-bound entry points (the reference's own float device boundary): GB/s of forward/inverse_f32
     seam = None
-    if rank == 0:
-        ns = 8
-        a = torch.empty(W * H * 8 * ns, dtype=torch.float32, device=dev).uniform_(0, 255)
+    if rank == 0 and not args.quick:
+        ns = max(1, (64 * 1920 * 1080) // (W * H * cube))
+        a = torch.empty(W * H * cube * ns, dtype=torch.float32, device=dev).uniform_(0, 255)
         b = torch.empty_like(a)
         res = {}
         for name, fn in (("forward_f32", c.forward_f32_dev), ("inverse_f32", c.inverse_f32_dev)):
@@ -264,146 +408,246 @@ def run_ours(args):
         seam = res
         del a, b
 
-    t = torch.tensor([total_ms, enc_ms, dec_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, enc_ms_max, dec_ms_max = [float(v) for v in t.tolist()]
-    ms_per_step = total_ms / args.steps
-    value = world * F / (ms_per_step * 1e-3)
-
-    # ---- end to end through the host-buffer C ABI (pinned host memory) ---------------------------
-    # The clip is streamed the way the reference's C codec streams it (slab ranges in a loop): an
-    # encoder context on one host thread and a decoder context on another, so that the H2D copy of
-    # range i overlaps the D2H copy of range i-1 (PCIe is full duplex and is what bounds this number).
-    # Every range is a self-contained stream coded from bit 0, exactly like a multi-GPU slab range.
-    import queue
-    import threading as th
-    h_frames = torch.empty((F, H, W), dtype=torch.uint8, pin_memory=True)
+    # ---- end to end through the host-buffer C ABI (pinned host memory; H2D/D2H inside the timed region) ----------
+    # One call pair per step: the clip goes in as host frames and comes back as ONE host stream, which goes in again and
+    # comes back as host frames.  The chunked H2D / kernels / D2H overlap lives inside the library calls.  With N ranks
+    # every rank places its range into the same shared-memory stream and decodes its range from it.
+    lib = c.L
+    h_frames = torch.empty((Fr, H, W), dtype=torch.uint8, pin_memory=True)
     h_frames.copy_(frames)
-    h_out = torch.empty((F, H, W), dtype=torch.uint8, pin_memory=True)
-    nchunk = int(os.environ.get("DCT3D_E2E_RANGES", 16)) if F % 128 == 0 else 1
-    nthr = int(os.environ.get("DCT3D_E2E_THREADS", 2)) if nchunk > 1 else 1   # contexts (= host threads) per direction
-    cf = F // nchunk                                   # frames per range
-    ccap = W * H * cf // 2 + 4096
-    h_streams = [torch.zeros(ccap, dtype=torch.uint8, pin_memory=True) for _ in range(nchunk)]
-    enc_ctxs = [c] + [codec.Codec(W, H, cube, device=local) for _ in range(nthr - 1)]
-    dec_ctxs = [codec.Codec(W, H, cube, device=local) for _ in range(nthr)]
-    L = c.L
-    fsz = W * H * cf
-    sizes = [0] * nchunk
+    h_out = torch.empty((Fr, H, W), dtype=torch.uint8, pin_memory=True)
+    scap = (W * H * total_frames) // 2 + 4096
+    shm = None
+    if world > 1:
+        name = "dct3d_bench_%s" % os.environ.get("MASTER_PORT", "0")
+        if rank == 0:
+            shm = sh.SharedStream(name, scap, create=True)
+        dist.barrier()
+        if rank != 0:
+            shm = sh.SharedStream(name, scap, create=False)
+        assert lib.dct3d_host_register(shm.array.ctypes.data, scap) == 0
+        h_stream_np = shm.array
+        stream_ptr = shm.array.ctypes.data
+    else:
+        h_stream = torch.zeros(scap, dtype=torch.uint8, pin_memory=True)
+        h_stream_np = h_stream.numpy()
+        stream_ptr = h_stream.data_ptr()
+    e2e_state = {}
 
-    def e2e_step():
-        q = queue.Queue()
-        err = []
-
-        def enc(k):
+    def e2e_encode():
+        if world == 1:
             nb, ny = C.c_uint64(), C.c_size_t()
-            h = enc_ctxs[k].h
-            for i in range(k, nchunk, nthr):
-                rc = L.dct3d_encode_u8(h, h_frames.data_ptr() + i * fsz, cf, h_streams[i].data_ptr(), ccap, C.byref(nb), C.byref(ny))
-                if rc != 0:
-                    err.append(L.dct3d_last_error(h))
-                sizes[i] = ny.value
-                q.put(i)
-
-        def dec(k):
-            h = dec_ctxs[k].h
-            while True:
-                i = q.get()
-                if i < 0:
-                    return
-                rc = L.dct3d_decode_u8(h, h_streams[i].data_ptr(), sizes[i], cf, h_out.data_ptr() + i * fsz)
-                if rc != 0:
-                    err.append(L.dct3d_last_error(h))
-
-        te_ = [th.Thread(target=enc, args=(k,)) for k in range(nthr)]
-        td_ = [th.Thread(target=dec, args=(k,)) for k in range(nthr)]
-        for t_ in te_ + td_:
-            t_.start()
-        for t_ in te_:
-            t_.join()
-        for _ in td_:
-            q.put(-1)
-        for t_ in td_:
-            t_.join()
-        assert not err, err
-
-    def e2e_single():
-        nb, ny = C.c_uint64(), C.c_size_t()
-        big = h_streams[0] if nchunk == 1 else torch.zeros(cap, dtype=torch.uint8, pin_memory=True)
-        t0 = time.perf_counter()
-        rc = L.dct3d_encode_u8(c.h, h_frames.data_ptr(), F, big.data_ptr(), big.numel(), C.byref(nb), C.byref(ny))
-        assert rc == 0, L.dct3d_last_error(c.h)
-        rc = L.dct3d_decode_u8(c.h, big.data_ptr(), ny.value, F, h_out.data_ptr())
-        assert rc == 0, L.dct3d_last_error(c.h)
+            rc = lib.dct3d_encode_u8(c.h, h_frames.data_ptr(), Fr, stream_ptr, scap, C.byref(nb), C.byref(ny))
+            assert rc == 0, lib.dct3d_last_error(c.h)
+            e2e_state["offs"] = [0, nb.value]
+            return 0.0
+        nb = C.c_uint64()
+        rc = lib.dct3d_encode_u8_range(c.h, h_frames.data_ptr(), Fr, C.byref(nb))
+        assert rc == 0, lib.dct3d_last_error(c.h)
+        t0 = time.perf_counter()                                # from here on: the concatenation
+        mine = torch.tensor([nb.value], dtype=torch.int64)
+        allc = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(allc, mine, group=gloo)
+        o = sh.bit_offsets([int(v.item()) for v in allc])
+        fb = C.c_uint8(0)
+        rc = lib.dct3d_encode_u8_place(c.h, o[rank], 1 if rank == world - 1 else 0, stream_ptr, scap, C.byref(fb))
+        assert rc == 0, lib.dct3d_last_error(c.h)
+        dist.barrier(group=gloo)                                # the predecessor's bytes have landed
+        if o[rank] % 8:
+            h_stream_np[o[rank] // 8] |= fb.value
+        dist.barrier(group=gloo)
+        e2e_state["offs"] = o
         return time.perf_counter() - t0
 
-    e2e_step()
-    barrier()
+    def e2e_decode():
+        o = e2e_state["offs"]
+        end = C.c_uint64()
+        rc = lib.dct3d_decode_u8_range(c.h, stream_ptr, o[-1] // 8 + 1, o[rank], o[rank + 1], Fr, h_out.data_ptr(), C.byref(end))
+        assert rc == 0, lib.dct3d_last_error(c.h)
+        assert end.value == o[rank + 1]
+
+    def host_barrier():
+        if world > 1:
+            dist.barrier(group=gloo)
+
+    e2e_encode()
+    e2e_decode()
     e2e_steps = max(1, min(args.steps, 5))
+    host_barrier()
     t0 = time.perf_counter()
+    concat_s = te_s = 0.0
     for _ in range(e2e_steps):
-        e2e_step()
-    barrier()
+        ta = time.perf_counter()
+        concat_s += e2e_encode()
+        te_s += time.perf_counter() - ta
+        e2e_decode()
+    host_barrier()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    te2 = torch.tensor([e2e_s, te_s / e2e_steps, concat_s / e2e_steps], dtype=torch.float64, device=dev)
     if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * F / float(te.item())
+        dist.all_reduce(te2, op=dist.ReduceOp.MAX)
+    e2e_s, e2e_enc_s, concat_s = [float(v) for v in te2.tolist()]
+    e2e_value = total_frames / e2e_s
     roundtrip_ok = bool((h_out.to(dev) == d_out).all().item())
-    e2e_bytes = N + sum(sizes)
-    e2e_single()
-    single_s = e2e_single()
-    for x in enc_ctxs[1:] + dec_ctxs:
-        x.close()
+    ok_t = torch.tensor([1 if roundtrip_ok else 0], device=dev)
+    if world > 1:
+        dist.all_reduce(ok_t, op=dist.ReduceOp.MIN)
+    roundtrip_ok = bool(int(ok_t.item()))
+    sha = hashlib.sha256(h_stream_np[:S_total].tobytes()).hexdigest() if rank == 0 else None
+    e2e_h2d = W * H * total_frames + S_total
+    # two clips in flight at N = 1: a second context decodes clip k while the first encodes clip k+1 (PCIe is full
+    # duplex; every call is still the product call and every clip one stream)
+    duplex_value = None
+    if world == 1 and not args.quick:
+        c2 = codec.Codec(W, H, cube, device=local)
+        h_stream2 = [h_stream, torch.zeros(scap, dtype=torch.uint8, pin_memory=True)]
+        sizes = [0, 0]
+        nsteps = e2e_steps + 1
+        ready = [threading.Semaphore(0), threading.Semaphore(0)]
+        free = [threading.Semaphore(1), threading.Semaphore(1)]
+        errs = []
+
+        def enc_thread():
+            nb, ny = C.c_uint64(), C.c_size_t()
+            for k in range(nsteps):
+                free[k & 1].acquire()
+                if lib.dct3d_encode_u8(c.h, h_frames.data_ptr(), Fr, h_stream2[k & 1].data_ptr(), scap, C.byref(nb), C.byref(ny)) != 0:
+                    errs.append(lib.dct3d_last_error(c.h))
+                sizes[k & 1] = ny.value
+                ready[k & 1].release()
+
+        def dec_thread():
+            for k in range(nsteps):
+                ready[k & 1].acquire()
+                if lib.dct3d_decode_u8(c2.h, h_stream2[k & 1].data_ptr(), sizes[k & 1], Fr, h_out.data_ptr()) != 0:
+                    errs.append(lib.dct3d_last_error(c2.h))
+                free[k & 1].release()
+
+        ths = [threading.Thread(target=enc_thread), threading.Thread(target=dec_thread)]
+        t0 = time.perf_counter()
+        for t_ in ths:
+            t_.start()
+        for t_ in ths:
+            t_.join()
+        duplex_value = nsteps * Fr / (time.perf_counter() - t0)
+        assert not errs, errs
+        c2.close()
+
+    # ---- extra device-resident lines at N = 1: worst-case content and the 4^3 variant ------------------------------
+    extra = {}
+    if world == 1 and rank == 0 and not args.quick and args.config == "c2":
+        def quick_fps(cc, fr, nfr, reps=5):
+            cp = fr.numel() * 4 + 4096
+            ds = torch.zeros(cp, dtype=torch.uint8, device=dev)
+            do = torch.empty_like(fr)
+            for _ in range(2):
+                e_ = cc.encode_u8_dev(fr, nfr, ds, cp, 0, st)
+                cc.decode_u8_dev(ds, e_ // 8 + 1, nfr, do, 0, st)
+            a_, b_, c_ = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            te_ = td_ = 0.0
+            for _ in range(reps):
+                a_.record()
+                e_ = cc.encode_u8_dev(fr, nfr, ds, cp, 0, st)
+                b_.record()
+                cc.decode_u8_dev(ds, e_ // 8 + 1, nfr, do, 0, st)
+                c_.record()
+                torch.cuda.synchronize()
+                te_ += a_.elapsed_time(b_)
+                td_ += b_.elapsed_time(c_)
+            return {"frames": nfr, "encode_fps": nfr * reps / (te_ * 1e-3), "decode_fps": nfr * reps / (td_ * 1e-3),
+                    "bits_per_sample": e_ / fr.numel()}
+        noise = synth_slabs_torch(W, H, cube, 0, 8, 2, dev, kind="noise")
+        extra["noise_content"] = quick_fps(c, noise, 64)
+        del noise
+        with codec.Codec(W, H, 4, device=local) as c4:
+            f4 = synth_slabs_torch(W, H, 4, 0, 64, 1, dev)
+            extra["cube4"] = quick_fps(c4, f4, 256)
+            del f4
+        c.set_option("precision", 64)
+        f64 = frames[:64].contiguous()
+        extra["fp64_mode"] = quick_fps(c, f64, 64, reps=3)
+        c.set_option("precision", 32)
+
+    # ---- CPU baseline beside it + the four parity rules on the same sample slabs (rank 0, N = 1) -----------------
+    cpu = parity = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle as O
+        from oracle import parity as PAR
+        O.build()
+        cores = os.cpu_count() or 1
+        slabs = list(range(nslabs)) if nslabs <= 8 else sample_slabs(nslabs, 4)
+        te_ = td_ = 0.0
+        parts = []
+        for s in slabs:
+            piece = frames[s * cube:(s + 1) * cube].cpu().numpy()
+            a_, b_, ostream, odec = cpu_piece(piece, cube, cores)
+            te_ += a_
+            td_ += b_
+            p = PAR.piece_parity(c, piece, cube)
+            # the device-resident decode of the benchmark itself, against the CPU decode of the same slab
+            p["pixel_max_abs"] = max(p["pixel_max_abs"], int(np.abs(d_out[s * cube:(s + 1) * cube].cpu().numpy().astype(np.int16) - odec.astype(np.int16)).max()))
+            parts.append(p)
+        cpu = {"value": len(slabs) * cube / (te_ + td_), "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{len(slabs) * cube} frames (slabs {slabs} of the workload), encode+decode, oracle Java-structured port",
+               "encode_s_per_slab": te_ / len(slabs), "decode_s_per_slab": td_ / len(slabs)}
+        parity = PAR.merge(parts)
+        parity["slabs_checked"] = slabs
+        parity["rule"] = "coef <= 1e-4 rel; cubes equal except counted +-1 tie flips; stream bit-exact given cubes; pixels +-1"
 
     if rank == 0:
         peak, peak_src = peaks()
-        alg_bytes = N + S      # algorithmic bytes of encode_u8 and of decode_u8: pixels + stream
+        S_rank = nbits // 8 + 1
+        alg_bytes = N + S_rank   # algorithmic bytes of encode_u8 and of decode_u8 per launch: pixels + stream
         # dominant kernel of the step = the longer of the two transform kernels, timed live by CUDA events
         # recorded around it on the launching stream inside libdct3d
-        dom = ("reconstruct_coo_kernel<8>", krec_ms) if krec_ms >= kenc_ms else ("encode_kernel<8,MODE_ZZ>", kenc_ms)
+        dom = ((f"reconstruct_coo_kernel<{cube}>", krec_ms) if krec_ms >= kenc_ms else (f"encode_kernel<{cube},MODE_ZZ>", kenc_ms))
         achieved = alg_bytes / (dom[1] * 1e-3) / 1e9
-        cores = os.cpu_count() or 1
-        cpu = None
-        if world == 1 and not args.no_cpu_baseline:
-            fps, te_, td_, _ = cpu_baseline_sample(W, H, 8, cores)
-            cpu = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": "8 frames (1 slab) of the workload, encode+decode, oracle Java-structured port"}
+        traffic, traffic_src = ncu_traffic(dom[0].split("<")[0]) if args.config == "c2" else (None, None)
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "metric": metric_name(W, H), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": nwarm,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": f"{W}x{H} gray, {F} frames per GPU, 8x8x8 cubes (BASELINE configs[1])", "cube": 8,
-                       "frames_per_gpu": F, "l2": "inputs (%.0f MB) larger than L2" % (N / 1e6),
-                       "tma": c.stat("tma"), "stream_bytes": int(S), "bits_per_sample": nbits / N,
-                       "parallelism": f"slab-range x{world}, no collective"},
-            "encode_fps": world * F / (enc_ms_max * 1e-3), "decode_fps": world * F / (dec_ms_max * 1e-3),
+            "config": workload_config(args, world),
+            "detail": {"frames_per_gpu": Fr, "tma": c.stat("tma"), "stream_bytes": int(S_total),
+                       "bits_per_sample": total_bits / (W * H * total_frames),
+                       "parallelism": f"slab-range x{world}, one clip, one stream; bit counts all-gathered (N scalars), no data-path collective"},
+            "encode_fps": total_frames / (enc_ms_max * 1e-3), "decode_fps": total_frames / (dec_ms_max * 1e-3),
             "encode_ms": enc_ms_max, "decode_ms": dec_ms_max,
             "roofline": {"bound": "hbm", "kernel": dom[0], "kernel_ms": dom[1], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": 543.0e6 if dom[0].startswith("recon") else 635.0e6,
-                         "peak_source": peak_src, "algorithmic_bytes": int(alg_bytes),
-                         "traffic_source": "ncu dram__bytes_read+write of that kernel, profiles/r1_summary.md",
-                         "note": "the fused u8<->bitstream kernels are issue-bound (SM 62-82%, DRAM 13-21%), not HBM-bound: "
-                                 "DESIGN.md 4; the HBM-bound float seam is in roofline_f32_seam"},
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes": int(alg_bytes),
+                         "traffic_source": traffic_src,
+                         "step_frac": 2 * alg_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
+                         "note": "the fused u8<->bitstream kernels are issue-bound, not HBM-bound (DESIGN.md 4); "
+                                 "the HBM-bound float seam is in roofline_f32_seam"},
             "kernels_ms": {"encode_kernel": kenc_ms, "reconstruct_coo_kernel": krec_ms},
             "roofline_f32_seam": None if seam is None else {
                 "bound": "hbm", "unit": "GB/s", "peak": peak, "algorithmic_bytes_per_sample": 8,
                 "forward_f32": seam["forward_f32"], "inverse_f32": seam["inverse_f32"],
                 "frac": min(seam["forward_f32"], seam["inverse_f32"]) / peak},
             "cpu_baseline": cpu,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(e2e_bytes), "d2h_bytes_per_step": int(e2e_bytes),
-                    "steps": e2e_steps, "matches_device_path": roundtrip_ok,
-                    "how": f"dct3d_encode_u8 / dct3d_decode_u8 on pinned host buffers, {nchunk} slab ranges of {cf} frames streamed "
-                           f"through {nthr} encoder and {nthr} decoder contexts, one host thread each (PCIe is full duplex: the H2D of one "
-                           "range overlaps the compute and the D2H of others)",
-                    "single_call_value": world * F / single_s,
-                    "bound": "PCIe: %.2f GB each way per step" % (e2e_bytes / 1e9)},
+            "parity": parity,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(e2e_h2d), "d2h_bytes_per_step": int(e2e_h2d),
+                    "steps": e2e_steps, "matches_device_path": roundtrip_ok, "encode_ms": e2e_enc_s * 1e3,
+                    "decode_ms": (e2e_s - e2e_enc_s) * 1e3, "concat_ms": concat_s * 1e3,
+                    "stream_sha256": sha, "duplex_value": duplex_value, "chunks_per_call": c.stat("chunks"),
+                    "how": ("one dct3d_encode_u8 + one dct3d_decode_u8 per step on pinned host buffers" if world == 1 else
+                            f"per rank: dct3d_encode_u8_range, gloo all_gather of {world} bit counts, dct3d_encode_u8_place into the "
+                            "shared-memory stream, boundary byte OR-ed after a barrier (concat_ms = all of that), then "
+                            "dct3d_decode_u8_range from the rank's global start bit") +
+                           "; the chunked H2D / kernel / D2H overlap is inside the calls; duplex_value = a second context decodes "
+                           "clip k while clip k+1 is encoded",
+                    "bound": "PCIe: %.2f GB each way per step" % (e2e_h2d / 1e9)},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "wall_s": t_wall,
+            "extra": extra,
         }
         print(json.dumps(line))
+    if shm is not None:
+        lib.dct3d_host_unregister(shm.array.ctypes.data)
+        dist.barrier()
+        if rank == 0:
+            shm.unlink()
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -415,11 +659,15 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--width", type=int, default=1920)
-    ap.add_argument("--height", type=int, default=1080)
-    ap.add_argument("--frames", type=int, default=256)
+    ap.add_argument("--config", choices=sorted(CONFIGS), default="c2")
+    ap.add_argument("--width", type=int, default=0)
+    ap.add_argument("--height", type=int, default=0)
+    ap.add_argument("--frames", type=int, default=0)
     ap.add_argument("--tma", type=int, default=None)
+    ap.add_argument("--ref-slabs", type=int, default=4, help="reference arm: sample slabs of the workload per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-c", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="skip the seam, duplex and extra measurements")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

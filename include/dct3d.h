@@ -70,6 +70,7 @@ void dct3d_host_free(void *p);
  * read back) is only wiped up to where that call wrote -- the caller promises not to have written
  * beyond it in between.
  * "debug" (1 = print per-stage diagnostics to stderr).
+ * "chunk_frames" (default 0 = about 32 MB of pixels): frames per pipeline chunk of the host-buffer calls.
  * "precision" (32 [default] or 64): with 64 the fused and stage entry points (encode_u8, decode_u8, quantize_u8,
  * reconstruct_i16 and the streaming calls) compute in double like the Java reference (J/dct/DCT.java:41-59,
  * J/Encoder.java:82, J/Decoder.java:89,112): quantised cubes then equal the fp64 oracle without rounding-tie
@@ -93,6 +94,58 @@ int dct3d_encode_u8(dct3d_ctx *ctx, const uint8_t *frames, int nframes,
 /* Exp-Golomb stream -> u8 frames: parse + dequantise + inverse DCT + clamp + truncate.
  * Replaces J/Decoder.java:61-117 and, per slab, C/decoder.c:229-295. */
 int dct3d_decode_u8(dct3d_ctx *ctx, const uint8_t *stream, size_t nbytes, int nframes, uint8_t *frames);
+
+/* Both calls above move the clip as a pipeline of slab-range chunks (option "chunk_frames", default about 32 MB of
+ * pixels): the H2D copy of one chunk runs beside the kernels of the previous one and beside the D2H copy of what is
+ * finished, and the chunks of one call form ONE stream (the bit position is chained on the device), exactly as the
+ * reference's slab loop carries its partial byte (C/encoder.c:203-278, C/ExpGolomb.c:112-130). */
+
+/* ---- sharded coding: one slab range per GPU (or per process), one stream ------------------------
+ * Every slab of `cube` frames is an independent key-frame group (reference README.md:10); only the bit position
+ * couples them.  A range is coded from bit 0 on its own GPU (phase 1), the bit counts of all ranges are prefix-summed
+ * by the caller (G scalars, any channel), and every range is then moved to its place in the clip's one stream
+ * (phase 2).  This is the concatenation rule of expGolomb_freeBuffer (C/ExpGolomb.c:112-130) with C/encoder.c:263-271,
+ * applied across GPUs instead of across loop iterations. */
+
+/* Phase 1: codes `nframes` host frames into the context's device buffer from bit 0; *nbits = the range's bit count. */
+int dct3d_encode_u8_range(dct3d_ctx *ctx, const uint8_t *frames, int nframes, uint64_t *nbits);
+
+/* Phase 2: moves the range coded by the last dct3d_encode_u8_range to global bit `start_bit` of the host buffer `stream`
+ * (capacity `cap` bytes).  The bits are shifted to phase start_bit % 8 on the GPU and copied straight to byte
+ * start_bit / 8 onwards.  When start_bit % 8 != 0 the range's first byte is shared with its predecessor: it is NOT
+ * written but returned in *first_byte, to be OR-ed into stream[start_bit / 8] by the caller once the predecessor's bytes
+ * have landed.  The byte after the range's last bit is written only when the range has bits in it or `last` != 0 (the
+ * stream's closing byte: floor(bits/8)+1 bytes in all, J/Encoder.java:117, C/encoder.c:270). */
+int dct3d_encode_u8_place(dct3d_ctx *ctx, uint64_t start_bit, int last, uint8_t *stream, size_t cap, uint8_t *first_byte);
+
+/* Decodes `nframes` frames whose first code starts at bit `start_bit` of the host buffer `stream` (any bit, no
+ * alignment).  end_bit_hint (0 = unknown): the bit at which the range ends when the caller knows it; it only limits how
+ * much of the stream is copied to the GPU.  *end_bit (may be NULL) = first bit after the range. */
+int dct3d_decode_u8_range(dct3d_ctx *ctx, const uint8_t *stream, size_t nbytes, uint64_t start_bit, uint64_t end_bit_hint,
+                          int nframes, uint8_t *frames, uint64_t *end_bit);
+
+/* Page-locks an existing host buffer (e.g. a shared-memory mapping that several processes place their ranges into). */
+int dct3d_host_register(void *p, size_t bytes);
+int dct3d_host_unregister(void *p);
+
+/* Several GPUs in one process.  `devices` = CUDA ordinals (NULL = 0..ndevices-1).  GPU g codes slabs
+ * [g*n/G, (g+1)*n/G) on its own host thread; dct3d_multi_encode_u8 returns the ONE stream the reference would have
+ * written for the whole clip (bit-identical to dct3d_encode_u8 on a single GPU) and, in range_start_bits (G+1 entries,
+ * may be NULL), the bit at which every range starts.  dct3d_multi_decode_u8 takes those as side information; with
+ * range_start_bits == NULL (a file from the reference itself: the format stores no index, J/ExpGolombReader.java:19-63)
+ * the start bits are found by index discovery first (dct3d_multi_locate).  Replaces the single-device flow of
+ * C/encoder.c:148-278 / C/decoder.c:153-295; there is no collective on the data path. */
+typedef struct dct3d_multi dct3d_multi;
+int dct3d_multi_create(dct3d_multi **out, const int *devices, int ndevices, int width, int height, int cube);
+void dct3d_multi_destroy(dct3d_multi *m);
+const char *dct3d_multi_last_error(const dct3d_multi *m);
+int dct3d_multi_set_option(dct3d_multi *m, const char *key, long value);
+dct3d_ctx *dct3d_multi_context(dct3d_multi *m, int index);   /* the per-GPU context (statistics, options) */
+int dct3d_multi_encode_u8(dct3d_multi *m, const uint8_t *frames, int nframes, uint8_t *stream, size_t cap,
+                          uint64_t *nbits, size_t *nbytes, uint64_t *range_start_bits);
+int dct3d_multi_locate(dct3d_multi *m, const uint8_t *stream, size_t nbytes, int nframes, uint64_t *range_start_bits);
+int dct3d_multi_decode_u8(dct3d_multi *m, const uint8_t *stream, size_t nbytes, int nframes, uint8_t *frames,
+                          const uint64_t *range_start_bits);
 
 /* ---- streaming (the C codec's slab loop with a carried bit position) -------------------- */
 
@@ -157,11 +210,11 @@ int dct3d_eg_locate(dct3d_ctx *ctx, const uint8_t *stream, size_t nbytes, uint64
  * stream that work was enqueued on).  Work is enqueued on that stream; scalar results are written to
  * host memory after an internal stream synchronisation unless the pointer is NULL.
  * d_stream must be 4-byte aligned, zero-filled from start_bit on, and `cap` must include 8
- * bytes of slack. */
+ * bytes of slack.  d_frames must be aligned to the cube edge (8 or 4 bytes; 16 for the TMA path, else plain loads are
+ * used), d_qcubes and the f32/f64 buffers to 16 bytes; a misaligned pointer is rejected with DCT3D_E_INVALID. */
 int dct3d_encode_u8_dev(dct3d_ctx *ctx, const void *d_frames, int nframes, void *d_stream, size_t cap,
                         uint64_t start_bit, uint64_t *end_bit, void *cuda_stream);
-/* slab_bit_offsets (host array of nframes/cube+1 entries, may be NULL): side information from
- * the encoder; when NULL the cube boundaries are discovered from the stream itself. */
+/* The cube boundaries are discovered from the stream itself (it stores no index); start_bit is any bit of d_stream. */
 int dct3d_decode_u8_dev(dct3d_ctx *ctx, const void *d_stream, size_t nbytes, uint64_t start_bit,
                         int nframes, void *d_frames, uint64_t *end_bit, void *cuda_stream);
 int dct3d_forward_f32_dev(dct3d_ctx *ctx, const void *d_cubes_in, void *d_coef_out, int nslabs, void *cuda_stream);
@@ -176,6 +229,10 @@ int dct3d_eg_decode_i16_dev(dct3d_ctx *ctx, const void *d_stream, size_t nbytes,
                             size_t ncubes, void *d_qcubes, uint64_t *end_bit, void *cuda_stream);
 int dct3d_eg_locate_dev(dct3d_ctx *ctx, const void *d_stream, size_t nbytes, uint64_t start_bit, size_t ncubes,
                         uint64_t *end_bit, void *cuda_stream);
+/* d_dst bit (phase + i) = d_src bit i for i < nbits, the first `phase` (0..7) bits of d_dst zero: a range coded from bit 0
+ * moved to its phase in the clip's stream (device-resident form of dct3d_encode_u8_place).  d_src must be zero beyond
+ * its last bit; cap >= 4 * ((nbits + phase + 31) / 32 + 1). */
+int dct3d_stream_shift_dev(dct3d_ctx *ctx, const void *d_src, uint64_t nbits, unsigned phase, void *d_dst, size_t cap, void *cuda_stream);
 
 /* ---- colour planes (the reference codes colour video as three gray streams) --------------------
  * RGBUtils split / mix (J/RGBUtils.java:39-92 and :94-131): byte i of a raw RGB24 buffer belongs to

@@ -152,3 +152,32 @@ def test_segment_scan_counts_and_overhang(hh, oracle):
         total += n.value
         pos = nxt.value
     assert total >= vals.size
+
+
+def test_scan_does_not_count_a_code_cut_by_the_end_of_the_stream(hh):
+    """bytes FD 80 hold six zeros (1 1 1 1 1 1), then the 3-bit code 0 1 1 across the byte boundary.  Cut to
+    one byte the last code is incomplete: it must not be counted, and the scan must not report a position past the
+    end of the stream."""
+    n, nxt = C.c_uint32(), C.c_uint64()
+    two = np.array([0xFD, 0x80], np.uint8)
+    assert hh.hh_eg_scan(two, 2, 0, 16, C.byref(n), C.byref(nxt)) == 0
+    assert n.value >= 7
+    one = np.array([0xFD], np.uint8)
+    assert hh.hh_eg_scan(one, 1, 0, 8, C.byref(n), C.byref(nxt)) == 0
+    assert n.value == 6 and nxt.value <= 8
+
+
+def test_scan_rejects_17_bit_code_numbers_beyond_int16(hh, oracle):
+    """Only m = 65537 (v = -32768) is a legal 33-bit code: the codec's cubes are int16."""
+    def scan(bits):
+        bits += "0" * (-len(bits) % 8)
+        buf = np.frombuffer(int(bits, 2).to_bytes(len(bits) // 8, "big") + b"\0\0\0\0", np.uint8).copy()
+        n, nxt = C.c_uint32(), C.c_uint64()
+        rc = hh.hh_eg_scan(buf, buf.size, 0, 64, C.byref(n), C.byref(nxt))
+        return rc, n.value, nxt.value
+    ok = "111" + "0" * 16 + format(65537, "017b") + "1" * 40
+    assert scan(ok)[:2] == (0, 3 + 1 + 28)
+    stream, end = oracle.eg_encode(np.array([0, 0, 0, -32768], np.int32))
+    assert end == 36 and "".join(format(b, "08b") for b in stream)[:36] == ok[:36]
+    for m in (65536, 65538, 0x1FFFF):
+        assert scan("111" + "0" * 16 + format(m, "017b") + "1" * 40)[0] == -1
