@@ -122,6 +122,45 @@ class SharedStream:
             pass
 
 
+class ShmExchange:
+    """The one exchange step of the sharded codec, "N scalars through the host" (SURVEY.md 8e), for ranks that are
+    processes of one node: a shared-memory table with one 64-byte line per rank.  all_gather() publishes this rank's
+    bit count and returns everybody's; signal() / wait_for() order a rank's boundary byte after its predecessor's
+    copy.  Sequence numbers make the table reusable without a reset; values are double-buffered by sequence parity
+    because a fast rank may publish exchange k+1 while a slow one still reads exchange k.  (x86 stores are ordered:
+    the value is written before the sequence number that announces it.)"""
+    SEQ, VAL0, VAL1, FLAG = 0, 1, 2, 3
+
+    def __init__(self, name: str, world: int, rank: int, create: bool):
+        self.shm = SharedStream(name, world * 64, create)
+        self.tab = self.shm.array.view(np.int64).reshape(world, 8)
+        if create:
+            self.tab[:] = 0
+        self.world, self.rank, self.seq, self.fseq = world, rank, 0, 0
+
+    def all_gather(self, value: int) -> list[int]:
+        self.seq += 1
+        slot = self.VAL0 + (self.seq & 1)
+        self.tab[self.rank, slot] = value
+        self.tab[self.rank, self.SEQ] = self.seq
+        seqs = self.tab[:, self.SEQ]
+        while (seqs < self.seq).any():
+            pass
+        return [int(v) for v in self.tab[:, slot]]
+
+    def signal(self):
+        self.fseq += 1
+        self.tab[self.rank, self.FLAG] = self.fseq
+
+    def wait_for(self, peer: int):
+        """Blocks until `peer` has signalled as many times as this rank has."""
+        while self.tab[peer, self.FLAG] < self.fseq:
+            pass
+
+    def unlink(self):
+        self.shm.unlink()
+
+
 def sharded_encode(codec, frames, shared: np.ndarray, rank: int, world: int, group=None):
     """One rank's part of a multi-process encode: phase 1 on the GPU, all_gather of the bit counts, phase 2 straight
     into the shared stream, then the boundary byte.  Returns the exclusive prefix of the bit counts (world + 1)."""

@@ -261,3 +261,19 @@ def test_contexts_created_concurrently(codec_mod, synth):
     for t in th:
         t.join()
     assert not errs and all(o == out[0] for o in out)
+
+
+def test_multi_object_on_every_visible_gpu(codec_mod, synth):
+    """The same on real distinct GPUs when the box has more than one (skipped on a single-GPU box)."""
+    n = pkg("_lib").load().dct3d_device_count()
+    if n < 2:
+        pytest.skip("one GPU visible")
+    W, H, F = 256, 128, 8 * 3 * n + 8
+    clip = synth.natural(W, H, F, 41)
+    want, wbits, wdec = one_shot(codec_mod, clip, W, H, 8)
+    with codec_mod.MultiCodec(W, H, 8, devices=list(range(n))) as m:
+        m.set_option("chunk_frames", 8)
+        stream, nbits, starts = m.encode_u8(clip)
+        assert nbits == wbits and stream.tobytes() == want.tobytes()
+        assert (m.decode_u8(stream, F, starts) == wdec).all()
+        assert (m.decode_u8(stream, F) == wdec).all()

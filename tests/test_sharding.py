@@ -117,3 +117,57 @@ def test_two_ranks_over_gloo():
     same, offs = q.get(timeout=10)
     assert same and offs[0] == 0 and offs[1] > 0
     assert q.get(timeout=10)
+
+
+def _worker_shm(rank, world, tag, q):
+    """The multi-process flow of bench.py's e2e path with the GPU replaced by the oracle and the host model of the
+    placement kernel: code the rank's slab range from bit 0, exchange the bit counts through the shared-memory table,
+    place whole bytes into the shared stream, OR the boundary byte once the predecessor has landed."""
+    sys.path.insert(0, ROOT)
+    import importlib
+    from oracle import oracle as O
+    sh = importlib.import_module("3ddctvideoencoding_b200.sharding")
+    synth = importlib.import_module("3ddctvideoencoding_b200.synth")
+    W, H, nslabs = 64, 48, 7
+    clip = synth.natural_slabs(W, H, 8, 0, nslabs, 3)
+    whole, bits = O.encode_u8(clip, 8, 0)
+    xch = sh.ShmExchange("dct3d_test_x_%s" % tag, world, rank, create=False)
+    shared = sh.SharedStream("dct3d_test_s_%s" % tag, bits // 8 + 1, create=False)
+    ok = True
+    for rep in range(20):                                # the table is reused without a reset
+        lo, hi = sh.slab_range(nslabs, rank, world)
+        part, nb = O.encode_u8(clip[lo * 8:hi * 8], 8, 0) if hi > lo else (np.zeros(1, np.uint8), 0)
+        offs = sh.bit_offsets(xch.all_gather(nb))
+        fb = sh.place_shifted(shared.array, sh.shift_to_phase(part, nb, offs[rank] % 8), offs[rank], nb, rank == world - 1)
+        xch.signal()
+        if offs[rank] % 8:
+            xch.wait_for(rank - 1)
+            shared.array[offs[rank] // 8] |= fb
+        # wait for everybody before checking (and before the next repetition overwrites the stream)
+        done = xch.all_gather(1)
+        ok = ok and offs[-1] == bits and shared.array.tobytes() == whole.tobytes() and sum(done) == world
+        xch.all_gather(2)
+    q.put(bool(ok))
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_shared_memory_exchange_and_placement(world):
+    import torch.multiprocessing as mp
+    sh = pkg("sharding")
+    tag = "%d_%d" % (os.getpid(), world)
+    # rank 0's role of creating the mappings is played by the test itself
+    xch = sh.ShmExchange("dct3d_test_x_%s" % tag, world, 0, create=True)
+    shared = sh.SharedStream("dct3d_test_s_%s" % tag, 1 << 20, create=True)
+    try:
+        ctx = mp.get_context("spawn")
+        q = ctx.Queue()
+        procs = [ctx.Process(target=_worker_shm, args=(r, world, tag, q)) for r in range(world)]
+        for p in procs:
+            p.start()
+        for p in procs:
+            p.join(timeout=300)
+            assert p.exitcode == 0
+        assert all(q.get(timeout=10) for _ in range(world))
+    finally:
+        xch.unlink()
+        shared.unlink()
