@@ -70,7 +70,9 @@ _LIB = None
 
 
 def lib_path() -> str:
-    return _build.LIB
+    """libdct3d.so built in-tree; DCT3D_LIB names another build of the same sources (kernel-variant experiments of
+    profiles/tools/step_time.py).  Either way it is this CUDA library or nothing."""
+    return os.environ.get("DCT3D_LIB") or _build.LIB
 
 
 def load() -> C.CDLL:
@@ -78,6 +80,11 @@ def load() -> C.CDLL:
     global _LIB
     if _LIB is None:
         path = lib_path()
+        if path == _build.LIB and _build.stale() and os.path.exists(os.path.join(_build.CSRC, "dct3d_api.cu")):
+            try:
+                _build.build()
+            except Exception:   # noqa: BLE001  (no nvcc on this box: the shipped library is used as it is)
+                pass
         if not os.path.exists(path):
             raise RuntimeError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                                "(nvcc, sm_100a). This package has no CPU fallback.")

@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <condition_variable>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -38,6 +39,8 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+constexpr int kKevRing = 32;
+
 struct Ctrl {               // small device control block, zeroed before every launch
     unsigned int ticket;
     unsigned int err;
@@ -65,8 +68,11 @@ struct dct3d_ctx {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::string err;
     DevBuf frames, bits, q, ctrl, seg, seglist, fa, fb, zz, cmask, coo, coocnt;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // around encode_kernel / reconstruct_coo_kernel
-    bool ev_valid[2] = {false, false};
+    // CUDA events around the last kKevRing launches of encode_kernel [0] / reconstruct_coo_kernel [1]: the kernels' device
+    // times can be read after a run of calls without synchronising inside it (statistics ns_*_kernel)
+    cudaEvent_t kev[2][kKevRing][2] = {};
+    unsigned long kcalls[2] = {0, 0};
+    cudaEvent_t ev_ctrl = nullptr;   // the control block of a decode has reached the host
     Ctrl *h_ctrl = nullptr;          // pinned
     unsigned long long *h_u64 = nullptr;  // pinned scratch (4 entries)
     // streaming state
@@ -230,9 +236,10 @@ int launch_encode(dct3d_ctx *ctx, const EncParams &P, const CUtensorMap &tm, cud
     }
     if (occ < 1) return fail(ctx, DCT3D_E_CUDA, "encode kernel does not fit on an SM");
     const long long grid = std::min<long long>((P.L.nunits + kWarps - 1) / kWarps, (long long)ctx->num_sms * occ);
-    if (MODE == MODE_ZZ) cudaEventRecord(ctx->ev[0], st);
+    cudaEvent_t *kev = ctx->kev[0][ctx->kcalls[0] % kKevRing];
+    if (MODE == MODE_ZZ) cudaEventRecord(kev[0], st);
     kern<<<(unsigned)grid, kThreads, smem, st>>>(tm, P);
-    if (MODE == MODE_ZZ) { cudaEventRecord(ctx->ev[1], st); ctx->ev_valid[0] = true; }
+    if (MODE == MODE_ZZ) { cudaEventRecord(kev[1], st); ctx->kcalls[0]++; }
     ctx->launches++;
     CU_CHECK(ctx, cudaGetLastError());
     return DCT3D_OK;
@@ -285,6 +292,8 @@ int zero_stream(dct3d_ctx *ctx, void *d_stream, size_t cap, uint64_t start_bit, 
 template <int C>
 static int launch_reconstruct_coo(dct3d_ctx *ctx, const Layout &L, void *d_frames, cudaStream_t st, long long cube_base = 0)
 {
+    // the lists hold at most one entry per coefficient of the parsed cubes; ctx->coo has room for Geo<C>::CS more
+    const unsigned long long coo_limit = ctx->coo.cap >= (size_t)Geo<C>::CS * 8 ? (unsigned long long)(ctx->coo.cap / 4 - Geo<C>::CS) : 0ull;
     auto kern = reconstruct_coo_kernel<C>;
     const int smem = CooSmem<C>::TOTAL;
     int &occ = ctx->occ_cache[5];
@@ -294,10 +303,11 @@ static int launch_reconstruct_coo(dct3d_ctx *ctx, const Layout &L, void *d_frame
     }
     const long long groups = (L.ncubes + Geo<C>::CPW - 1) / Geo<C>::CPW;
     const long long grid = std::min<long long>((groups + kWarps - 1) / kWarps, (long long)ctx->num_sms * std::max(occ, 1));
-    cudaEventRecord(ctx->ev[2], st);
-    kern<<<(unsigned)grid, kThreads, smem, st>>>(L, (const uint32_t *)ctx->coo.p, (const unsigned long long *)ctx->coocnt.p, (uint8_t *)d_frames, cube_base);
-    cudaEventRecord(ctx->ev[3], st);
-    ctx->ev_valid[1] = true;
+    cudaEvent_t *kev = ctx->kev[1][ctx->kcalls[1] % kKevRing];
+    cudaEventRecord(kev[0], st);
+    kern<<<(unsigned)grid, kThreads, smem, st>>>(L, (const uint32_t *)ctx->coo.p, (const unsigned long long *)ctx->coocnt.p, (uint8_t *)d_frames, cube_base, coo_limit);
+    cudaEventRecord(kev[1], st);
+    ctx->kcalls[1]++;
     ctx->launches++;
     CU_CHECK(ctx, cudaGetLastError());
     return DCT3D_OK;
@@ -409,7 +419,10 @@ int dct3d_create(dct3d_ctx **out, int device, int width, int height, int cube)
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
-        for (int i = 0; i < 4 && e == cudaSuccess; i++) e = cudaEventCreate(&ctx->ev[i]);
+        for (int k = 0; k < 2; k++)
+            for (int i = 0; i < kKevRing; i++)
+                for (int j = 0; j < 2 && e == cudaSuccess; j++) e = cudaEventCreate(&ctx->kev[k][i][j]);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_ctrl, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaMallocHost((void **)&ctx->h_ctrl, sizeof(Ctrl));
         if (e == cudaSuccess) e = cudaMallocHost((void **)&ctx->h_u64, 4 * sizeof(unsigned long long));
         if (e == cudaSuccess) e = cudaMallocHost((void **)&ctx->h_byte, 16);
@@ -434,7 +447,10 @@ void dct3d_destroy(dct3d_ctx *ctx)
     if (ctx->h_byte) cudaFreeHost(ctx->h_byte);
     if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
     if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
-    for (int i = 0; i < 4; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    for (int k = 0; k < 2; k++)
+        for (int i = 0; i < kKevRing; i++)
+            for (int j = 0; j < 2; j++) if (ctx->kev[k][i][j]) cudaEventDestroy(ctx->kev[k][i][j]);
+    if (ctx->ev_ctrl) cudaEventDestroy(ctx->ev_ctrl);
     if (ctx->h_ctrl) cudaFreeHost(ctx->h_ctrl);
     if (ctx->h_u64) cudaFreeHost(ctx->h_u64);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
@@ -474,6 +490,7 @@ int dct3d_set_option(dct3d_ctx *ctx, const char *key, long value)
         return DCT3D_OK;
     }
     if (!strcmp(key, "rounding")) { ctx->rounding = value ? 1 : 0; return DCT3D_OK; }
+    if (!strcmp(key, "kernel_times_reset")) { ctx->kcalls[0] = ctx->kcalls[1] = 0; return DCT3D_OK; }
     if (!strcmp(key, "chunk_frames")) {
         if (value < 0 || value % ctx->C) return fail(ctx, DCT3D_E_INVALID, "chunk_frames must be a non-negative multiple of the cube edge");
         ctx->chunk_frames = (int)value;
@@ -493,14 +510,24 @@ long dct3d_get_stat(const dct3d_ctx *ctx, const char *key)
     // device time of the last encode_kernel / reconstruct_coo_kernel launch, nanoseconds (CUDA events on
     // the launching stream; waits for that launch to finish)
     for (int k = 0; k < 2; k++) {
-        if (!strcmp(key, k == 0 ? "ns_encode_kernel" : "ns_reconstruct_kernel")) {
-            if (!ctx->ev_valid[k]) return -1;
+        const bool last = !strcmp(key, k == 0 ? "ns_encode_kernel" : "ns_reconstruct_kernel");
+        const bool avg = !strcmp(key, k == 0 ? "ns_encode_kernel_avg" : "ns_reconstruct_kernel_avg");
+        if (!last && !avg) continue;
+        // duration of the last launch, or the mean over the launches since "kernel_times_reset" (at most kKevRing)
+        const unsigned long n = ctx->kcalls[k];
+        if (n == 0) return -1;
+        const unsigned long cnt = last ? 1 : std::min<unsigned long>(n, kKevRing);
+        double sum = 0;
+        for (unsigned long i = n - cnt; i < n; i++) {
+            cudaEvent_t const *e = ctx->kev[k][i % kKevRing];
             float ms = 0.f;
-            if (cudaEventSynchronize(ctx->ev[2 * k + 1]) != cudaSuccess) return -1;
-            if (cudaEventElapsedTime(&ms, ctx->ev[2 * k], ctx->ev[2 * k + 1]) != cudaSuccess) return -1;
-            return (long)(ms * 1e6f);
+            if (cudaEventSynchronize(e[1]) != cudaSuccess) return -1;
+            if (cudaEventElapsedTime(&ms, e[0], e[1]) != cudaSuccess) return -1;
+            sum += ms;
         }
+        return (long)(sum / cnt * 1e6);
     }
+    if (!strcmp(key, "kernel_launches_timed")) return (long)std::min<unsigned long>(ctx->kcalls[0], kKevRing);
     return -1;
 }
 
@@ -721,8 +748,12 @@ int dct3d_eg_encode_i16_dev(dct3d_ctx *ctx, const void *d_qcubes, size_t ncubes,
 }
 
 // Index discovery + emit: stream -> CSR lists of the cubes' non-zero coefficients (ctx->coo, ctx->coocnt).
+// `tail` (optional) enqueues what consumes the lists (the inverse kernel): it is launched BEFORE the host looks at the
+// control block, so the GPU does not idle for a host round trip between index discovery and the inverse transform.  In
+// the rare case that the fix-up rounds had not converged, or the stream is damaged, the tail has run on inconsistent
+// (but bounds-safe) lists: it is run again after convergence, or the call fails and the output is unspecified.
 static int parse_common(dct3d_ctx *ctx, const void *d_stream, size_t nbytes, uint64_t start_bit, size_t ncubes,
-                        uint64_t *end_bit, cudaStream_t st, bool locate_only = false)
+                        uint64_t *end_bit, cudaStream_t st, bool locate_only = false, const std::function<int()> *tail = nullptr)
 {
     int rc;
     const int C = ctx->C, CS = C * C * C;
@@ -790,7 +821,10 @@ static int parse_common(dct3d_ctx *ctx, const void *d_stream, size_t nbytes, uin
     // overhang; only then (the constructed worst case) it iterates to convergence and redoes prefix + emit.
     if ((rc = fix_round()) || (rc = fix_round()) || (rc = prefix_and_parse())) return rc;
     CU_CHECK(ctx, cudaMemcpyAsync(ctx->h_u64, P.seg_first + n, 8, cudaMemcpyDeviceToHost, st));
-    if ((rc = fetch_ctrl(ctx, st))) return rc;
+    CU_CHECK(ctx, cudaMemcpyAsync(ctx->h_ctrl, ctx->ctrl.p, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
+    CU_CHECK(ctx, cudaEventRecord(ctx->ev_ctrl, st));
+    if (tail && (rc = (*tail)())) return rc;
+    CU_CHECK(ctx, cudaEventSynchronize(ctx->ev_ctrl));
     if (ctx->h_ctrl->changed == round) {
         for (unsigned long long it = 0; it <= P.nseg && ctx->h_ctrl->changed == round; it++) {
             if ((rc = fix_round()) || (rc = fetch_ctrl(ctx, st))) return rc;
@@ -800,6 +834,7 @@ static int parse_common(dct3d_ctx *ctx, const void *d_stream, size_t nbytes, uin
         if ((rc = prefix_and_parse())) return rc;
         CU_CHECK(ctx, cudaMemcpyAsync(ctx->h_u64, P.seg_first + n, 8, cudaMemcpyDeviceToHost, st));
         if ((rc = fetch_ctrl(ctx, st))) return rc;
+        if (tail && (rc = (*tail)())) return rc;                 // again, on the converged lists
     }
     if (ctx->h_u64[0] < (unsigned long long)ncubes * CS)
         return fail(ctx, DCT3D_E_NEED_MORE, "stream holds %llu codes, %llu needed", ctx->h_u64[0], (unsigned long long)ncubes * CS);
@@ -880,9 +915,12 @@ int dct3d_decode_u8_dev(dct3d_ctx *ctx, const void *d_stream, size_t nbytes, uin
         if (end_bit) *end_bit = end;
         return reconstruct_f64(ctx, ctx->q.p, nslabs, d_frames, st);
     }
-    if ((rc = parse_common(ctx, d_stream, nbytes, start_bit, (size_t)L.ncubes, &end, st))) return rc;
+    const std::function<int()> tail = [&]() -> int {
+        return C == 8 ? launch_reconstruct_coo<8>(ctx, L, d_frames, st) : launch_reconstruct_coo<4>(ctx, L, d_frames, st);
+    };
+    if ((rc = parse_common(ctx, d_stream, nbytes, start_bit, (size_t)L.ncubes, &end, st, false, &tail))) return rc;
     if (end_bit) *end_bit = end;
-    return C == 8 ? launch_reconstruct_coo<8>(ctx, L, d_frames, st) : launch_reconstruct_coo<4>(ctx, L, d_frames, st);
+    return DCT3D_OK;
 }
 
 static int rgb_dev(dct3d_ctx *ctx, bool split, void *d_rgb, void *d_r, void *d_g, void *d_b, size_t nbytes, void *cuda_stream)

@@ -1142,6 +1142,10 @@ __device__ __forceinline__ void idct_store(float (&b)[C][C], uint8_t *xbuf, int 
 // conflict-free.  Only the 3% non-zero coefficients are ever converted or multiplied.  Counts and the
 // first 3*C entries of the NEXT group are prefetched into registers while the current group is
 // transformed.
+// Occupancy note (measured, round 2): the kernel runs 4 CTAs = 16 warps per SM at 128 registers.  Buying a fifth or sixth
+// CTA with fewer registers (96: 16 bytes of spills, 80: 144 bytes) and with the exchange buffer aliased onto the cubes made
+// it SLOWER (388 -> 417 us for the aliasing alone, 442 us at 5 CTAs, 528 us at 6): the shared-memory pipe and the issue slots
+// are co-limiters, so extra wipes and spill traffic cost more than the extra warps hide.
 template <int C>
 struct CooSmem {
     using G = Geo<C>;
@@ -1154,8 +1158,10 @@ struct CooSmem {
 template <int C>
 __global__ void __launch_bounds__(kThreads, 4)
 reconstruct_coo_kernel(const Layout L, const uint32_t *__restrict__ coo, const unsigned long long *__restrict__ coo_start_all,
-                       uint8_t *__restrict__ frames, const long long cube_base)
+                       uint8_t *__restrict__ frames, const long long cube_base, const unsigned long long coo_limit)
 {
+    // coo_limit: row pointers are clamped to it, so that a launch that runs ahead of the host's look at the control
+    // block (lists of a stream whose index discovery has not converged, or of a damaged stream) stays inside the buffer
     // cube_base: the launch reconstructs cubes [cube_base, cube_base + L.ncubes) of the parsed stream into a frame buffer
     // that starts at the first of them (a whole number of slabs): the pipelined decoder's chunks
     const unsigned long long *__restrict__ coo_start = coo_start_all + cube_base;
@@ -1181,7 +1187,7 @@ reconstruct_coo_kernel(const Layout L, const uint32_t *__restrict__ coo, const u
     auto fetch_rows = [&](long long grp) {
         const long long cube = grp * G::CPW + cl;
         const bool ok = grp < ngroups && cube < L.ncubes;
-        z_nn = ok ? __ldg(coo_start + cube) : 0ull;
+        z_nn = ok ? min(__ldg(coo_start + cube), coo_limit) : 0ull;
         zend_nn = ok ? __ldg(reinterpret_cast<const uint32_t *>(coo_start + cube + 1)) : 0u;
     };
     auto rotate_rows = [&]() {

@@ -77,8 +77,10 @@ void dct3d_host_free(void *p);
  * flips, at a fraction of the fp32 path's speed.  "rounding" (fp64 mode only): 0 = Math.round = floor(v + 0.5)
  * (J/Encoder.java:82), 1 = C round(), ties away from zero (C/encoder.c:53).
  * Statistics (dct3d_get_stat): "launches" = kernels launched by the context so far; "tma" = 1 when the
- * TMA path is active; "num_sms"; "ns_encode_kernel" / "ns_reconstruct_kernel" = duration in ns of the
- * last transform kernel of each direction, from CUDA events recorded around it on the launching stream. */
+ * TMA path is active; "num_sms"; "chunks" = pipeline chunks of the last host-buffer call; "ns_encode_kernel" /
+ * "ns_reconstruct_kernel" = duration in ns of the last transform kernel of each direction, from CUDA events recorded around
+ * it on the launching stream; "ns_encode_kernel_avg" / "ns_reconstruct_kernel_avg" = the mean over the launches since option
+ * "kernel_times_reset" was set (a ring of the last 32), read without having synchronised in between. */
 int dct3d_set_option(dct3d_ctx *ctx, const char *key, long value);
 long dct3d_get_stat(const dct3d_ctx *ctx, const char *key);
 
