@@ -538,44 +538,34 @@ static unsigned ew_grid(dct3d_ctx *ctx, unsigned long long n)
     return (unsigned)std::min<unsigned long long>((n + 255) / 256, (unsigned long long)ctx->num_sms * 32);
 }
 
-// fp64 mode, forward half: u8 frames -> natural-order int16 cubes through the f64 transform seam
-static int quantize_f64(dct3d_ctx *ctx, const void *d_frames, int nslabs, void *d_q, cudaStream_t st)
+// fp64 mode: one fused kernel per direction (codec_f64_kernel), u8 frames <-> natural-order int16 cubes
+extern "C++" template <bool INVERSE>
+int codec_f64(dct3d_ctx *ctx, const void *d_in, int nslabs, void *d_out, cudaStream_t st)
 {
     const int C = ctx->C;
     const Layout L = make_layout(ctx->W, ctx->H, C, nslabs);
-    const unsigned long long n = (unsigned long long)L.ncubes * C * C * C;
-    if ((ctx->W * sizeof(double)) % 16) return fail(ctx, DCT3D_E_INVALID, "fp64 mode needs an even width");
-    CU_CHECK(ctx, ctx->fa.reserve(n * sizeof(double)));
-    CU_CHECK(ctx, ctx->fb.reserve(n * sizeof(double)));
-    u8_to_f64_kernel<<<ew_grid(ctx, n), 256, 0, st>>>((const uint8_t *)d_frames, (double *)ctx->fa.p, n);
-    ctx->launches++;
-    int rc = dct3d_forward_f64_dev(ctx, ctx->fa.p, ctx->fb.p, nslabs * C, st);
-    if (rc) return rc;
-    if (C == 8) quant_f64_kernel<8, true><<<ew_grid(ctx, n), 256, 0, st>>>(L, (double *)ctx->fb.p, (int16_t *)d_q, ctx->rounding);
-    else quant_f64_kernel<4, true><<<ew_grid(ctx, n), 256, 0, st>>>(L, (double *)ctx->fb.p, (int16_t *)d_q, ctx->rounding);
+    const int cpw = 32 / C;
+    const long long groups = (L.ncubes + cpw - 1) / cpw;
+    const long long grid = std::min<long long>((groups + kWarps - 1) / kWarps, (long long)ctx->num_sms * 8);
+    const uint8_t *fin = INVERSE ? nullptr : (const uint8_t *)d_in;
+    const int16_t *qin = INVERSE ? (const int16_t *)d_in : nullptr;
+    int16_t *qout = INVERSE ? nullptr : (int16_t *)d_out;
+    uint8_t *fout = INVERSE ? (uint8_t *)d_out : nullptr;
+    if (C == 8) codec_f64_kernel<8, INVERSE><<<(unsigned)grid, kThreads, kWarps * Xch<8, double>::WARP_BYTES, st>>>(L, fin, qout, qin, fout, ctx->rounding);
+    else codec_f64_kernel<4, INVERSE><<<(unsigned)grid, kThreads, kWarps * Xch<4, double>::WARP_BYTES, st>>>(L, fin, qout, qin, fout, ctx->rounding);
     ctx->launches++;
     CU_CHECK(ctx, cudaGetLastError());
     return DCT3D_OK;
 }
 
-// fp64 mode, inverse half: natural-order int16 cubes -> u8 frames
+static int quantize_f64(dct3d_ctx *ctx, const void *d_frames, int nslabs, void *d_q, cudaStream_t st)
+{
+    return codec_f64<false>(ctx, d_frames, nslabs, d_q, st);
+}
+
 static int reconstruct_f64(dct3d_ctx *ctx, const void *d_q, int nslabs, void *d_frames, cudaStream_t st)
 {
-    const int C = ctx->C;
-    const Layout L = make_layout(ctx->W, ctx->H, C, nslabs);
-    const unsigned long long n = (unsigned long long)L.ncubes * C * C * C;
-    if ((ctx->W * sizeof(double)) % 16) return fail(ctx, DCT3D_E_INVALID, "fp64 mode needs an even width");
-    CU_CHECK(ctx, ctx->fa.reserve(n * sizeof(double)));
-    CU_CHECK(ctx, ctx->fb.reserve(n * sizeof(double)));
-    if (C == 8) quant_f64_kernel<8, false><<<ew_grid(ctx, n), 256, 0, st>>>(L, (double *)ctx->fa.p, (int16_t *)const_cast<void *>(d_q), 0);
-    else quant_f64_kernel<4, false><<<ew_grid(ctx, n), 256, 0, st>>>(L, (double *)ctx->fa.p, (int16_t *)const_cast<void *>(d_q), 0);
-    ctx->launches++;
-    int rc = dct3d_inverse_f64_dev(ctx, ctx->fa.p, ctx->fb.p, nslabs * C, st);
-    if (rc) return rc;
-    f64_to_u8_kernel<<<ew_grid(ctx, n), 256, 0, st>>>((const double *)ctx->fb.p, (uint8_t *)d_frames, n);
-    ctx->launches++;
-    CU_CHECK(ctx, cudaGetLastError());
-    return DCT3D_OK;
+    return codec_f64<true>(ctx, d_q, nslabs, d_frames, st);
 }
 
 // Bit positions chained on the device: the pipelined host-buffer encoder codes a clip as consecutive slab ranges

@@ -1443,44 +1443,104 @@ transform_kernel(const Layout L, const T *__restrict__ in, T *__restrict__ out)
 }
 
 // ------------------------------------------------------------------------------------------
-// fp64 mode (option "precision" = 64): the reference's Java flavour computes in double
-// (DCT.java:41-59, Encoder.java:82, Decoder.java:89,112); these element-wise kernels sit around the
-// f64 transform seam so that the quantised cubes match it without rounding-tie flips.
+// fp64 mode (option "precision" = 64): the reference's Java flavour computes in double (DCT.java:41-59,
+// Encoder.java:82, Decoder.java:89,112).  One fused kernel per direction: u8 frames -> double butterflies ->
+// the reference's quantiser -> natural-order int16 cubes, and back; no planar doubles in HBM (3 bytes of traffic
+// per sample instead of 34).  Same operations in the same order as the f64 transform seam (transform_kernel<C,
+// double, false, .>), so the quantised cubes match the fp64 oracle without rounding-tie flips.
+//   forward: q = Math.round(c / d) = floor(c / d + 0.5) (Encoder.java:82; rounding 0) or C round(), ties away from
+//            zero (encoder.c:53; rounding 1), d = max(1, 5(k0+k1+k2));
+//   inverse: c = q * d (Decoder.java:89), clamp to [0,255] (InverseDCT.java:74-80), (byte)(double) truncates
+//            (Decoder.java:112).
 // ------------------------------------------------------------------------------------------
-__global__ void u8_to_f64_kernel(const uint8_t *__restrict__ in, double *__restrict__ out, unsigned long long n)
+template <int C, bool INVERSE>
+__global__ void __launch_bounds__(kThreads)
+codec_f64_kernel(const Layout L, const uint8_t *__restrict__ frames_in, int16_t *__restrict__ q_out,
+                 const int16_t *__restrict__ q_in, uint8_t *__restrict__ frames_out, int rounding)
 {
-    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n; i += gridDim.x * (unsigned long long)blockDim.x)
-        out[i] = (double)in[i];
-}
-
-// clamp happened in the inverse transform; (byte)(double) truncates (Decoder.java:112)
-__global__ void f64_to_u8_kernel(const double *__restrict__ in, uint8_t *__restrict__ out, unsigned long long n)
-{
-    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n; i += gridDim.x * (unsigned long long)blockDim.x)
-        out[i] = (uint8_t)(int)in[i];
-}
-
-// planar f64 coefficients [F][H][W] <-> natural-order int16 cubes [cube][k0][k1][k2].
-// QUANT: q = Math.round(c / d) = floor(c / d + 0.5) (Encoder.java:82; rounding 0) or C round(), ties away
-// from zero (encoder.c:53; rounding 1), d = max(1, 5(k0+k1+k2)).  Otherwise c = q * d (Decoder.java:89).
-template <int C, bool QUANT>
-__global__ void quant_f64_kernel(const Layout L, double *__restrict__ planar, int16_t *__restrict__ q, int rounding)
-{
-    constexpr int CS = C * C * C;
-    const unsigned long long n = (unsigned long long)L.ncubes * CS;
-    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n; i += gridDim.x * (unsigned long long)blockDim.x) {
-        const unsigned long long cube = i / CS;
-        const int e = (int)(i % CS), k2 = e % C, k1 = (e / C) % C, k0 = e / (C * C);
+    using G = Geo<C>;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int cl = lane / C, r = lane % C;
+    const long long ngroups = (L.ncubes + G::CPW - 1) / G::CPW;
+    const size_t fs = (size_t)L.W * L.H;
+    uint8_t *xbuf = smem + warp * Xch<C, double>::WARP_BYTES;
+    for (long long g = (long long)blockIdx.x * kWarps + warp; g < ngroups; g += (long long)gridDim.x * kWarps) {
+        const long long cube = g * G::CPW + cl;
+        const bool valid = cube < L.ncubes;
+        const long long cc = valid ? cube : 0;
         const int per_slab = L.by * L.bx;
-        const int slab = (int)(cube / per_slab), rem = (int)(cube % per_slab), byi = rem / L.bx, bxi = rem % L.bx;
-        const size_t at = ((size_t)(slab * C + k0) * L.H + (byi * C + k1)) * L.W + (bxi * C + k2);
-        const double d = (double)quant_divisor(k0 + k1 + k2);
-        if (QUANT) {
-            const double v = planar[at] / d;
-            const double r = rounding ? (v < 0 ? -floor(-v + 0.5) : floor(v + 0.5)) : floor(v + 0.5);
-            q[i] = (int16_t)max(-32768.0, min(32767.0, r));
+        const int slab = (int)(cc / per_slab);
+        const int rem = (int)(cc - (long long)slab * per_slab);
+        const int byi = rem / L.bx, bxi = rem - byi * L.bx;
+        const size_t pix0 = (size_t)(slab * C) * fs + (size_t)(byi * C) * L.W + (size_t)bxi * C;   // pixel (t = 0, y = 0, x = 0) of the cube
+        double a[C][C], b[C][C];
+        if (!INVERSE) {
+            // thread = row y: b[t][x]; t pass, exchange, thread = k0: a[y][x]; y and x passes; quantise
+#pragma unroll
+            for (int t = 0; t < C; t++) {
+                const uint8_t *src = frames_in + pix0 + (size_t)t * fs + (size_t)r * L.W;
+                uint32_t w[2] = {0, 0};
+                if (valid) {
+                    if (C == 8) { const uint2 v = __ldg(reinterpret_cast<const uint2 *>(src)); w[0] = v.x; w[1] = v.y; }
+                    else w[0] = __ldg(reinterpret_cast<const uint32_t *>(src));
+                }
+#pragma unroll
+                for (int x = 0; x < C; x++) b[t][x] = (double)((w[x / 4] >> (8 * (x % 4))) & 0xffu);
+            }
+            fwd_t<C, double>(b);
+            Xch<C, double>::transpose(xbuf, cl, r, b, a);
+            fwd_xy<C, double>(a);
+            if (valid) {
+                int16_t *dst = q_out + (size_t)cube * G::CS + (size_t)r * C * C;
+#pragma unroll
+                for (int k1 = 0; k1 < C; k1++) {
+                    uint32_t w[C / 2];
+#pragma unroll
+                    for (int k2 = 0; k2 < C; k2++) {
+                        const double v = a[k1][k2] / (double)quant_divisor(r + k1 + k2);
+                        const double q = rounding ? (v < 0 ? -floor(-v + 0.5) : floor(v + 0.5)) : floor(v + 0.5);
+                        const uint32_t h = (uint32_t)(int)fmax(-32768.0, fmin(32767.0, q)) & 0xffffu;
+                        if (k2 & 1) w[k2 / 2] |= h << 16; else w[k2 / 2] = h;
+                    }
+                    if (C == 8) *reinterpret_cast<uint4 *>(dst + k1 * C) = make_uint4(w[0], w[1], w[2 % (C / 2)], w[3 % (C / 2)]);
+                    else *reinterpret_cast<uint2 *>(dst + k1 * C) = make_uint2(w[0], w[1]);
+                }
+            }
         } else {
-            planar[at] = (double)q[i] * d;
+            // thread = k1: b[k0][k2] = q * d; t pass, exchange, thread = frame t: a[y][x]; y and x passes; clamp, truncate
+            const int16_t *src = q_in + (size_t)cc * G::CS + (size_t)r * C;
+#pragma unroll
+            for (int k0 = 0; k0 < C; k0++) {
+                uint32_t w[4] = {0, 0, 0, 0};
+                if (valid) {
+                    if (C == 8) { const uint4 v = __ldg(reinterpret_cast<const uint4 *>(src + k0 * C * C)); w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w; }
+                    else { const uint2 v = __ldg(reinterpret_cast<const uint2 *>(src + k0 * C * C)); w[0] = v.x; w[1] = v.y; }
+                }
+#pragma unroll
+                for (int k2 = 0; k2 < C; k2++) {
+                    const int q = (int)(int16_t)((w[k2 / 2] >> ((k2 & 1) * 16)) & 0xffffu);
+                    b[k0][k2] = (double)q * (double)quant_divisor(k0 + r + k2);
+                }
+            }
+            inv_t<C, double>(b);
+            Xch<C, double>::transpose(xbuf, cl, r, b, a);
+            inv_yx<C, double>(a);
+            if (valid) {
+                uint8_t *dst = frames_out + pix0 + (size_t)r * fs;
+#pragma unroll
+                for (int y = 0; y < C; y++) {
+                    uint32_t w[2] = {0, 0};
+#pragma unroll
+                    for (int x = 0; x < C; x++) {
+                        const double v = a[y][x];
+                        const double c = v > 255.0 ? 255.0 : (v < 0.0 ? 0.0 : v);
+                        w[x / 4] |= ((uint32_t)(int)c & 0xffu) << (8 * (x % 4));
+                    }
+                    if (C == 8) *reinterpret_cast<uint2 *>(dst + (size_t)y * L.W) = make_uint2(w[0], w[1]);
+                    else *reinterpret_cast<uint32_t *>(dst + (size_t)y * L.W) = w[0];
+                }
+            }
         }
     }
 }
