@@ -1019,7 +1019,9 @@ constexpr int kRing = 3;
 
 // Codes host frames into ctx->bits from bit 0.  With `out` the finished bytes flow back to the host beside the following
 // chunks and out[0 .. *nbits/8] is the complete stream; without it the stream stays on the device (dct3d_encode_u8_range).
-static int pipe_encode(dct3d_ctx *ctx, const uint8_t *frames, int nframes, size_t dcap, uint8_t *out, size_t cap, uint64_t *nbits)
+// start_bit (0..7) / first_byte: the stream continues a partial byte carried over from an earlier call (dct3d_stream_encode).
+static int pipe_encode(dct3d_ctx *ctx, const uint8_t *frames, int nframes, size_t dcap, uint8_t *out, size_t cap, uint64_t *nbits,
+                       unsigned start_bit = 0, uint8_t first_byte = 0)
 {
     int rc;
     const int C = ctx->C, nslabs = nframes / C;
@@ -1029,13 +1031,19 @@ static int pipe_encode(dct3d_ctx *ctx, const uint8_t *frames, int nframes, size_
     CU_CHECK(ctx, ctx->bits.reserve(dcap));
     const int K = chunk_slabs(ctx, nslabs), nchunks = nslabs ? (nslabs + K - 1) / K : 0;
     ctx->chunks_last = nchunks;
+    // the carried partial byte becomes byte 0 of the device buffer
+    CU_CHECK(ctx, cudaMemsetAsync(ctx->bits.p, 0, 4, st));
+    if (start_bit) {
+        ctx->h_byte[0] = first_byte;
+        CU_CHECK(ctx, cudaMemcpyAsync(ctx->bits.p, ctx->h_byte, 1, cudaMemcpyHostToDevice, st));
+    }
     if (nchunks <= 1 || ctx->precision == 64) {
         // one shot: a single chunk, or the fp64 mode (whose packer is not chained)
         const size_t n = slab_bytes * nslabs;
         CU_CHECK(ctx, ctx->ring[0].reserve(n + 16));
         if (n) H2D(ctx, ctx->ring[0].p, frames, n);
         uint64_t end = 0;
-        if ((rc = dct3d_encode_u8_dev(ctx, ctx->ring[0].p, nframes, ctx->bits.p, dcap, 0, &end, nullptr))) return rc;
+        if ((rc = dct3d_encode_u8_dev(ctx, ctx->ring[0].p, nframes, ctx->bits.p, dcap, start_bit, &end, nullptr))) return rc;
         if (out) {
             const size_t nb = (size_t)(end / 8) + 1;
             if (nb > cap) return fail(ctx, DCT3D_E_OVERFLOW, "stream needs %zu bytes, buffer has %zu", nb, cap);
@@ -1065,7 +1073,11 @@ static int pipe_encode(dct3d_ctx *ctx, const uint8_t *frames, int nframes, size_
     auto ev = [&](int i, int what) { return pipe_event(ctx, (size_t)3 * i + what); };   // 0: chunk on the device, 1: chunk coded, 2: its end bit on the host
     if (!ev(nchunks - 1, 2)) return fail(ctx, DCT3D_E_CUDA, "cudaEventCreate failed");
     CU_CHECK(ctx, cudaMemsetAsync(ctx->chain.p, 0, nslots * 8, st));
-    if ((rc = zero_stream(ctx, ctx->bits.p, dcap, 0, st))) return rc;
+    if (start_bit) {
+        ctx->h_chain[0] = start_bit;
+        CU_CHECK(ctx, cudaMemcpyAsync(ctx->chain.p, ctx->h_chain, 8, cudaMemcpyHostToDevice, st));
+    }
+    if ((rc = zero_stream(ctx, ctx->bits.p, dcap, start_bit, st))) return rc;
 
     size_t sent = 0;
     auto drain = [&](int j, bool last) -> int {                  // bytes that chunk j completed go home
@@ -1512,24 +1524,18 @@ int dct3d_stream_encode(dct3d_ctx *ctx, const uint8_t *frames, int nframes, int 
     if ((rc = check_frames(ctx, nframes))) return rc;
     if (nframes % ctx->C) return fail(ctx, DCT3D_E_INVALID, "streaming encode needs a multiple of %d frames", ctx->C);
     if (!out) return fail(ctx, DCT3D_E_INVALID, "null output buffer");
-    const size_t n = frame_bytes(ctx, nframes);
+    if (frame_bytes(ctx, nframes) && !frames) return fail(ctx, DCT3D_E_INVALID, "null frame pointer");
     const size_t dcap = ((cap + 3) & ~(size_t)3) + 64;
-    CU_CHECK(ctx, ctx->frames.reserve(n + 16));
-    CU_CHECK(ctx, ctx->bits.reserve(dcap));
-    // the carried partial byte becomes byte 0 of the device buffer
-    CU_CHECK(ctx, cudaMemsetAsync(ctx->bits.p, 0, 4, ctx->stream));
-    CU_CHECK(ctx, cudaMemcpyAsync(ctx->bits.p, &ctx->carry_byte, 1, cudaMemcpyHostToDevice, ctx->stream));
-    if (n) H2D(ctx, ctx->frames.p, frames, n);
+    // any number of slabs per call: they flow through the chunk pipeline (pipe_encode) and continue the carried byte
     uint64_t end = 0;
-    if ((rc = dct3d_encode_u8_dev(ctx, ctx->frames.p, nframes, ctx->bits.p, dcap, (uint64_t)ctx->carry_bits, &end, nullptr))) return rc;
+    if ((rc = pipe_encode(ctx, frames, nframes, dcap, nullptr, 0, &end, (unsigned)ctx->carry_bits, ctx->carry_byte))) return rc;
     const size_t full = (size_t)(end / 8);
     const size_t give = last ? full + 1 : full;
     if (give > cap) return fail(ctx, DCT3D_E_OVERFLOW, "stream needs %zu bytes, buffer has %zu", give, cap);
     if (give) D2H(ctx, out, ctx->bits.p, give);
-    uint8_t tail = 0;
-    CU_CHECK(ctx, cudaMemcpyAsync(&tail, (uint8_t *)ctx->bits.p + full, 1, cudaMemcpyDeviceToHost, ctx->stream));
+    D2H(ctx, ctx->h_byte + 8, (uint8_t *)ctx->bits.p + full, 1);
     SYNC(ctx);
-    ctx->carry_byte = last ? 0 : tail;
+    ctx->carry_byte = last ? 0 : ctx->h_byte[8];
     ctx->carry_bits = last ? 0 : (int)(end % 8);
     if (nbytes) *nbytes = give;
     return DCT3D_OK;
@@ -1541,19 +1547,13 @@ int dct3d_stream_decode(dct3d_ctx *ctx, const uint8_t *in, size_t nbytes, uint64
     if (rc) return rc;
     if ((rc = check_frames(ctx, nframes))) return rc;
     if (!bitpos) return fail(ctx, DCT3D_E_INVALID, "null bit position");
-    const size_t n = frame_bytes(ctx, nframes);
-    if (n == 0) return DCT3D_OK;
+    if (frame_bytes(ctx, nframes) == 0) return DCT3D_OK;
     if (!in || !frames) return fail(ctx, DCT3D_E_INVALID, "null pointer");
-    const size_t padded = ((nbytes + 3) & ~(size_t)3) + 8;
-    CU_CHECK(ctx, ctx->bits.reserve(padded));
-    CU_CHECK(ctx, ctx->frames.reserve(n + 16));
-    CU_CHECK(ctx, cudaMemsetAsync((uint8_t *)ctx->bits.p + (nbytes & ~(size_t)3), 0, padded - (nbytes & ~(size_t)3), ctx->stream));
-    H2D(ctx, ctx->bits.p, in, nbytes);
+    if ((uint64_t)nbytes * 8 <= *bitpos) return fail(ctx, DCT3D_E_NEED_MORE, "stream holds no data past the start bit");
+    const size_t byte0 = (size_t)(*bitpos / 8);
     uint64_t end = 0;
-    if ((rc = dct3d_decode_u8_dev(ctx, ctx->bits.p, nbytes, *bitpos, nframes, ctx->frames.p, &end, nullptr))) return rc;
-    D2H(ctx, frames, ctx->frames.p, n);
-    SYNC(ctx);
-    *bitpos = end;
+    if ((rc = pipe_decode(ctx, in + byte0, nbytes - byte0, *bitpos % 8, nframes, frames, &end))) return rc;   // DCT3D_E_NEED_MORE changes nothing
+    *bitpos = (uint64_t)byte0 * 8 + end;
     return DCT3D_OK;
 }
 
