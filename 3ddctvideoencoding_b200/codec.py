@@ -344,6 +344,29 @@ class MultiCodec:
         self._check(self.L.dct3d_multi_encode_u8(self.h, _ptr(fr), F, _ptr(out), cap, C.byref(nbits), C.byref(nbytes), starts))
         return out[: nbytes.value], nbits.value, list(starts)
 
+    def stream_begin(self):
+        self._check(self.L.dct3d_multi_stream_begin(self.h))
+
+    def stream_encode(self, frames: np.ndarray, last: bool, cap: int | None = None) -> np.ndarray:
+        fr = np.ascontiguousarray(frames, np.uint8)
+        F = fr.size // (self.width * self.height)
+        cap = cap or (fr.size // 2 + 4096)
+        out = np.zeros(cap, np.uint8)
+        n = C.c_size_t()
+        self._check(self.L.dct3d_multi_stream_encode(self.h, _ptr(fr), F, 1 if last else 0, _ptr(out), cap, C.byref(n)))
+        return out[: n.value]
+
+    def stream_decode(self, buf, bitpos: int, nframes: int):
+        """-> (frames, new bitpos) or None when more input is needed."""
+        s = np.ascontiguousarray(buf, np.uint8)
+        out = np.zeros((nframes - nframes % self.cube, self.height, self.width), np.uint8)
+        bp = C.c_uint64(bitpos)
+        rc = self.L.dct3d_multi_stream_decode(self.h, _ptr(s), s.size, C.byref(bp), nframes, _ptr(out))
+        if rc == _lib.E_NEED_MORE:
+            return None
+        self._check(rc)
+        return out, bp.value
+
     def locate(self, stream, nframes: int):
         s = stream if not isinstance(stream, np.ndarray) else np.ascontiguousarray(stream, np.uint8)
         starts = (C.c_uint64 * (self.n + 1))()

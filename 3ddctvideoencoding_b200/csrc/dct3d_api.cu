@@ -85,12 +85,15 @@ struct dct3d_ctx {
     DevBuf ring[3];                  // frame chunks in flight
     DevBuf chain;                    // u64 bit positions between chunks + the chain's error word
     DevBuf bits2;                    // a range's stream moved to its phase (dct3d_encode_u8_place)
-    unsigned long long *h_chain = nullptr;   // pinned mirror of the chain slots
+    unsigned long long *h_chain = nullptr;   // mapped page-locked mirror of the chain slots, written by the packer itself
+    unsigned long long *h_chain_dev = nullptr;   // its device address
     size_t h_chain_n = 0;
     uint8_t *h_byte = nullptr;       // pinned scratch (the first byte of a placed range)
     uint64_t range_bits = 0;         // bit count of the range held in `bits` (dct3d_encode_u8_range)
     bool range_valid = false;
     long chunks_last = 0;            // statistics: pipeline chunks of the last host-buffer call
+    DecParams part_P;                // segment arrays of the last count-only pass over a stream part (part_locate)
+    bool part_valid = false;
 };
 
 namespace {
@@ -551,8 +554,8 @@ int codec_f64(dct3d_ctx *ctx, const void *d_in, int nslabs, void *d_out, cudaStr
     const int16_t *qin = INVERSE ? (const int16_t *)d_in : nullptr;
     int16_t *qout = INVERSE ? nullptr : (int16_t *)d_out;
     uint8_t *fout = INVERSE ? (uint8_t *)d_out : nullptr;
-    if (C == 8) codec_f64_kernel<8, INVERSE><<<(unsigned)grid, kThreads, kWarps * Xch<8, double>::WARP_BYTES, st>>>(L, fin, qout, qin, fout, ctx->rounding);
-    else codec_f64_kernel<4, INVERSE><<<(unsigned)grid, kThreads, kWarps * Xch<4, double>::WARP_BYTES, st>>>(L, fin, qout, qin, fout, ctx->rounding);
+    if (C == 8) codec_f64_kernel<8, INVERSE><<<(unsigned)grid, kThreads, kWarps * Xch<8, double>::WARP_BYTES + 256, st>>>(L, fin, qout, qin, fout, ctx->rounding);
+    else codec_f64_kernel<4, INVERSE><<<(unsigned)grid, kThreads, kWarps * Xch<4, double>::WARP_BYTES + 256, st>>>(L, fin, qout, qin, fout, ctx->rounding);
     ctx->launches++;
     CU_CHECK(ctx, cudaGetLastError());
     return DCT3D_OK;
@@ -573,6 +576,7 @@ static int reconstruct_f64(dct3d_ctx *ctx, const void *d_q, int nslabs, void *d_
 struct Chain {
     const unsigned long long *d_start = nullptr;   // the packer reads its start bit here ...
     unsigned long long *d_end = nullptr;           // ... and leaves its end bit here
+    unsigned long long *h_end = nullptr;           // ... and here (device address of mapped host memory), for the host
     unsigned int *d_err = nullptr;                 // sticky error word of the whole chain (not reset per call)
 };
 
@@ -588,7 +592,7 @@ static int run_pack_noreset(dct3d_ctx *ctx, EncParams &P, void *d_stream, size_t
     P.start_bit = start_bit;
     P.tile_status = status_words(ctx);
     P.ticket = &dc->ticket; P.err = &dc->err; P.end_bit = &dc->end_bit;
-    if (chain) { P.start_bit_dev = chain->d_start; P.end_bit = chain->d_end; P.err = chain->d_err; }
+    if (chain) { P.start_bit_dev = chain->d_start; P.end_bit = chain->d_end; P.end_bit_host = chain->h_end; P.err = chain->d_err; }
     int &occ = ctx->occ_cache[4];
     if (occ == 0) {
         if (ctx->C == 8) CU_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, eg_pack_kernel<8>, kPackThreads, 0));
@@ -742,8 +746,19 @@ int dct3d_eg_encode_i16_dev(dct3d_ctx *ctx, const void *d_qcubes, size_t ncubes,
 // control block, so the GPU does not idle for a host round trip between index discovery and the inverse transform.  In
 // the rare case that the fix-up rounds had not converged, or the stream is damaged, the tail has run on inconsistent
 // (but bounds-safe) lists: it is run again after convergence, or the call fails and the output is unspecified.
+// `part` (optional): count-only pass over a PART of a stream, bits [start_bit, part->count_end_bit), for the distributed
+// index discovery of dct3d_multi_locate: no lists are emitted; the segment arrays stay in the context for part_locate().
+struct PartOpts {
+    uint64_t count_end_bit = 0;   // codes that start before this bit are counted
+    int first_entry = 0;          // DecParams::first_entry
+    uint64_t ncodes = 0;          // out: codes that start in the part
+    uint32_t over_out = 0;        // out: how far the last of them runs past count_end_bit
+    uint32_t entry_used = 0;      // out: entry point of the part's first segment
+};
+
 static int parse_common(dct3d_ctx *ctx, const void *d_stream, size_t nbytes, uint64_t start_bit, size_t ncubes,
-                        uint64_t *end_bit, cudaStream_t st, bool locate_only = false, const std::function<int()> *tail = nullptr)
+                        uint64_t *end_bit, cudaStream_t st, bool locate_only = false, const std::function<int()> *tail = nullptr,
+                        PartOpts *part = nullptr)
 {
     int rc;
     const int C = ctx->C, CS = C * C * C;
@@ -758,7 +773,11 @@ static int parse_common(dct3d_ctx *ctx, const void *d_stream, size_t nbytes, uin
     P.nbits_total = (unsigned long long)nbytes * 8;
     P.start_bit = start_bit;
     P.seg_bits = kSegWords * 32;
-    P.nseg = (P.nbits_total - start_bit + P.seg_bits - 1) / P.seg_bits;
+    P.count_end_bit = part ? std::min<unsigned long long>(part->count_end_bit, P.nbits_total) : P.nbits_total;
+    P.first_entry = part ? part->first_entry : 0;
+    if (part && (P.count_end_bit <= start_bit || (part->first_entry < 0 && start_bit < 128)))
+        return fail(ctx, DCT3D_E_INVALID, "bad stream part");
+    P.nseg = (P.count_end_bit - start_bit + P.seg_bits - 1) / P.seg_bits;
     // seg arrays: count[nseg] over[nseg+1] used[nseg] work[nseg] (u32) first[nseg+1] nzfirst[nseg+1] (u64)
     const size_t n = (size_t)P.nseg;
     const size_t off_first = ((4 * n + 1) * 4 + 7) & ~(size_t)7;
@@ -766,7 +785,7 @@ static int parse_common(dct3d_ctx *ctx, const void *d_stream, size_t nbytes, uin
     CU_CHECK(ctx, ctx->seglist.reserve(((n + 31) / 32) * 32 * kSegListVec * sizeof(uint4)));   // dense-addressed, only the heads are touched
     const long long stiles = (long long)((P.nseg + kScanThreads * kScanItems - 1) / (kScanThreads * kScanItems));
     CU_CHECK(ctx, ctx->ctrl.reserve(kCtrlBytes + (size_t)stiles * 16));
-    if (!locate_only) {
+    if (!locate_only && !part) {
         CU_CHECK(ctx, ctx->coo.reserve(ncubes * CS * sizeof(uint32_t) + 2048));   // worst case: every coefficient non-zero, + the tail of the last segment's list
         CU_CHECK(ctx, ctx->coocnt.reserve((ncubes + 1) * 8));
     }
@@ -799,6 +818,7 @@ static int parse_common(dct3d_ctx *ctx, const void *d_stream, size_t nbytes, uin
         }
         const long long grid = std::min<long long>(stiles, (long long)ctx->num_sms * 8);
         seg_prefix_kernel<<<(unsigned)grid, kScanThreads, 0, st>>>(P, status_words(ctx), status_words(ctx) + stiles, &dc->ticket);
+        if (part) { ctx->launches++; CU_CHECK(ctx, cudaGetLastError()); return DCT3D_OK; }
         const unsigned pg = (unsigned)std::min<unsigned long long>((P.nseg + kEmitThreads - 1) / kEmitThreads, (unsigned long long)ctx->num_sms * 12);
         if (C == 8) seg_emit_kernel<8><<<pg, kEmitThreads, 0, st>>>(P); else seg_emit_kernel<4><<<pg, kEmitThreads, 0, st>>>(P);
         ctx->launches += 2;
@@ -810,7 +830,14 @@ static int parse_common(dct3d_ctx *ctx, const void *d_stream, size_t nbytes, uin
     // the pipeline follows, and the host checks ONCE at the end whether the second round still moved an
     // overhang; only then (the constructed worst case) it iterates to convergence and redoes prefix + emit.
     if ((rc = fix_round()) || (rc = fix_round()) || (rc = prefix_and_parse())) return rc;
+    auto fetch_part = [&]() -> int {
+        if (!part) return DCT3D_OK;
+        CU_CHECK(ctx, cudaMemcpyAsync(ctx->h_u64 + 1, P.seg_over + n, 4, cudaMemcpyDeviceToHost, st));
+        CU_CHECK(ctx, cudaMemcpyAsync(ctx->h_u64 + 2, P.seg_used, 4, cudaMemcpyDeviceToHost, st));
+        return DCT3D_OK;
+    };
     CU_CHECK(ctx, cudaMemcpyAsync(ctx->h_u64, P.seg_first + n, 8, cudaMemcpyDeviceToHost, st));
+    if ((rc = fetch_part())) return rc;
     CU_CHECK(ctx, cudaMemcpyAsync(ctx->h_ctrl, ctx->ctrl.p, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
     CU_CHECK(ctx, cudaEventRecord(ctx->ev_ctrl, st));
     if (tail && (rc = (*tail)())) return rc;
@@ -823,9 +850,20 @@ static int parse_common(dct3d_ctx *ctx, const void *d_stream, size_t nbytes, uin
         CU_CHECK(ctx, cudaMemsetAsync(&dc->err, 0, 4, st));
         if ((rc = prefix_and_parse())) return rc;
         CU_CHECK(ctx, cudaMemcpyAsync(ctx->h_u64, P.seg_first + n, 8, cudaMemcpyDeviceToHost, st));
+        if ((rc = fetch_part())) return rc;
         if ((rc = fetch_ctrl(ctx, st))) return rc;
         if (tail && (rc = (*tail)())) return rc;                 // again, on the converged lists
     }
+    if (part) {
+        if (ctx->h_ctrl->err & 2u) return fail(ctx, DCT3D_E_STREAM, "malformed Exp-Golomb code in stream");
+        part->ncodes = ctx->h_u64[0];
+        part->over_out = (uint32_t)ctx->h_u64[1];
+        part->entry_used = (uint32_t)ctx->h_u64[2];
+        ctx->part_P = P;
+        ctx->part_valid = true;
+        return DCT3D_OK;
+    }
+    ctx->part_valid = false;
     if (ctx->h_u64[0] < (unsigned long long)ncubes * CS)
         return fail(ctx, DCT3D_E_NEED_MORE, "stream holds %llu codes, %llu needed", ctx->h_u64[0], (unsigned long long)ncubes * CS);
     if (ctx->h_ctrl->err & 2u) return fail(ctx, DCT3D_E_STREAM, "malformed Exp-Golomb code in stream");
@@ -1065,13 +1103,16 @@ static int pipe_encode(dct3d_ctx *ctx, const uint8_t *frames, int nframes, size_
     if (ctx->h_chain_n < nslots) {
         if (ctx->h_chain) cudaFreeHost(ctx->h_chain);
         ctx->h_chain = nullptr; ctx->h_chain_n = 0;
-        CU_CHECK(ctx, cudaMallocHost((void **)&ctx->h_chain, (nslots + 64) * 8));
+        CU_CHECK(ctx, cudaHostAlloc((void **)&ctx->h_chain, (nslots + 64) * 8, cudaHostAllocMapped));
+        CU_CHECK(ctx, cudaHostGetDevicePointer((void **)&ctx->h_chain_dev, ctx->h_chain, 0));
         ctx->h_chain_n = nslots + 64;
     }
     unsigned long long *d_chain = (unsigned long long *)ctx->chain.p;
     unsigned int *d_err = (unsigned int *)(d_chain + nchunks + 1);
-    auto ev = [&](int i, int what) { return pipe_event(ctx, (size_t)3 * i + what); };   // 0: chunk on the device, 1: chunk coded, 2: its end bit on the host
-    if (!ev(nchunks - 1, 2)) return fail(ctx, DCT3D_E_CUDA, "cudaEventCreate failed");
+    // The end bit of every chunk reaches the host through mapped memory, written by the packer: a D2H copy of 8 bytes would
+    // queue behind whatever else the copy engine is doing (another context's frame copies) and stall this thread.
+    auto ev = [&](int i, int what) { return pipe_event(ctx, (size_t)2 * i + what); };   // 0: chunk on the device, 1: chunk coded
+    if (!ev(nchunks - 1, 1)) return fail(ctx, DCT3D_E_CUDA, "cudaEventCreate failed");
     CU_CHECK(ctx, cudaMemsetAsync(ctx->chain.p, 0, nslots * 8, st));
     if (start_bit) {
         ctx->h_chain[0] = start_bit;
@@ -1081,7 +1122,7 @@ static int pipe_encode(dct3d_ctx *ctx, const uint8_t *frames, int nframes, size_
 
     size_t sent = 0;
     auto drain = [&](int j, bool last) -> int {                  // bytes that chunk j completed go home
-        CU_CHECK(ctx, cudaEventSynchronize(ev(j, 2)));
+        CU_CHECK(ctx, cudaEventSynchronize(ev(j, 1)));
         const size_t full = (size_t)(ctx->h_chain[j + 1] / 8), give = last ? full + 1 : full;
         if (give > cap) return fail(ctx, DCT3D_E_OVERFLOW, "stream needs %zu bytes, buffer has %zu", give, cap);
         if (give > sent) CU_CHECK(ctx, cudaMemcpyAsync(out + sent, (const uint8_t *)ctx->bits.p + sent, give - sent, cudaMemcpyDeviceToHost, ctx->s_d2h));
@@ -1095,20 +1136,25 @@ static int pipe_encode(dct3d_ctx *ctx, const uint8_t *frames, int nframes, size_
             CU_CHECK(ctx, cudaMemcpyAsync(ctx->ring[b].p, frames + (size_t)s0 * slab_bytes, (size_t)ns * slab_bytes, cudaMemcpyHostToDevice, ctx->s_h2d));
             CU_CHECK(ctx, cudaEventRecord(ev(i, 0), ctx->s_h2d));
             CU_CHECK(ctx, cudaStreamWaitEvent(st, ev(i, 0), 0));
-            const Chain ch{d_chain + i, d_chain + i + 1, d_err};
+            const Chain ch{d_chain + i, d_chain + i + 1, ctx->h_chain_dev + i + 1, d_err};
             if ((rc = encode_common(ctx, ctx->ring[b].p, ns * C, ctx->bits.p, dcap, 0, nullptr, st, nullptr, &ch))) return rc;
+            if (i == nchunks - 1)                                // the chain's error word follows the last chunk home
+                CU_CHECK(ctx, cudaMemcpyAsync(ctx->h_chain + nchunks + 1, d_err, 8, cudaMemcpyDeviceToHost, st));
             CU_CHECK(ctx, cudaEventRecord(ev(i, 1), st));
-            CU_CHECK(ctx, cudaStreamWaitEvent(ctx->s_d2h, ev(i, 1), 0));
-            CU_CHECK(ctx, cudaMemcpyAsync(ctx->h_chain + i + 1, d_chain + i + 1, i == nchunks - 1 ? 16 : 8, cudaMemcpyDeviceToHost, ctx->s_d2h));   // the last one brings the error word along
-            CU_CHECK(ctx, cudaEventRecord(ev(i, 2), ctx->s_d2h));
-            if (out && i >= 1 && (rc = drain(i - 1, false))) return rc;
+            if (out && i >= 1) {
+                CU_CHECK(ctx, cudaStreamWaitEvent(ctx->s_d2h, ev(i - 1, 1), 0));
+                if ((rc = drain(i - 1, false))) return rc;
+            }
         }
-        CU_CHECK(ctx, cudaEventSynchronize(ev(nchunks - 1, 2)));
+        CU_CHECK(ctx, cudaEventSynchronize(ev(nchunks - 1, 1)));
         const unsigned int err = (unsigned int)ctx->h_chain[nchunks + 1];
         if (err & 16u) return fail(ctx, DCT3D_E_CUDA, "TMA tile load timed out");
         if (err & 8u) return fail(ctx, DCT3D_E_CUDA, "tile look-back timed out");
         if (err & 1u) return fail(ctx, DCT3D_E_OVERFLOW, "stream buffer of %zu bytes is too small", dcap);
-        if (out && (rc = drain(nchunks - 1, true))) return rc;
+        if (out) {
+            CU_CHECK(ctx, cudaStreamWaitEvent(ctx->s_d2h, ev(nchunks - 1, 1), 0));
+            if ((rc = drain(nchunks - 1, true))) return rc;
+        }
         CU_CHECK(ctx, cudaStreamSynchronize(ctx->s_d2h));
         return DCT3D_OK;
     };
@@ -1315,6 +1361,8 @@ struct dct3d_multi {
     std::vector<dct3d_ctx *> ctx;
     int W = 0, H = 0, C = 8;
     std::string err;
+    uint8_t carry_byte = 0;          // streaming state (dct3d_multi_stream_*), as in dct3d_ctx
+    int carry_bits = 0;
 };
 
 namespace {
@@ -1450,29 +1498,134 @@ int dct3d_multi_encode_u8(dct3d_multi *m, const uint8_t *frames, int nframes, ui
     return DCT3D_OK;
 }
 
-int dct3d_multi_locate(dct3d_multi *m, const uint8_t *stream, size_t nbytes, int nframes, uint64_t *range_start_bits)
+// ---- distributed index discovery -----------------------------------------------------------------------------------
+// The format stores no index (J/ExpGolombReader.java:19-63 is the only way the reference knows where a code starts), so a
+// GPU that is to decode slab range g of a stream it did not code has to find the range's first bit.  Instead of every GPU
+// scanning the stream in front of its range (G/2 times the stream in total), the BYTES of the stream are cut into G equal
+// parts, GPU g counts the codes that start in part g (scan from a guessed entry point, fix-up, prefix: the decoder's own
+// index discovery without the emit step), the G counts and overhangs meet on the host, where every part's entry guess is
+// checked against its predecessor's overhang (a wrong guess -- rare -- is recounted from the verified entry), and the
+// first code of every slab range is then located inside the one part that holds it.  One pass over the stream in total,
+// G + G scalars through the host, no collective.
+
+namespace {
+
+// Count the codes of stream bits [part_lo, part_hi) on ctx's GPU.  entry < 0: guess the entry point (part in mid-stream).
+int part_count(dct3d_ctx *ctx, const uint8_t *stream, size_t nbytes, uint64_t part_lo, uint64_t part_hi, int entry,
+               PartOpts &po, uint64_t &window_bit0)
 {
-    if (!m || !range_start_bits) return mfail(m, DCT3D_E_INVALID, "null argument");
+    int rc = bind(ctx);
+    if (rc) return rc;
+    // window: 16 bytes in front of the part (the lead-in walk of the entry guess) and 16 behind (codes that overhang), word aligned
+    const size_t lead = entry == 0 ? 0 : 16;
+    size_t wb0 = (size_t)(part_lo / 8);
+    wb0 = wb0 >= lead ? wb0 - lead : 0;
+    wb0 &= ~(size_t)3;
+    const size_t wb1 = std::min<size_t>(nbytes, (size_t)((part_hi + 7) / 8) + 16);
+    const size_t wn = wb1 - wb0, padded = ((wn + 3) & ~(size_t)3) + 8;
+    ctx->range_valid = false;
+    ctx->clean_ptr = nullptr;
+    CU_CHECK(ctx, ctx->bits.reserve(padded));
+    CU_CHECK(ctx, cudaMemsetAsync((uint8_t *)ctx->bits.p + (wn & ~(size_t)3), 0, padded - (wn & ~(size_t)3), ctx->stream));
+    H2D(ctx, ctx->bits.p, stream + wb0, wn);
+    window_bit0 = (uint64_t)wb0 * 8;
+    po.count_end_bit = part_hi - window_bit0;
+    po.first_entry = entry;
+    return parse_common(ctx, ctx->bits.p, wn, part_lo - window_bit0, 0, nullptr, ctx->stream, false, nullptr, &po);
+}
+
+// Bit (relative to the window of the last part_count) at which code number `target` of the part starts.
+int part_locate(dct3d_ctx *ctx, uint64_t target, uint64_t *bit)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (!ctx->part_valid) return fail(ctx, DCT3D_E_INVALID, "no counted stream part");
+    Ctrl *dc = (Ctrl *)ctx->ctrl.p;
+    seg_locate_kernel<<<1, 32, 0, ctx->stream>>>(ctx->part_P, target, &dc->end_bit);
+    ctx->launches++;
+    CU_CHECK(ctx, cudaGetLastError());
+    if ((rc = fetch_ctrl(ctx, ctx->stream))) return rc;
+    if (ctx->h_ctrl->err & 2u) return fail(ctx, DCT3D_E_STREAM, "malformed Exp-Golomb code in stream");
+    *bit = ctx->h_ctrl->end_bit;
+    return DCT3D_OK;
+}
+
+// Start bit of every slab range of the `nframes` frames whose first code is at bit `start_bit` of `stream`.
+// sb[0] = start_bit, sb[G] = 0 (unknown: the last range ends where its decoder says).  DCT3D_E_NEED_MORE when the
+// buffered bytes do not hold the first code of every range yet.
+int multi_discover(dct3d_multi *m, const uint8_t *stream, size_t nbytes, uint64_t start_bit, int nframes, uint64_t *sb)
+{
     const int G = (int)m->ctx.size(), C = m->C, nslabs = nframes / C;
-    const size_t cubes_per_slab = (size_t)(m->W / C) * (m->H / C);
+    const uint64_t codes_per_slab = (uint64_t)(m->W / C) * (m->H / C) * C * C * C;
+    for (int g = 0; g <= G; g++) sb[g] = 0;
+    sb[0] = start_bit;
+    if (G == 1 || nslabs == 0) return DCT3D_OK;
+    const uint64_t total_bits = (uint64_t)nbytes * 8;
+    if (total_bits <= start_bit) return mfail(m, DCT3D_E_NEED_MORE, "stream holds no data past the start bit");
+    std::vector<int> lo(G + 1, nslabs);
+    for (int g = 0; g < G; g++) { int hi; slab_range(nslabs, g, G, lo[g], hi); }
     std::vector<int> rcs(G, 0);
-    std::vector<uint64_t> sb(G + 1, 0);
-    // every GPU g > 0 finds the first bit of its own range: index discovery over the stream in front of it
-    auto work = [&](int g) {
-        int lo, hi;
-        slab_range(nslabs, g, G, lo, hi);
-        if (lo == 0) { sb[g] = 0; return; }
-        rcs[g] = dct3d_eg_locate(m->ctx[g], stream, nbytes, 0, (size_t)lo * cubes_per_slab, &sb[g]);
-    };
-    std::vector<std::thread> th;
-    for (int g = 2; g < G; g++) th.emplace_back(work, g);
-    if (G > 1) work(1);
-    for (auto &t : th) t.join();
+    const uint64_t span = total_bits - start_bit;
+    if (span < (uint64_t)G * (1u << 19)) {
+        // a small stream: every GPU g > 0 simply scans from the start bit to its own range (dct3d_eg_locate)
+        const size_t byte0 = (size_t)(start_bit / 8);
+        auto work = [&](int g) {
+            if (lo[g] == 0) { sb[g] = start_bit; return; }
+            uint64_t e = 0;
+            rcs[g] = dct3d_eg_locate(m->ctx[g], stream + byte0, nbytes - byte0, start_bit % 8, (size_t)(lo[g] * (codes_per_slab / (C * C * C))), &e);
+            if (rcs[g] == DCT3D_E_STREAM && strstr(m->ctx[g]->err.c_str(), "truncated")) rcs[g] = DCT3D_E_NEED_MORE;
+            sb[g] = (uint64_t)byte0 * 8 + e;
+        };
+        std::vector<std::thread> th;
+        for (int g = 2; g < G; g++) th.emplace_back(work, g);
+        work(1);
+        for (auto &t : th) t.join();
+        return first_failure(m, rcs);
+    }
+    // ---- phase 1: every GPU counts its part of the bytes ----------------------------------------------------------
+    std::vector<uint64_t> plo(G + 1), win0(G, 0);
+    for (int g = 0; g <= G; g++) plo[g] = g == 0 ? start_bit : g == G ? total_bits : ((start_bit + span * g / G) & ~(uint64_t)31);
+    std::vector<PartOpts> po(G);
+    auto count = [&](int g, int entry) { rcs[g] = part_count(m->ctx[g], stream, nbytes, plo[g], plo[g + 1], entry, po[g], win0[g]); };
+    {
+        std::vector<std::thread> th;
+        for (int g = 1; g < G; g++) th.emplace_back(count, g, -1);
+        count(0, 0);
+        for (auto &t : th) t.join();
+    }
     int rc = first_failure(m, rcs);
     if (rc) return rc;
-    sb[G] = 0;                                                   // unknown: the last range ends where the clip ends
-    for (int g = 0; g <= G; g++) range_start_bits[g] = sb[g];
+    // ---- phase 2: the guesses against the predecessors' overhangs (a recount moves the part's own overhang: in order) -----
+    for (int g = 1; g < G; g++) {
+        if (po[g].entry_used == po[g - 1].over_out) continue;
+        count(g, (int)po[g - 1].over_out + 1);
+        if ((rc = first_failure(m, rcs))) return rc;
+    }
+    std::vector<uint64_t> first(G + 1, 0);               // number of the first code of every part
+    for (int g = 0; g < G; g++) first[g + 1] = first[g] + po[g].ncodes;
+    // ---- phase 3: the first code of every slab range, inside the part that holds it --------------------------------
+    for (int g = 1; g < G; g++) {
+        const uint64_t target = (uint64_t)lo[g] * codes_per_slab;
+        if (lo[g] == 0) { sb[g] = start_bit; continue; }
+        if (target >= first[G]) return mfail(m, DCT3D_E_NEED_MORE, "stream holds %llu codes, range %d starts at code %llu",
+                                             (unsigned long long)first[G], g, (unsigned long long)target);
+        int owner = 0;
+        while (owner + 1 < G && first[owner + 1] <= target) owner++;
+        uint64_t bit = 0;
+        if ((rc = part_locate(m->ctx[owner], target - first[owner], &bit))) return mfail(m, rc, "GPU %d: %s", m->ctx[owner]->device, m->ctx[owner]->err.c_str());
+        sb[g] = win0[owner] + bit;
+    }
     return DCT3D_OK;
+}
+
+}  // namespace
+
+int dct3d_multi_locate(dct3d_multi *m, const uint8_t *stream, size_t nbytes, int nframes, uint64_t *range_start_bits)
+{
+    if (!m || !range_start_bits || !stream) return mfail(m, DCT3D_E_INVALID, "null argument");
+    const int rc = multi_discover(m, stream, nbytes, 0, nframes, range_start_bits);
+    if (rc == DCT3D_E_NEED_MORE) return mfail(m, DCT3D_E_STREAM, "Exp-Golomb stream truncated: %s", m->err.c_str());
+    return rc;
 }
 
 int dct3d_multi_decode_u8(dct3d_multi *m, const uint8_t *stream, size_t nbytes, int nframes, uint8_t *frames,
@@ -1507,6 +1660,113 @@ int dct3d_multi_decode_u8(dct3d_multi *m, const uint8_t *stream, size_t nbytes, 
     work(0);
     for (auto &t : th) t.join();
     return first_failure(m, rcs);
+}
+
+// ---- streaming over several GPUs: the C codec's batch loop with a carried bit position ------------------------------
+
+int dct3d_multi_stream_begin(dct3d_multi *m)
+{
+    if (!m) return mfail(nullptr, DCT3D_E_INVALID, "null context");
+    m->carry_byte = 0;
+    m->carry_bits = 0;
+    return dct3d_stream_begin(m->ctx[0]);
+}
+
+int dct3d_multi_stream_encode(dct3d_multi *m, const uint8_t *frames, int nframes, int last, uint8_t *out, size_t cap, size_t *nbytes)
+{
+    if (!m) return mfail(nullptr, DCT3D_E_INVALID, "null context");
+    const int G = (int)m->ctx.size(), C = m->C;
+    if (G == 1) {
+        const int rc = dct3d_stream_encode(m->ctx[0], frames, nframes, last, out, cap, nbytes);
+        return rc ? mfail(m, rc, "%s", m->ctx[0]->err.c_str()) : DCT3D_OK;
+    }
+    if (nframes < 0 || nframes % C) return mfail(m, DCT3D_E_INVALID, "streaming encode needs a multiple of %d frames", C);
+    if (!out || cap == 0) return mfail(m, DCT3D_E_INVALID, "null output buffer");
+    const int nslabs = nframes / C;
+    if (nslabs && !frames) return mfail(m, DCT3D_E_INVALID, "null frame pointer");
+    const size_t slab_bytes = (size_t)m->W * m->H * C;
+    std::vector<uint64_t> bits(G, 0), start(G + 1, 0);
+    std::vector<int> rcs(G, 0);
+    std::vector<uint8_t> fb(G, 0);
+    HostBarrier bar(G);
+    const uint64_t carry = (uint64_t)m->carry_bits;
+    auto work = [&](int g) {
+        int lo, hi;
+        slab_range(nslabs, g, G, lo, hi);
+        rcs[g] = dct3d_encode_u8_range(m->ctx[g], frames + (size_t)lo * slab_bytes, (hi - lo) * C, &bits[g]);
+        bar.wait();
+        for (int j = 0; j < G; j++) if (rcs[j]) return;
+        uint64_t b = carry;
+        for (int j = 0; j < g; j++) b += bits[j];
+        rcs[g] = dct3d_encode_u8_place(m->ctx[g], b, last && g == G - 1, out, cap, &fb[g]);
+    };
+    std::vector<std::thread> th;
+    for (int g = 1; g < G; g++) th.emplace_back(work, g);
+    work(0);
+    for (auto &t : th) t.join();
+    int rc = first_failure(m, rcs);
+    if (rc) return rc;
+    start[0] = carry;
+    for (int g = 0; g < G; g++) start[g + 1] = start[g] + bits[g];
+    const uint64_t end = start[G];
+    const size_t full = (size_t)(end / 8), give = last ? full + 1 : full;
+    if (give > cap || (end % 8 && full >= cap)) return mfail(m, DCT3D_E_OVERFLOW, "stream needs %zu bytes, buffer has %zu", full + 1, cap);
+    if (end == carry) {                                          // no slab at all: the carried byte is all there is
+        if (carry || last) out[0] = m->carry_byte;
+    } else {
+        // the first range starts inside the carried byte, the others inside their predecessor's last byte
+        for (int g = 0; g < G; g++) {
+            if (bits[g] == 0 || start[g] % 8 == 0) continue;
+            if (start[g] / 8 == 0 && start[g] == carry) out[0] = (uint8_t)(m->carry_byte | fb[g]);
+            else out[start[g] / 8] |= fb[g];
+        }
+    }
+    m->carry_byte = last ? 0 : (end % 8 ? out[full] : 0);
+    m->carry_bits = last ? 0 : (int)(end % 8);
+    if (nbytes) *nbytes = give;
+    return DCT3D_OK;
+}
+
+int dct3d_multi_stream_decode(dct3d_multi *m, const uint8_t *in, size_t nbytes, uint64_t *bitpos, int nframes, uint8_t *frames)
+{
+    if (!m) return mfail(nullptr, DCT3D_E_INVALID, "null context");
+    const int G = (int)m->ctx.size(), C = m->C;
+    if (G == 1) {
+        const int rc = dct3d_stream_decode(m->ctx[0], in, nbytes, bitpos, nframes, frames);
+        return rc ? mfail(m, rc, "%s", m->ctx[0]->err.c_str()) : DCT3D_OK;
+    }
+    if (!bitpos) return mfail(m, DCT3D_E_INVALID, "null bit position");
+    const int nslabs = nframes / C;
+    if (nslabs == 0) return DCT3D_OK;
+    if (!in || !frames) return mfail(m, DCT3D_E_INVALID, "null pointer");
+    const size_t slab_bytes = (size_t)m->W * m->H * C;
+    std::vector<uint64_t> sb(G + 1, 0), ends(G, 0);
+    int rc = multi_discover(m, in, nbytes, *bitpos, nframes, sb.data());
+    if (rc) return rc;                                           // DCT3D_E_NEED_MORE: nothing has changed
+    std::vector<int> rcs(G, 0);
+    auto work = [&](int g) {
+        int lo, hi;
+        slab_range(nslabs, g, G, lo, hi);
+        if (hi == lo) return;
+        dct3d_ctx *ctx = m->ctx[g];
+        if ((rcs[g] = bind(ctx))) return;
+        uint64_t hint = 0;
+        for (int j = g + 1; j < G && !hint; j++) hint = sb[j] > sb[g] ? sb[j] : 0;
+        const size_t byte0 = (size_t)(sb[g] / 8);
+        const size_t upto = hint ? std::min<size_t>(nbytes, (size_t)(hint / 8) + 1) : nbytes;
+        uint64_t e = 0;
+        rcs[g] = byte0 < upto ? pipe_decode(ctx, in + byte0, upto - byte0, sb[g] % 8, (hi - lo) * C, frames + (size_t)lo * slab_bytes, &e)
+                              : fail(ctx, DCT3D_E_NEED_MORE, "stream holds no data at the range's start bit");
+        ends[g] = (uint64_t)byte0 * 8 + e;
+    };
+    std::vector<std::thread> th;
+    for (int g = 1; g < G; g++) th.emplace_back(work, g);
+    work(0);
+    for (auto &t : th) t.join();
+    for (int g = 0; g < G; g++) if (rcs[g] == DCT3D_E_NEED_MORE) return mfail(m, DCT3D_E_NEED_MORE, "GPU %d: %s", m->ctx[g]->device, m->ctx[g]->err.c_str());
+    if ((rc = first_failure(m, rcs))) return rc;
+    for (int g = G - 1; g >= 0; g--) if (ends[g]) { *bitpos = ends[g]; break; }
+    return DCT3D_OK;
 }
 
 int dct3d_stream_begin(dct3d_ctx *ctx)

@@ -72,6 +72,8 @@ struct EncParams {
     unsigned int *ticket;             // zeroed
     unsigned int *err;                // zeroed; bit0 = overflow
     unsigned long long *end_bit;      // out: start_bit + total bits
+    unsigned long long *end_bit_host; // optional mirror in mapped page-locked host memory: the host learns the end bit of a
+                                      // pipeline chunk without a copy that would queue behind other D2H traffic
     int16_t *zzg;                     // zig-zag chunk scratch [cube][CS] (sparsely touched)
     uint32_t *cmask;                  // [cube] mask of non-zero 16-coefficient chunks
     int16_t *qcubes;                  // MODE_NAT: natural-order int16 cubes out
@@ -683,7 +685,10 @@ eg_pack_kernel(const EncParams P)
             const unsigned long long off = tile_lookback(P.tile_status, tile, total, start_bit, lane, P.err);
             if (lane == 0) {
                 s_off = off;
-                if (tile == ntiles - 1) *P.end_bit = off + total;
+                if (tile == ntiles - 1) {
+                    *P.end_bit = off + total;
+                    if (P.end_bit_host) *P.end_bit_host = off + total;
+                }
             }
         }
         __syncthreads();
@@ -816,6 +821,11 @@ struct DecParams {
     Layout L;
     const uint32_t *words; unsigned long long nwords; unsigned long long nbits_total;  // stream
     unsigned long long start_bit;
+    unsigned long long count_end_bit;   // codes that START before this bit are counted (= nbits_total, except for a part of a stream
+                                        // whose successor part is counted by another GPU: the window then extends past it)
+    int first_entry;                    // entry point of segment 0: 0 = the stream's first code starts at start_bit; -1 = unknown,
+                                        // guess it like any other segment's (a part in the middle of a stream; needs 128 bits of
+                                        // stream in front of start_bit); > 0 = that many bits + 1 (a verified overhang)
     // index discovery
     unsigned int seg_bits; unsigned long long nseg;
     unsigned int *seg_count;            // [nseg] codes starting in the segment | non-zero codes << 16 | malformed << 31
@@ -843,19 +853,19 @@ seg_scan_kernel(const DecParams P)
     const unsigned long long k = blockIdx.x * (unsigned long long)kSegThreads + threadIdx.x;
     // the window starts 4 words early (not for the first CTA): room for the lead-in walk below
     const StagedSource src = stage_stream(s_words, P.words, P.nwords, P.start_bit, blockIdx.x * (unsigned long long)kSegThreads,
-                                          blockIdx.x ? 4u : 0u);
+                                          (blockIdx.x || P.first_entry < 0) ? 4u : 0u);
     if (k >= P.nseg) return;
     const uint32_t seg0 = src.rel(P.start_bit + k * (unsigned long long)P.seg_bits);
     const uint32_t eos = src.rel(P.nbits_total);
-    uint32_t lim = seg0 + P.seg_bits;
+    uint32_t lim = min(seg0 + P.seg_bits, src.rel(P.count_end_bit));
     if (lim > eos) lim = eos;
     uint32_t n = 0, next = 0, nz = 0;
     // Guess the entry point: walk the last kLeadBits bits of the previous segment from an arbitrary
     // phase.  Exp-Golomb streams resynchronise within a few codes (every run of one-bits is a run of
     // complete codes), so the walk usually arrives at the segment's first code; the guess is verified
     // against the predecessor's overhang by seg_fix_kernel like any other.
-    uint32_t entry = 0;
-    if (k > 0 && seg0 < lim) {
+    uint32_t entry = (k == 0 && P.first_entry > 0) ? (uint32_t)P.first_entry - 1u : 0u;
+    if ((k > 0 || P.first_entry < 0) && seg0 < lim) {
         uint32_t nd, nx;
         if (eg_scan_segment(src, seg0 - kLeadBits, seg0, eos, nd, nx) && nx - seg0 <= 33u) entry = nx - seg0;
     }
@@ -870,7 +880,7 @@ seg_scan_kernel(const DecParams P)
     P.seg_count[k] = n | (nz << 16) | bad;
     P.seg_used[k] = entry;
     P.seg_over[k + 1] = next > lim ? next - lim : 0u;
-    if (k == 0) P.seg_over[0] = 0u;              // the stream's first code starts at its first bit
+    if (k == 0) P.seg_over[0] = entry;           // 0 for a whole stream: its first code starts at its first bit
 }
 
 // Fix-up rounds: every thread compares the entry point its segment was scanned with against the
@@ -889,7 +899,7 @@ seg_fix_kernel(const DecParams P, unsigned int round)
     src.fill(P.words, P.nwords);
     const uint32_t seg0 = src.rel(P.start_bit + k * (unsigned long long)P.seg_bits);
     const uint32_t eos = src.rel(P.nbits_total);
-    uint32_t lim = seg0 + P.seg_bits;
+    uint32_t lim = min(seg0 + P.seg_bits, src.rel(P.count_end_bit));
     if (lim > eos) lim = eos;
     uint32_t n = 0, next = 0, nz = 0;
     unsigned int bad = 0;
@@ -1060,13 +1070,39 @@ seg_emit_kernel(const DecParams P)
             src.fill(P.words, P.nwords);
             const uint32_t seg0 = src.rel(P.start_bit + k * (unsigned long long)P.seg_bits);
             const uint32_t eos = src.rel(P.nbits_total);
-            uint32_t lim = seg0 + P.seg_bits;
+            uint32_t lim = min(seg0 + P.seg_bits, src.rel(P.count_end_bit));
             if (lim > eos) lim = eos;
             uint32_t n = 0, next = seg0 + P.seg_over[k];
             if (!eg_scan_segment<LocalSource, NullNzSink, true>(src, seg0 + P.seg_over[k], lim, eos, n, next, nullptr, NullNzSink(), span)) atomicOr(P.err, 2u);
             *P.end_bit = src.w0 * 32ull + next;
         }
     }
+}
+
+// Where does code number `target` (counted from the first code of the scanned range) start?  One thread: bisect the
+// prefix of the segments' code counts, then walk that one segment.  Used after a count-only pass over a part of a stream
+// (distributed index discovery, dct3d_multi_locate); target must be below seg_first[nseg].
+__global__ void seg_locate_kernel(const DecParams P, unsigned long long target, unsigned long long *out_bit)
+{
+    if (blockIdx.x || threadIdx.x) return;
+    unsigned long long lo = 0, hi = P.nseg;              // seg_first[lo] <= target < seg_first[hi]
+    while (hi - lo > 1) {
+        const unsigned long long mid = (lo + hi) >> 1;
+        if (P.seg_first[mid] <= target) lo = mid; else hi = mid;
+    }
+    const unsigned long long k = lo;
+    LocalSource src;
+    src.w0 = (P.start_bit >> 5) + k * kSegWords;
+    src.fill(P.words, P.nwords);
+    const uint32_t seg0 = src.rel(P.start_bit + k * (unsigned long long)P.seg_bits);
+    const uint32_t eos = src.rel(P.nbits_total);
+    uint32_t lim = min(seg0 + P.seg_bits, src.rel(P.count_end_bit));
+    if (lim > eos) lim = eos;
+    uint32_t n = 0, next = seg0 + P.seg_over[k];
+    if (!eg_scan_segment<LocalSource, NullNzSink, true>(src, seg0 + P.seg_over[k], lim, eos, n, next, nullptr, NullNzSink(),
+                                                        (uint32_t)(target - P.seg_first[k])))
+        atomicOr(P.err, 2u);
+    *out_bit = src.w0 * 32ull + next;
 }
 
 // non-zero lists -> dense natural-order int16 cubes (dct3d_eg_decode_i16; qcubes zeroed beforehand).
@@ -1453,6 +1489,31 @@ transform_kernel(const Layout L, const T *__restrict__ in, T *__restrict__ out)
 //   inverse: c = q * d (Decoder.java:89), clamp to [0,255] (InverseDCT.java:74-80), (byte)(double) truncates
 //            (Decoder.java:112).
 // ------------------------------------------------------------------------------------------
+// fp64 <-> integer without the conversion pipe (I2F.F64 / F2I.F64 / FRND.F64 run at a fraction of the DADD rate and were
+// 60% of the first version of these kernels): integers travel through the mantissa of 2^52-scaled doubles.
+constexpr double kMagic52 = 4503599627370496.0;            // 2^52
+constexpr double kMagicRn = 6755399441055744.0;            // 1.5 * 2^52: (x + kMagicRn) has round-to-nearest-even(x) in its low word
+__device__ __forceinline__ double u32_to_f64(uint32_t x) { return __hiloint2double(0x43300000, (int)x) - kMagic52; }           // exact
+__device__ __forceinline__ double i32_to_f64(int x) { return __hiloint2double(0x43300000, x ^ (int)0x80000000) - (kMagic52 + 2147483648.0); }
+// floor(t) for |t| < 2^31 as an int, and as a double in *fl
+__device__ __forceinline__ int floor_f64(double t, double *fl)
+{
+    const double qq = __dadd_rn(t, kMagicRn);
+    const double rn = __dadd_rn(qq, -kMagicRn);            // nearest integer, ties to even
+    const bool over = rn > t;
+    *fl = over ? rn - 1.0 : rn;
+    return __double2loint(qq) - (over ? 1 : 0);
+}
+
+// The reference's quantiser as written: round(c / d) with a true division (Encoder.java:82 / encoder.c:53).  Out of line on
+// purpose: it is only taken next to a rounding tie, and 64 inlined copies of the division sequence made the kernel
+// three times larger than the instruction cache likes.
+__device__ __noinline__ int quant_exact_f64(double c, int s, int rounding)
+{
+    const double v = c / (double)quant_divisor(s);
+    return (int)(rounding ? (v < 0 ? -floor(-v + 0.5) : floor(v + 0.5)) : floor(v + 0.5));
+}
+
 template <int C, bool INVERSE>
 __global__ void __launch_bounds__(kThreads)
 codec_f64_kernel(const Layout L, const uint8_t *__restrict__ frames_in, int16_t *__restrict__ q_out,
@@ -1465,6 +1526,10 @@ codec_f64_kernel(const Layout L, const uint8_t *__restrict__ frames_in, int16_t 
     const long long ngroups = (L.ncubes + G::CPW - 1) / G::CPW;
     const size_t fs = (size_t)L.W * L.H;
     uint8_t *xbuf = smem + warp * Xch<C, double>::WARP_BYTES;
+    // forward: 1 / max(1, 5 s); inverse: max(1, 5 s); s = k0 + k1 + k2
+    double *s_inv = reinterpret_cast<double *>(smem + kWarps * Xch<C, double>::WARP_BYTES);
+    if (tid < 3 * C - 2) s_inv[tid] = INVERSE ? (double)quant_divisor(tid) : 1.0 / (double)quant_divisor(tid);
+    __syncthreads();
     for (long long g = (long long)blockIdx.x * kWarps + warp; g < ngroups; g += (long long)gridDim.x * kWarps) {
         const long long cube = g * G::CPW + cl;
         const bool valid = cube < L.ncubes;
@@ -1486,7 +1551,7 @@ codec_f64_kernel(const Layout L, const uint8_t *__restrict__ frames_in, int16_t 
                     else w[0] = __ldg(reinterpret_cast<const uint32_t *>(src));
                 }
 #pragma unroll
-                for (int x = 0; x < C; x++) b[t][x] = (double)((w[x / 4] >> (8 * (x % 4))) & 0xffu);
+                for (int x = 0; x < C; x++) b[t][x] = u32_to_f64((w[x / 4] >> (8 * (x % 4))) & 0xffu);
             }
             fwd_t<C, double>(b);
             Xch<C, double>::transpose(xbuf, cl, r, b, a);
@@ -1498,9 +1563,17 @@ codec_f64_kernel(const Layout L, const uint8_t *__restrict__ frames_in, int16_t 
                     uint32_t w[C / 2];
 #pragma unroll
                     for (int k2 = 0; k2 < C; k2++) {
-                        const double v = a[k1][k2] / (double)quant_divisor(r + k1 + k2);
-                        const double q = rounding ? (v < 0 ? -floor(-v + 0.5) : floor(v + 0.5)) : floor(v + 0.5);
-                        const uint32_t h = (uint32_t)(int)fmax(-32768.0, fmin(32767.0, q)) & 0xffffu;
+                        // Division in double is a long software sequence: multiply by the tabulated inverse instead, and
+                        // let the reference's own quotient decide only where the product is within 1e-9 of a rounding tie
+                        // (the product is within 1e-11 of the quotient, so everywhere else both round the same way)
+                        const int s = r + k1 + k2;
+                        const double v = a[k1][k2] * s_inv[s];
+                        double q;
+                        int qi = floor_f64(v + 0.5, &q);
+                        const double fr = (v + 0.5) - q;
+                        if (fr < 1e-9 || fr > 1.0 - 1e-9) qi = quant_exact_f64(a[k1][k2], s, rounding);
+                        // |q| <= 255 * sqrt(C^3) = 5770 for u8 input: int16 holds it without a clamp
+                        const uint32_t h = (uint32_t)qi & 0xffffu;
                         if (k2 & 1) w[k2 / 2] |= h << 16; else w[k2 / 2] = h;
                     }
                     if (C == 8) *reinterpret_cast<uint4 *>(dst + k1 * C) = make_uint4(w[0], w[1], w[2 % (C / 2)], w[3 % (C / 2)]);
@@ -1520,7 +1593,7 @@ codec_f64_kernel(const Layout L, const uint8_t *__restrict__ frames_in, int16_t 
 #pragma unroll
                 for (int k2 = 0; k2 < C; k2++) {
                     const int q = (int)(int16_t)((w[k2 / 2] >> ((k2 & 1) * 16)) & 0xffffu);
-                    b[k0][k2] = (double)q * (double)quant_divisor(k0 + r + k2);
+                    b[k0][k2] = i32_to_f64(q) * s_inv[k0 + r + k2];
                 }
             }
             inv_t<C, double>(b);
@@ -1535,7 +1608,8 @@ codec_f64_kernel(const Layout L, const uint8_t *__restrict__ frames_in, int16_t 
                     for (int x = 0; x < C; x++) {
                         const double v = a[y][x];
                         const double c = v > 255.0 ? 255.0 : (v < 0.0 ? 0.0 : v);
-                        w[x / 4] |= ((uint32_t)(int)c & 0xffu) << (8 * (x % 4));
+                        double unused;
+                        w[x / 4] |= ((uint32_t)floor_f64(c, &unused) & 0xffu) << (8 * (x % 4));   // c >= 0: truncation is floor
                     }
                     if (C == 8) *reinterpret_cast<uint2 *>(dst + (size_t)y * L.W) = make_uint2(w[0], w[1]);
                     else *reinterpret_cast<uint32_t *>(dst + (size_t)y * L.W) = w[0];

@@ -497,12 +497,13 @@ def run_ours(args):
     e2e_h2d = W * H * total_frames + S_total
     # two clips in flight at N = 1: a second context decodes clip k while the first encodes clip k+1 (PCIe is full
     # duplex; every call is still the product call and every clip one stream)
-    duplex_value = None
+    duplex_value = duplex_trace = None
     if world == 1 and not args.quick:
         c2 = codec.Codec(W, H, cube, device=local)
         h_stream2 = [h_stream, torch.zeros(scap, dtype=torch.uint8, pin_memory=True)]
         sizes = [0, 0]
-        nsteps = e2e_steps + 1
+        nsteps = 2 * e2e_steps + 2
+        trace = {"enc": [], "dec": []}
         ready = [threading.Semaphore(0), threading.Semaphore(0)]
         free = [threading.Semaphore(1), threading.Semaphore(1)]
         errs = []
@@ -511,16 +512,20 @@ def run_ours(args):
             nb, ny = C.c_uint64(), C.c_size_t()
             for k in range(nsteps):
                 free[k & 1].acquire()
+                ta_ = time.perf_counter()
                 if lib.dct3d_encode_u8(c.h, h_frames.data_ptr(), Fr, h_stream2[k & 1].data_ptr(), scap, C.byref(nb), C.byref(ny)) != 0:
                     errs.append(lib.dct3d_last_error(c.h))
+                trace["enc"].append((ta_, time.perf_counter()))
                 sizes[k & 1] = ny.value
                 ready[k & 1].release()
 
         def dec_thread():
             for k in range(nsteps):
                 ready[k & 1].acquire()
+                ta_ = time.perf_counter()
                 if lib.dct3d_decode_u8(c2.h, h_stream2[k & 1].data_ptr(), sizes[k & 1], Fr, h_out.data_ptr()) != 0:
                     errs.append(lib.dct3d_last_error(c2.h))
+                trace["dec"].append((ta_, time.perf_counter()))
                 free[k & 1].release()
 
         assert lib.dct3d_decode_u8(c2.h, stream_ptr, e2e_state["offs"][-1] // 8 + 1, Fr, h_out.data_ptr()) == 0   # warm-up: allocations
@@ -532,6 +537,7 @@ def run_ours(args):
             t_.join()
         duplex_value = nsteps * Fr / (time.perf_counter() - t0)
         assert not errs, errs
+        duplex_trace = {k: [(round((a - t0) * 1e3, 1), round((b - t0) * 1e3, 1)) for a, b in v] for k, v in trace.items()}
         c2.close()
 
     # ---- extra device-resident lines at N = 1: worst-case content and the 4^3 variant ------------------------------
@@ -633,7 +639,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(e2e_h2d), "d2h_bytes_per_step": int(e2e_h2d),
                     "steps": e2e_steps, "matches_device_path": roundtrip_ok, "encode_ms": e2e_enc_s * 1e3,
                     "decode_ms": (e2e_s - e2e_enc_s) * 1e3, "concat_ms": concat_s * 1e3,
-                    "stream_sha256": sha, "duplex_value": duplex_value, "chunks_per_call": chunks_per_call,
+                    "stream_sha256": sha, "duplex_value": duplex_value, "duplex_trace_ms": duplex_trace, "chunks_per_call": chunks_per_call,
                     "how": ("one dct3d_encode_u8 + one dct3d_decode_u8 per step on pinned host buffers" if world == 1 else
                             f"per rank: dct3d_encode_u8_range, {world} bit counts exchanged through a shared-memory table, dct3d_encode_u8_place "
                             "into the shared-memory stream, boundary byte OR-ed once the predecessor has landed (concat_ms = all of that), then "

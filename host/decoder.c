@@ -4,8 +4,8 @@
  * buffered, decode them, write the frames, drop the consumed bytes and keep the bit position of the partial byte
  * (expGolomb_freeBuffer(..., 0), ExpGolomb.c:123-129).  What changed:
  *   - expGolomb_readValue + reorderDctCoeffs + applyDequantization + the cl* sequence + writeCubes (:229-295) are ONE call,
- *     dct3d_stream_decode, which reports DCT3D_E_NEED_MORE while the buffered input does not yet hold all the codes;
- *   - the unit of work is a BATCH of slabs per call (DCT3D_BATCH_SLABS, default 16 = 128 frames) instead of one slab
+ *     dct3d_multi_stream_decode (one GPU or several, see encoder.c), which reports DCT3D_E_NEED_MORE while the buffered input does not yet hold all the codes;
+ *   - the unit of work is a BATCH of slabs per call (DCT3D_BATCH_SLABS, default 16 = 128 frames per GPU) instead of one slab
  *     (:207), so the library's chunk pipeline overlaps the inverse kernels with the D2H copies;
  *   - three stages run side by side instead of in turn: an inflate thread (the reference's fread + inflate loop,
  *     :210-227; inflate of one zlib stream is inherently serial, so it gets a core of its own and runs ahead), the GPU
@@ -117,7 +117,9 @@ int decode(char *inputFileName, char *outputFileName, int width, int height, int
 {
     const size_t slabBytes = (size_t)width * height * DCT_BLOCK_DEPTH;
     const char *bs = getenv("DCT3D_BATCH_SLABS");
-    int batchSlabs = bs ? atoi(bs) : 16;
+    int devices[64];
+    const int ndevices = codec_devices(platformIndex, devices, 64);
+    int batchSlabs = bs ? atoi(bs) : 16 * ndevices;              /* every GPU gets 16 slabs of a batch */
     if (batchSlabs < 1) batchSlabs = 1;
     const int totalSlabs = (framesToDecode + DCT_BLOCK_DEPTH - 1) / DCT_BLOCK_DEPTH;   /* decoder.c:207 decodes whole slabs */
     if (batchSlabs > totalSlabs) batchSlabs = totalSlabs > 0 ? totalSlabs : 1;
@@ -147,8 +149,8 @@ int decode(char *inputFileName, char *outputFileName, int width, int height, int
     pthread_create(&inflateThread, NULL, inflater_main, &inf);
 
     printf("Getting device id\n");
-    dct3d_ctx *ctx = NULL;
-    if (dct3d_create(&ctx, platformIndex - 1, width, height, DCT_BLOCK_WIDTH) != DCT3D_OK) {
+    dct3d_multi *ctx = NULL;
+    if (dct3d_multi_create(&ctx, devices, ndevices, width, height, DCT_BLOCK_WIDTH) != DCT3D_OK) {
         printf("Error creating dct3d context: %s\n", dct3d_last_error(NULL));
         return 1;
     }
@@ -197,13 +199,13 @@ int decode(char *inputFileName, char *outputFileName, int width, int height, int
         pthread_mutex_unlock(&writer.mu);
         unsigned char *frames = writer.buf[cur];
         const uint64_t before = bitpos;
-        int dr = have ? dct3d_stream_decode(ctx, expGolombCodedData, have, &bitpos, n * DCT_BLOCK_DEPTH, frames) : DCT3D_E_NEED_MORE;
+        int dr = have ? dct3d_multi_stream_decode(ctx, expGolombCodedData, have, &bitpos, n * DCT_BLOCK_DEPTH, frames) : DCT3D_E_NEED_MORE;
         if (dr == DCT3D_E_NEED_MORE) {
             if (inflated_all) { printf("Input ended before all frames were decoded\n"); rc = 1; break; }
             want = have + (have / 4 > INFLATE_BLOCK ? have / 4 : INFLATE_BLOCK);          /* buffer more and try again */
             continue;
         }
-        if (dr != DCT3D_OK) { printf("Error decoding slab: %s\n", dct3d_last_error(ctx)); rc = 1; break; }
+        if (dr != DCT3D_OK) { printf("Error decoding slab: %s\n", dct3d_multi_last_error(ctx)); rc = 1; break; }
         /* Writing the resulting pixels to the output file (handed to the writer thread) */
         pthread_mutex_lock(&writer.mu);
         writer.bytes[cur] = slabBytes * (size_t)n;
@@ -238,7 +240,7 @@ int decode(char *inputFileName, char *outputFileName, int width, int height, int
     fflush(outputFile);
     fclose(outputFile);
     fclose(inputFile);
-    dct3d_destroy(ctx);
+    dct3d_multi_destroy(ctx);
     dct3d_host_free(expGolombCodedData); dct3d_host_free(writer.buf[0]); dct3d_host_free(writer.buf[1]);
     if (!rc) printf("Decoding process completed");
     return rc;

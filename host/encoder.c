@@ -4,9 +4,10 @@
  * complete bytes, carry the partial byte into the next round, Z_FINISH after the last one.  What changed:
  *   - what sits between the read and deflate: readCubes' float reshuffle (:10-45), the clEnqueueWriteBuffer / two
  *     kernels / clEnqueueReadBuffer sequence (:209-254), applyQuantization (:47-58) and applyExpGolombCoding (:60-71)
- *     with expGolomb_freeBuffer (ExpGolomb.c:112-122) are ONE call, dct3d_stream_encode, which takes raw u8 frames and
- *     returns the complete stream bytes; OpenCLUtils.c is replaced by dct3d_create;
- *   - the unit of work: a BATCH of slabs per call (DCT3D_BATCH_SLABS, default 16 = 128 frames) instead of one slab
+ *     with expGolomb_freeBuffer (ExpGolomb.c:112-122) are ONE call, dct3d_multi_stream_encode, which takes raw u8 frames and
+ *     returns the complete stream bytes; OpenCLUtils.c is replaced by dct3d_multi_create (one GPU, or the list in
+ *     DCT3D_DEVICES / a comma-separated last argument: the batch is then shared out as slab ranges, one stream);
+ *   - the unit of work: a BATCH of slabs per call (DCT3D_BATCH_SLABS, default 16 = 128 frames per GPU) instead of one slab
  *     (:203-206), so that the library's chunk pipeline overlaps the H2D copies with the kernels, and there is one
  *     host round trip per batch instead of one per 8 frames;
  *   - the read (:21-27, a blocking fread per slab): a reader thread fills the other of two page-locked batch buffers
@@ -88,7 +89,9 @@ int encode(char *inputFileName, char *outputFileName, int width, int height, int
 {
     const size_t slabBytes = (size_t)width * height * DCT_BLOCK_DEPTH;
     const char *bs = getenv("DCT3D_BATCH_SLABS");
-    int batchSlabs = bs ? atoi(bs) : 16;
+    int devices[64];
+    const int ndevices = codec_devices(platformIndex, devices, 64);
+    int batchSlabs = bs ? atoi(bs) : 16 * ndevices;              /* every GPU gets 16 slabs of a batch */
     if (batchSlabs < 1) batchSlabs = 1;
     const int totalSlabs = (framesToEncode + DCT_BLOCK_DEPTH - 1) / DCT_BLOCK_DEPTH;   /* the reference codes whole slabs (:203) */
     if (batchSlabs > totalSlabs) batchSlabs = totalSlabs > 0 ? totalSlabs : 1;
@@ -114,12 +117,12 @@ int encode(char *inputFileName, char *outputFileName, int width, int height, int
     if (!zlibStream) { printf("Error starting deflate\n"); return 1; }
 
     printf("Getting device id\n");
-    dct3d_ctx *ctx = NULL;
-    if (dct3d_create(&ctx, platformIndex - 1, width, height, DCT_BLOCK_WIDTH) != DCT3D_OK) {
+    dct3d_multi *ctx = NULL;
+    if (dct3d_multi_create(&ctx, devices, ndevices, width, height, DCT_BLOCK_WIDTH) != DCT3D_OK) {
         printf("Error creating dct3d context: %s\n", dct3d_last_error(NULL));
         return 1;
     }
-    dct3d_stream_begin(ctx);
+    dct3d_multi_stream_begin(ctx);
 
     pthread_mutex_init(&reader.mu, NULL);
     pthread_cond_init(&reader.cv, NULL);
@@ -151,9 +154,9 @@ int encode(char *inputFileName, char *outputFileName, int width, int height, int
 
         /* DCT + quantization + zig-zag + Exp-Golomb on the GPU; complete bytes come back */
         size_t expGolombCodedDataSize = 0;
-        if (dct3d_stream_encode(ctx, frames, n * DCT_BLOCK_DEPTH, last, expGolombBuffer, egCap,
-                                &expGolombCodedDataSize) != DCT3D_OK) {
-            printf("Error encoding slab: %s\n", dct3d_last_error(ctx));
+        if (dct3d_multi_stream_encode(ctx, frames, n * DCT_BLOCK_DEPTH, last, expGolombBuffer, egCap,
+                                      &expGolombCodedDataSize) != DCT3D_OK) {
+            printf("Error encoding slab: %s\n", dct3d_multi_last_error(ctx));
             rc = 1;
             break;
         }
@@ -182,7 +185,7 @@ int encode(char *inputFileName, char *outputFileName, int width, int height, int
     fflush(outputFile);
     fclose(outputFile);
     close(reader.fd);
-    dct3d_destroy(ctx);
+    dct3d_multi_destroy(ctx);
     dct3d_host_free(reader.buf[0]); dct3d_host_free(reader.buf[1]); dct3d_host_free(expGolombBuffer);
     if (!rc) printf("Encoding process completed");
     return rc;

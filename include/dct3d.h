@@ -149,6 +149,14 @@ int dct3d_multi_locate(dct3d_multi *m, const uint8_t *stream, size_t nbytes, int
 int dct3d_multi_decode_u8(dct3d_multi *m, const uint8_t *stream, size_t nbytes, int nframes, uint8_t *frames,
                           const uint64_t *range_start_bits);
 
+/* The streaming calls below (dct3d_stream_*) over several GPUs: a batch of slabs per call, shared out as slab ranges, the
+ * partial byte carried between calls.  dct3d_multi_stream_decode finds the ranges' start bits by distributed index
+ * discovery on the buffered bytes (every GPU counts the codes of 1/G of the bytes) and returns
+ * DCT3D_E_NEED_MORE, changing nothing, while they do not hold the whole batch. */
+int dct3d_multi_stream_begin(dct3d_multi *m);
+int dct3d_multi_stream_encode(dct3d_multi *m, const uint8_t *frames, int nframes, int last, uint8_t *out, size_t cap, size_t *nbytes);
+int dct3d_multi_stream_decode(dct3d_multi *m, const uint8_t *in, size_t nbytes, uint64_t *bitpos, int nframes, uint8_t *frames);
+
 /* ---- streaming (the C codec's slab loop with a carried bit position) -------------------- */
 
 /* Resets the carried bit state (expGolomb_createStream, C/ExpGolomb.c:24-30). */

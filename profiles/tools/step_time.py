@@ -10,6 +10,7 @@ F = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
 cube = int(sys.argv[3]) if len(sys.argv) > 3 else 8
 kind = sys.argv[4] if len(sys.argv) > 4 else "natural"
+precision = int(sys.argv[5]) if len(sys.argv) > 5 else 32
 W, H = 1920, 1080
 dev = torch.device('cuda', 0)
 frames = bench.synth_slabs_torch(W, H, cube, 0, F // cube, 1, dev, kind=kind)
@@ -18,6 +19,7 @@ d_stream = torch.zeros(cap, dtype=torch.uint8, device=dev)
 d_out = torch.empty_like(frames)
 c = codec.Codec(W, H, cube)
 c.set_option("reuse_zeroed", 1)
+c.set_option("precision", precision)
 ts = torch.cuda.Stream(); torch.cuda.set_stream(ts); st = ts.cuda_stream
 for i in range(5):
     end = c.encode_u8_dev(frames, F, d_stream, cap, 0, st)
@@ -41,7 +43,7 @@ e1.record()
 torch.cuda.synchronize()
 te = sum(a.elapsed_time(b) for a, b, d in evs) / steps
 td = sum(b.elapsed_time(d) for a, b, d in evs) / steps
-print(json.dumps({"lib": os.path.basename(os.environ.get("DCT3D_LIB", "in-tree")), "frames": F, "cube": cube, "kind": kind,
+print(json.dumps({"lib": os.path.basename(os.environ.get("DCT3D_LIB", "in-tree")), "frames": F, "cube": cube, "kind": kind, "precision": precision,
                   "ms_per_step": e0.elapsed_time(e1) / steps, "encode_ms": te, "decode_ms": td,
                   "encode_kernel_ms": c.stat("ns_encode_kernel_avg") * 1e-6, "reconstruct_kernel_ms": c.stat("ns_reconstruct_kernel_avg") * 1e-6,
                   "fps": F * steps / (e0.elapsed_time(e1) * 1e-3), "bits": end,

@@ -277,3 +277,117 @@ def test_multi_object_on_every_visible_gpu(codec_mod, synth):
         assert nbits == wbits and stream.tobytes() == want.tobytes()
         assert (m.decode_u8(stream, F, starts) == wdec).all()
         assert (m.decode_u8(stream, F) == wdec).all()
+
+
+@pytest.mark.parametrize("batch,chunk", [(1, 8), (3, 8), (2, 16), (5, 0)])
+def test_streaming_in_batches_of_slabs(codec_mod, synth, batch, chunk):
+    """dct3d_stream_encode / _decode with several slabs per call (the C codec's batch loop, host/encoder.c): the carried
+    partial byte continues through the chunk pipeline (device-chained start bit), the concatenated output is the
+    one-shot stream, and the streaming decoder returns NEED_MORE until a batch is complete."""
+    W, H, F = 128, 64, 88                                   # 11 slabs: the last batch is short
+    clip = synth.natural(W, H, F, 17)
+    want, wbits, wdec = one_shot(codec_mod, clip, W, H, 8)
+    with codec_mod.Codec(W, H, 8) as c:
+        c.set_option("chunk_frames", chunk)
+        c.stream_begin()
+        parts = []
+        for s in range(0, 11, batch):
+            n = min(batch, 11 - s)
+            parts.append(c.stream_encode(clip[s * 8:(s + n) * 8], last=(s + n == 11)))
+        got = np.concatenate(parts)
+        assert got.tobytes() == want.tobytes()
+        # decode side: feed the stream in pieces of 1000 bytes
+        buf, pos, done, frames = np.zeros(0, np.uint8), 0, 0, []
+        fed = 0
+        while done < 11:
+            n = min(batch, 11 - done)
+            res = c.stream_decode(buf, pos, n * 8) if buf.size else None
+            if res is None:
+                assert fed < got.size, "decoder asks for more than the stream holds"
+                buf = np.concatenate([buf, got[fed:fed + 1000]])
+                fed += 1000
+                continue
+            out, pos = res
+            frames.append(out)
+            buf = buf[pos // 8:]
+            pos %= 8
+            done += n
+        assert (np.concatenate(frames) == wdec).all()
+
+
+@pytest.mark.parametrize("ndev", [2, 3, 8])
+@pytest.mark.parametrize("kind", ["natural", "noise"])
+def test_distributed_index_discovery(codec_mod, synth, ndev, kind):
+    """dct3d_multi_locate on a stream large enough for the distributed path (every GPU counts the codes of 1/G of the
+    bytes, the host checks the entry guesses and locates the ranges): the start bits are the encoder's, and a decode
+    without side information gives the one-shot frames."""
+    W, H, F = 640, 480, 64 if kind == "natural" else 32
+    clip = synth.natural(W, H, F, 13) if kind == "natural" else synth.noise(W, H, F, 14)
+    with codec_mod.Codec(W, H, 8) as c:
+        stream, nbits = c.encode_u8(clip, cap=4 * clip.size + 4096)
+        wdec = c.decode_u8(stream, F)
+        cps = (W // 8) * (H // 8)
+    assert stream.size * 8 >= ndev * (1 << 19)                   # above the small-stream fallback
+    with codec_mod.MultiCodec(W, H, 8, devices=[0] * ndev) as m:
+        _, nb2, starts = m.encode_u8(clip, cap=4 * clip.size + 4096)
+        assert nb2 == nbits
+        found = m.locate(stream, F)
+        assert found[:ndev] == starts[:ndev]
+        assert (m.decode_u8(stream, F) == wdec).all()
+        # truncated in the middle of the last range: an error, not garbage
+        with pytest.raises(codec_mod.Dct3dError):
+            m.decode_u8(stream[: stream.size - 1000], F)
+        # truncated before the last range starts
+        with pytest.raises(codec_mod.Dct3dError):
+            m.decode_u8(stream[: starts[ndev - 1] // 8 - 10], F)
+
+
+def test_distributed_discovery_with_wrong_entry_guesses(codec_mod):
+    """A stream of equal 33-bit codes never resynchronises: the entry guess of every part is wrong, so every part is
+    recounted from its predecessor's verified overhang (and every segment inside it needs its own fix-up round)."""
+    W = H = 64
+    nslabs, cps = 8, 64
+    q = np.full((nslabs * cps, 8, 8, 8), -32768, np.int16)
+    with codec_mod.Codec(W, H, 8) as c:
+        stream, end = c.eg_encode_i16(q)
+    assert end == q.size * 33
+    sh = pkg("sharding")
+    with codec_mod.MultiCodec(W, H, 8, devices=[0] * 4) as m:
+        found = m.locate(stream, nslabs * 8)
+        for g in range(4):
+            lo, _ = sh.slab_range(nslabs, g, 4)
+            assert found[g] == lo * cps * 512 * 33
+
+
+@pytest.mark.parametrize("ndev,batch", [(2, 4), (3, 5)])
+def test_multi_streaming_in_batches(codec_mod, synth, ndev, batch):
+    """dct3d_multi_stream_encode / _decode: batches of slabs shared out over `ndev` contexts with the partial byte carried
+    between calls give the one-shot stream; the decoder discovers the range boundaries of every batch and asks for more
+    input until a batch is complete."""
+    W, H, nsl = 128, 64, 11
+    clip = synth.natural(W, H, nsl * 8, 19)
+    want, wbits, wdec = one_shot(codec_mod, clip, W, H, 8)
+    with codec_mod.MultiCodec(W, H, 8, devices=[0] * ndev) as m:
+        m.set_option("chunk_frames", 8)
+        m.stream_begin()
+        parts = []
+        for s in range(0, nsl, batch):
+            n = min(batch, nsl - s)
+            parts.append(m.stream_encode(clip[s * 8:(s + n) * 8], last=(s + n == nsl)))
+        got = np.concatenate(parts)
+        assert got.tobytes() == want.tobytes()
+        buf, pos, done, frames, fed = np.zeros(0, np.uint8), 0, 0, [], 0
+        while done < nsl:
+            n = min(batch, nsl - done)
+            res = m.stream_decode(buf, pos, n * 8) if buf.size else None
+            if res is None:
+                assert fed < got.size, "decoder asks for more than the stream holds"
+                buf = np.concatenate([buf, got[fed:fed + 3000]])
+                fed += 3000
+                continue
+            out, pos = res
+            frames.append(out)
+            buf = buf[pos // 8:]
+            pos %= 8
+            done += n
+        assert (np.concatenate(frames) == wdec).all()
