@@ -585,7 +585,7 @@ static int run_pack_noreset(dct3d_ctx *ctx, EncParams &P, void *d_stream, size_t
                             const Chain *chain = nullptr)
 {
     int rc;
-    const long long ptiles = (P.L.ncubes + kPackThreads - 1) / kPackThreads;
+    const long long ptiles = (P.L.ncubes + kPackWorkers - 1) / kPackWorkers;
     Ctrl *dc = (Ctrl *)ctx->ctrl.p;
     P.out_words = (uint32_t *)d_stream;
     P.cap_bits = (unsigned long long)(cap / 4) * 32;
@@ -616,7 +616,7 @@ static int run_pack_noreset(dct3d_ctx *ctx, EncParams &P, void *d_stream, size_t
 
 static int run_pack(dct3d_ctx *ctx, EncParams &P, void *d_stream, size_t cap, uint64_t start_bit, uint64_t *end_bit, cudaStream_t st)
 {
-    const long long ptiles = (P.L.ncubes + kPackThreads - 1) / kPackThreads;
+    const long long ptiles = (P.L.ncubes + kPackWorkers - 1) / kPackWorkers;
     int rc = reset_ctrl(ctx, ptiles, st);
     return rc ? rc : run_pack_noreset(ctx, P, d_stream, cap, start_bit, end_bit, st);
 }
@@ -657,7 +657,7 @@ static int encode_common(dct3d_ctx *ctx, const void *d_frames, int nframes, void
     P.qcubes = (int16_t *)d_qcubes;
     P.use_tma = ctx->use_tma && !((uintptr_t)d_frames & 15);
     P.debug = ctx->debug;
-    CU_CHECK(ctx, ctx->ctrl.reserve(kCtrlBytes + (size_t)((P.L.ncubes + kPackThreads - 1) / kPackThreads) * 8));   // final size: the pointer below stays valid
+    CU_CHECK(ctx, ctx->ctrl.reserve(kCtrlBytes + (size_t)((P.L.ncubes + kPackWorkers - 1) / kPackWorkers) * 8));   // final size: the pointer below stays valid
     P.err = chain ? chain->d_err : &((Ctrl *)ctx->ctrl.p)->err;
     if (!emit_q) {
         CU_CHECK(ctx, ctx->zz.reserve((size_t)P.L.ncubes * C * C * C * sizeof(int16_t)));
@@ -680,7 +680,7 @@ static int encode_common(dct3d_ctx *ctx, const void *d_frames, int nframes, void
     }
     // the control block is zeroed here (before kernel 1, which may flag a TMA time-out in it) and
     // again only partially by run_pack: keep one reset, done by run_pack, and run kernel 1 after it
-    const long long ptiles = (P.L.ncubes + kPackThreads - 1) / kPackThreads;
+    const long long ptiles = (P.L.ncubes + kPackWorkers - 1) / kPackWorkers;
     if ((rc = reset_ctrl(ctx, ptiles, st))) return rc;
     if (chain) {                                                   // the caller wiped the whole stream buffer once
         rc = C == 8 ? launch_encode<8, MODE_ZZ>(ctx, P, tm, st) : launch_encode<4, MODE_ZZ>(ctx, P, tm, st);
@@ -1097,7 +1097,7 @@ static int pipe_encode(dct3d_ctx *ctx, const uint8_t *frames, int nframes, size_
     for (int b = 0; b < kRing; b++) CU_CHECK(ctx, ctx->ring[b].reserve((size_t)K * slab_bytes + 16));
     CU_CHECK(ctx, ctx->zz.reserve(cubes_chunk * C * C * C * sizeof(int16_t)));
     CU_CHECK(ctx, ctx->cmask.reserve(cubes_chunk * 4));
-    CU_CHECK(ctx, ctx->ctrl.reserve(kCtrlBytes + ((cubes_chunk + kPackThreads - 1) / kPackThreads) * 8));
+    CU_CHECK(ctx, ctx->ctrl.reserve(kCtrlBytes + ((cubes_chunk + kPackWorkers - 1) / kPackWorkers) * 8));
     const size_t nslots = (size_t)nchunks + 2;                   // bit position before every chunk and after the last; error word
     CU_CHECK(ctx, ctx->chain.reserve(nslots * 8));
     if (ctx->h_chain_n < nslots) {

@@ -74,7 +74,9 @@ struct EncParams {
     unsigned long long *end_bit;      // out: start_bit + total bits
     unsigned long long *end_bit_host; // optional mirror in mapped page-locked host memory: the host learns the end bit of a
                                       // pipeline chunk without a copy that would queue behind other D2H traffic
-    int16_t *zzg;                     // zig-zag chunk scratch [cube][CS] (sparsely touched)
+    int16_t *zzg;                     // zig-zag chunk scratch: a region of CPW * CS int16 per warp unit (CPW cubes side by
+                                      // side in a cube row), holding only the unit's NON-ZERO 16-coefficient chunks, one after
+                                      // the other in (cube, chunk) order: contiguous for the packer, no 64-byte DRAM over-fetch
     uint32_t *cmask;                  // [cube] mask of non-zero 16-coefficient chunks
     int16_t *qcubes;                  // MODE_NAT: natural-order int16 cubes out
     const int16_t *qcubes_in;         // EG-only kernel: natural-order int16 cubes in
@@ -567,6 +569,8 @@ encode_kernel(const __grid_constant__ CUtensorMap tmap, const EncParams P)
         __syncwarp();
         // chunk masks + sparse store: lane <-> 16-coefficient chunk
         constexpr int ITER = (G::CPW * G::CHUNKS) / 32;   // 4 (C=8) / 1 (C=4)
+        uint32_t run = 0;                                 // non-zero chunks of this unit stored so far
+        int16_t *const unit_zz = P.zzg + (size_t)cube0 * G::CS;
 #pragma unroll
         for (int k = 0; k < ITER; k++) {
             const int ci = k * 32 + lane;
@@ -582,13 +586,15 @@ encode_kernel(const __grid_constant__ CUtensorMap tmap, const EncParams P)
             const long long gc = cube0 + cube;
             if (any != 0) {
                 if (ok) {
-                    uint4 *dst = reinterpret_cast<uint4 *>(P.zzg + (size_t)gc * G::CS + chunk * 16);
+                    const uint32_t at = run + (uint32_t)__popc(bal & ((1u << lane) - 1u));   // dense: rank among the unit's non-zero chunks
+                    uint4 *dst = reinterpret_cast<uint4 *>(unit_zz + (size_t)at * 16);
                     dst[hsel] = va;
                     dst[hsel ^ 1] = vb;
                 }
                 q[0] = make_uint4(0, 0, 0, 0);      // leave the buffer clean for the next unit
                 q[1] = make_uint4(0, 0, 0, 0);
             }
+            run += (uint32_t)__popc(bal);
             if (G::CHUNKS == 32) { if (lane == 0 && ok) P.cmask[gc] = bal; }
             else { if (chunk == 0 && ok) P.cmask[gc] = (bal >> (cube * G::CHUNKS)) & ((1u << (G::CHUNKS & 31)) - 1u); }
         }
@@ -596,8 +602,21 @@ encode_kernel(const __grid_constant__ CUtensorMap tmap, const EncParams P)
     }
 }
 
+// Where the packer finds a cube's chunks in the scratch: the unit's region starts at its first cube's slot, the cube's chunks
+// follow those of the cubes before it in the unit.
+template <int C>
+__device__ __forceinline__ const int16_t *cube_chunks(const EncParams &P, long long cube)
+{
+    using G = Geo<C>;
+    const int idx = (int)(cube % P.L.bx) % G::CPW;                 // position of the cube inside its warp unit
+    const long long first = cube - idx;
+    uint32_t before = 0;
+    for (int j = 0; j < idx; j++) before += (uint32_t)__popc(P.cmask[first + j]);
+    return P.zzg + (size_t)first * G::CS + (size_t)before * 16;
+}
+
 // Natural-order int16 cubes -> the same zig-zag chunk scratch + masks (dct3d_eg_encode_i16).
-// One warp per cube, lane <-> chunk.
+// One warp per unit (the CPW cubes a warp of the fused encoder would hold), lane <-> chunk.
 template <int C>
 __global__ void __launch_bounds__(kThreads)
 zz_gather_kernel(const EncParams P)
@@ -607,11 +626,19 @@ zz_gather_kernel(const EncParams P)
     const long long wid = (long long)blockIdx.x * kWarps + (threadIdx.x >> 5);
     const long long nw = (long long)gridDim.x * kWarps;
     const uint16_t *lin = zz_lin<C>();
-    for (long long cube = wid; cube < P.L.ncubes; cube += nw) {
-        const int16_t *src = P.qcubes_in + (size_t)cube * G::CS;
-        uint32_t mask = 0;
-        for (int c0 = 0; c0 < G::CHUNKS; c0 += 32) {
-            const int chunk = c0 + lane;
+    const int bx = P.L.bx, bxu = P.L.bxu;
+    const long long nrows = (P.L.ncubes + bx - 1) / bx;
+    for (long long u = wid; u < nrows * bxu; u += nw) {
+        const long long row = u / bxu;
+        const int ux = (int)(u - row * bxu);
+        const long long cube0 = row * bx + (long long)ux * G::CPW;
+        const long long row_end = min(P.L.ncubes, (row + 1) * bx);
+        const int nvalid = (int)min((long long)G::CPW, row_end - cube0);
+        int16_t *const unit_zz = P.zzg + (size_t)cube0 * G::CS;
+        uint32_t run = 0;
+        for (int k = 0; k < nvalid; k++) {
+            const int16_t *src = P.qcubes_in + (size_t)(cube0 + k) * G::CS;
+            const int chunk = lane;
             uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             uint32_t any = 0;
             if (chunk < G::CHUNKS) {
@@ -622,15 +649,16 @@ zz_gather_kernel(const EncParams P)
                 }
 #pragma unroll
                 for (int i = 0; i < 8; i++) any |= w[i];
-                if (any) {
-                    uint4 *dst = reinterpret_cast<uint4 *>(P.zzg + (size_t)cube * G::CS + chunk * 16);
-                    dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
-                    dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
-                }
             }
-            mask |= __ballot_sync(0xffffffffu, any != 0);
+            const uint32_t bal = __ballot_sync(0xffffffffu, any != 0);
+            if (any) {
+                uint4 *dst = reinterpret_cast<uint4 *>(unit_zz + (size_t)(run + (uint32_t)__popc(bal & ((1u << lane) - 1u))) * 16);
+                dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+                dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+            }
+            run += (uint32_t)__popc(bal);
+            if (lane == 0) P.cmask[cube0 + k] = bal;
         }
-        if (lane == 0) P.cmask[cube] = mask;
     }
 }
 
@@ -641,8 +669,16 @@ zz_gather_kernel(const EncParams P)
 // The serial bit append per thread is latency-bound; it runs at full occupancy so that other
 // warps cover it.
 // ------------------------------------------------------------------------------------------
-constexpr int kPackThreads = 256;
+// Measured and dropped in round 2: a software-pipelined CTA (a ninth "scanner" warp resolves the look-back of tile i while
+// the eight worker warps count tile i+1, aggregates published early): 340 us instead of 173 -- two barriers per tile, a
+// lower occupancy (48 registers) and an idle warp cost more than the 28% barrier stall it was meant to remove.
+constexpr int kPackWorkers = 256;                   // one cube each
+constexpr int kPackThreads = kPackWorkers;
 
+// The CTA is software-pipelined over its tiles: while the scanner warp resolves the bit offset of tile i (decoupled
+// look-back: a chain of global-memory round trips), the 8 worker warps already run the count pass of tile i+1; the write
+// pass of tile i follows the barrier.  (First version: all 8 warps waited at a barrier around the look-back, 28% of the
+// kernel's warp time.)
 template <int C>
 __global__ void __launch_bounds__(kPackThreads)
 eg_pack_kernel(const EncParams P)
@@ -652,18 +688,18 @@ eg_pack_kernel(const EncParams P)
     __shared__ unsigned long long s_off;
     __shared__ long long s_tile;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const long long ntiles = (P.L.ncubes + kPackThreads - 1) / kPackThreads;
+    const long long ntiles = (P.L.ncubes + kPackWorkers - 1) / kPackWorkers;
     const unsigned long long start_bit = P.start_bit_dev ? *P.start_bit_dev : P.start_bit;
     for (;;) {
         if (tid == 0) s_tile = (long long)atomicAdd(P.ticket, 1u);
         __syncthreads();
         const long long tile = s_tile;
         if (tile >= ntiles) break;
-        const long long cube = tile * kPackThreads + tid;
+        const long long cube = tile * kPackWorkers + tid;
         const bool valid = cube < P.L.ncubes;
-        const int16_t *zz = P.zzg + (size_t)(valid ? cube : 0) * G::CS;
+        const int16_t *zz = valid ? cube_chunks<C>(P, cube) : P.zzg;
         const uint32_t cm = valid ? P.cmask[cube] : 0u;
-        const uint32_t nb = valid ? eg_count_cube<G::CS>(zz, cm) : 0u;
+        const uint32_t nb = valid ? eg_count_cube<G::CS, true>(zz, cm) : 0u;
         uint32_t incl = nb;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -698,12 +734,13 @@ eg_pack_kernel(const EncParams P)
                 atomicOr(P.err, 1u);
             } else {
                 GlobalSink sink{P.out_words};
-                eg_write_cube<G::CS>(zz, cm, off, sink);
+                eg_write_cube<G::CS, GlobalSink, true>(zz, cm, off, sink);
             }
         }
         __syncthreads();                        // s_tile / s_wsum / s_off are reused
     }
 }
+#endif
 
 // Placement of a slab range's stream inside the clip's one stream (the rule of ExpGolomb.c:112-130 with
 // encoder.c:263-271): a GPU codes its range from bit 0 of its own buffer; once the bit counts of the ranges before it are

@@ -121,14 +121,16 @@ EG_HD uint32_t eg_chunkmask(const int16_t *zz)
     return mask;
 }
 
-template <int CS>
+// DENSE: zz holds only the cube's non-zero chunks, one after the other in chunk order (the layout of the fused encoder's
+// scratch); otherwise zz is the whole cube and chunk c sits at zz + 16 c.
+template <int CS, bool DENSE = false>
 EG_HD uint32_t eg_count_cube(const int16_t *zz, uint32_t chunkmask)
 {
-    int extra = 0;
-    for (uint32_t mk = chunkmask; mk; mk &= mk - 1) {
+    int extra = 0, j = 0;
+    for (uint32_t mk = chunkmask; mk; mk &= mk - 1, j++) {
         const int c = 31 - clz32(mk & (0u - mk));
         uint32_t w[8];
-        load_chunk(zz, c, w);
+        load_chunk(zz, DENSE ? j : c, w);
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             const uint32_t p = w[i];
@@ -191,16 +193,16 @@ struct BitWriter {
     }
 };
 
-template <int CS, typename Sink>
+template <int CS, typename Sink, bool DENSE = false>
 EG_HD void eg_write_cube(const int16_t *zz, uint32_t chunkmask, uint64_t start_bit, Sink &sink)
 {
     BitWriter<Sink> bw(sink, start_bit);
-    int pos = 0;
-    for (uint32_t mk = chunkmask; mk; mk &= mk - 1) {
+    int pos = 0, j = 0;
+    for (uint32_t mk = chunkmask; mk; mk &= mk - 1, j++) {
         const int c = 31 - clz32(mk & (0u - mk));
         bw.put_ones(16 * c - pos);
         uint32_t w[8];
-        load_chunk(zz, c, w);
+        load_chunk(zz, DENSE ? j : c, w);
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             const uint32_t p = w[i];
