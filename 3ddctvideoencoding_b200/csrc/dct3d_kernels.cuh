@@ -740,7 +740,6 @@ eg_pack_kernel(const EncParams P)
         __syncthreads();                        // s_tile / s_wsum / s_off are reused
     }
 }
-#endif
 
 // Placement of a slab range's stream inside the clip's one stream (the rule of ExpGolomb.c:112-130 with
 // encoder.c:263-271): a GPU codes its range from bit 0 of its own buffer; once the bit counts of the ranges before it are
