@@ -203,3 +203,31 @@ def decode_range(codec, stream, nslabs: int, rank: int, world: int, cubes_per_sl
     hint = int(start_bits[rank + 1]) if start_bits is not None and len(start_bits) > rank + 1 else 0
     frames, _ = codec.decode_u8_range(stream, start, (hi - lo) * codec.cube, hint)
     return frames, start
+
+
+def bind_to_gpu_numa(index: int):
+    """Pins the calling process to the CPUs of GPU `index`'s NUMA node (sysfs local_cpulist of its PCI function), so that
+    its host threads and the page-locked buffers it allocates afterwards (first touch) are local to the GPU's PCIe root.
+    Returns a short description, or None when the topology cannot be read."""
+    import subprocess
+    try:
+        bdf = subprocess.run(["nvidia-smi", "-i", str(index), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        if bdf.count(":") == 2 and len(bdf.split(":")[0]) == 8:
+            bdf = bdf[4:]
+        path = f"/sys/bus/pci/devices/{bdf}/local_cpulist"
+        cpus = set()
+        for part in open(path).read().strip().split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        node = open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip()
+        return f"gpu {index} ({bdf}): numa node {node}, {len(cpus)} cpus"
+    except Exception:   # noqa: BLE001
+        return None

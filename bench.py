@@ -286,6 +286,8 @@ def run_ours(args):
     importlib.import_module(PKG + ".build").build()
     codec = importlib.import_module(PKG + ".codec")
     sh = importlib.import_module(PKG + ".sharding")
+    # the rank's host threads and, by first touch, its page-locked buffers stay on the NUMA node of its GPU
+    numa = sh.bind_to_gpu_numa(local) if world > 1 and not os.environ.get("DCT3D_NO_NUMA_BIND") else None
     W, H, F, cube, scaling, idx = config_of(args)
     total_frames = F * world if scaling == "weak" else F
     nslabs = total_frames // cube
@@ -618,7 +620,7 @@ def run_ours(args):
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": workload_config(args, world),
-            "detail": {"frames_per_gpu": Fr, "warmup_steps_run": nwarm, "tma": c.stat("tma"), "stream_bytes": int(S_total),
+            "detail": {"frames_per_gpu": Fr, "warmup_steps_run": nwarm, "numa_bind": numa, "tma": c.stat("tma"), "stream_bytes": int(S_total),
                        "bits_per_sample": total_bits / (W * H * total_frames),
                        "parallelism": f"slab-range x{world}, one clip, one stream; N bit counts through a host table, no data-path collective"},
             "encode_fps": total_frames / (enc_ms_max * 1e-3), "decode_fps": total_frames / (dec_ms_max * 1e-3),
