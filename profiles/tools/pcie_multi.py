@@ -12,15 +12,8 @@ sys.path.insert(0, ROOT)
 
 
 def gpu_cpus(index):
-    import torch
-    try:
-        bdf = torch.cuda.get_device_properties(index).pci_bus_id if hasattr(torch.cuda.get_device_properties(index), "pci_bus_id") else None
-    except Exception:
-        bdf = None
-    if bdf is None:
-        out = subprocess.run(["nvidia-smi", "-i", str(index), "--query-gpu=pci.bus_id", "--format=csv,noheader"], capture_output=True, text=True).stdout.strip()
-        bdf = out
-    bdf = bdf.lower()
+    out = subprocess.run(["nvidia-smi", "-i", str(index), "--query-gpu=pci.bus_id", "--format=csv,noheader"], capture_output=True, text=True).stdout.strip()
+    bdf = out.lower()
     if bdf.count(":") == 2 and len(bdf.split(":")[0]) == 8:
         bdf = bdf[4:]
     p = f"/sys/bus/pci/devices/{bdf}/local_cpulist"
@@ -33,7 +26,11 @@ def gpu_cpus(index):
             cpus.update(range(int(a), int(b) + 1))
         elif part:
             cpus.add(int(part))
-    return cpus, bdf
+    try:
+        node = open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip()
+    except OSError:
+        node = "?"
+    return cpus, f"{bdf} numa {node}"
 
 
 def worker(rank, world, bind, tag):
