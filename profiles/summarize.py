@@ -88,6 +88,8 @@ def main():
     for r in lrows[1:]:
         if len(r) <= vi or "gpu__time_duration" not in r[lh.index("Metric Name")]:
             continue
+        if not re.search(r"encode_kernel|eg_pack|seg_|reconstruct|transform_kernel|stream_shift|codec_f64|zz_gather|coo_scatter|rgb_planes", r[ki]):
+            continue                                   # torch's own kernels (clip generation)
         v = float(r[vi].replace(",", ""))
         v = v / 1e3 if r[ui] in ("ns", "nsecond") else v
         if main_stream is None:
@@ -106,25 +108,41 @@ def main():
     out.append(f"Sum: {total:.0f} us of kernel time per encode+decode step under ncu (serialised, cold cache).")
     out.append("")
     out.append("Other launches in the same run: " + "; ".join(f"{k} x{len(v)} (mean {sum(v) / len(v):.1f} us)" for k, v in other.items())
-               + " -- the f32 seam measurement and the 16-frame ranges of the e2e leg.")
+               + " -- the chunks of the e2e leg's pipelined calls (and the f32 seam measurement when bench.py runs without --quick).")
     out.append("")
 
     b = json.loads(open(p("bench.json")).read().strip().splitlines()[-1])
     out.append("## bench.py line of the same build")
     out.append("")
+    e2e = b["e2e"]
+    e2e_note = (f"single call {e2e['single_call_value']:.0f}" if "single_call_value" in e2e else
+                f"one encode call + one decode call; two clips in flight: {e2e.get('duplex_value') or 0:.0f}")
     out.append(f"value {b['value']:.0f} {b['unit']} (encode {b['encode_fps']:.0f}, decode {b['decode_fps']:.0f}; "
-               f"{b['ms_per_step']:.3f} ms per step), e2e {b['e2e']['value']:.0f} (single call "
-               f"{b['e2e']['single_call_value']:.0f}), cpu_baseline {b['cpu_baseline']['value']:.2f} on "
-               f"{b['cpu_baseline']['cores']} cores; f32 seams forward {b['roofline_f32_seam']['forward_f32']:.0f} / "
-               f"inverse {b['roofline_f32_seam']['inverse_f32']:.0f} GB/s of {b['roofline_f32_seam']['peak']} GB/s; "
-               f"clocks {b['clocks']['sm_mhz']:.0f}/{b['clocks']['sm_max_mhz']:.0f} MHz, reasons {b['clocks']['reasons']}.")
+               f"{b['ms_per_step']:.3f} ms per step), e2e {e2e['value']:.0f} ({e2e_note}), cpu_baseline "
+               f"{b['cpu_baseline']['value']:.2f} on {b['cpu_baseline']['cores']} cores; f32 seams forward "
+               f"{b['roofline_f32_seam']['forward_f32']:.0f} / inverse {b['roofline_f32_seam']['inverse_f32']:.0f} GB/s of "
+               f"{b['roofline_f32_seam']['peak']} GB/s; clocks {b['clocks']['sm_mhz']:.0f}/{b['clocks']['sm_max_mhz']:.0f} MHz, "
+               f"reasons {b['clocks']['reasons']}.")
     out.append("")
     dom = b["roofline"]
     out.append(f"Dominant kernel by the live CUDA-event timing inside bench.py: `{dom['kernel']}` "
                f"{dom['kernel_ms'] * 1e3:.0f} us = {100 * dom['kernel_ms'] / b['ms_per_step']:.0f}% of the step; "
                "the launch list above gives it the same share of GPU time (within a few points), as the contract asks.")
+    if b.get("parity"):
+        out.append("")
+        out.append("Parity on the benchmark clip (bench.py `parity`, oracle on 4 sampled slabs): " + json.dumps(b["parity"]))
     open(p("summary.md"), "w").write("\n".join(out) + "\n")
     print("\n".join(out))
+    # DRAM traffic per launch of every captured kernel, for bench.py's roofline.traffic
+    ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+    units = rows[1]
+    def to_bytes(v, u):
+        f = float(v.replace(",", ""))
+        return f * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+    traffic = {"source": f"profiles/r{rnd}_full_raw.csv (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch, 1920x1080x256)",
+               "kernels": {k.split("<")[0].replace("dct3d::", ""): {"dram_bytes": to_bytes(r[ir], units[ir]) + to_bytes(r[iw], units[iw]),
+                                              "read": to_bytes(r[ir], units[ir]), "write": to_bytes(r[iw], units[iw])} for k, r in kernels.items()}}
+    json.dump(traffic, open(os.path.join(HERE, "traffic.json"), "w"), indent=1)
 
 
 if __name__ == "__main__":
