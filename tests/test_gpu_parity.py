@@ -377,6 +377,43 @@ def test_c_cli_interoperates_with_reference_cli(codec_mod, oracle, synth, tmp_pa
         assert np.abs(a - b).max() <= 1
 
 
+def test_zero_source_change_mode_runs_the_reference_on_the_gpu(codec_mod, oracle, synth, tmp_path):
+    """the reference's own main.c / encoder.c / decoder.c / ExpGolomb.c / CubeUtils.c, compiled unmodified
+    against host/clshim (host/_refgpu/codec_ref_gpu: its cl* calls are served by dct3d_forward_f32 / dct3d_inverse_f32),
+    produce files that our C codec and the CPU-shimmed reference decode to the same frames (+-1), and decode our files."""
+    import os, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    gpu_ref = os.path.join(root, "host", "_refgpu", "codec_ref_gpu")
+    ours = os.path.join(root, "host", "codec")
+    cpu_ref = os.path.join(root, "oracle", "_ref", "codec_ref")
+    if not os.path.exists(gpu_ref):
+        pytest.skip("host/_refgpu/codec_ref_gpu is built only where the reference checkout exists")
+    W, H, F = 64, 48, 24
+    clip = synth.natural(W, H, F, 1)
+    raw = tmp_path / "in.raw"
+    clip.tofile(raw)
+    args = [str(W), str(H), str(F)]
+    run = lambda exe, *a: subprocess.run([exe, *a], check=True, stdout=subprocess.DEVNULL, cwd=str(tmp_path))
+    read = lambda name: np.fromfile(tmp_path / name, np.uint8).reshape(F, H, W).astype(int)
+    assert b"B200" in subprocess.run([gpu_ref, "list_platforms"], capture_output=True, check=True).stdout
+    run(gpu_ref, "encode", str(raw), "g.enc", *args)
+    run(gpu_ref, "decode", "g.enc", "gg.dec", *args)
+    run(ours, "decode", str(tmp_path / "g.enc"), str(tmp_path / "go.dec"), *args)
+    assert np.abs(read("gg.dec") - read("go.dec")).max() <= 1                  # rule (4), same file, two decoders
+    assert np.abs(read("gg.dec") - clip.astype(int)).mean() < 6.0              # and it is the clip
+    run(ours, "encode", str(raw), str(tmp_path / "o.enc"), *args)
+    run(gpu_ref, "decode", "o.enc", "og.dec", *args)
+    run(ours, "decode", str(tmp_path / "o.enc"), str(tmp_path / "oo.dec"), *args)
+    assert np.abs(read("og.dec") - read("oo.dec")).max() <= 1
+    if os.path.exists(cpu_ref):
+        run(cpu_ref, "decode", "g.enc", "gc.dec", *args)
+        assert np.abs(read("gg.dec") - read("gc.dec")).max() <= 1
+        # the two encoders (GPU butterflies vs the CPU restatement of 3dDCT.cl) differ at most by rounding-tie flips
+        run(cpu_ref, "encode", str(raw), "c.enc", *args)
+        run(cpu_ref, "decode", "c.enc", "cc.dec", *args)
+        assert (read("gg.dec") != read("cc.dec")).mean() < 0.02
+
+
 @pytest.mark.parametrize("world", [2, 4])
 def test_sharded_ranges_equal_one_shot(codec_mod, synth, world):
     """The multi-GPU path, emulated on one GPU: every 'rank' codes its slab range from bit 0 of its own
