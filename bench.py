@@ -595,6 +595,32 @@ def run_ours(args):
         extra["fp64_mode"] = quick_fps(c, f64, 64, reps=3)
         c.set_option("precision", 32)
 
+    # ---- the C codec command line (host/codec: file -> batches -> GPU -> parallel deflate -> file, and back) ------------
+    cli = None
+    if world == 1 and not args.quick and not args.no_cli and os.path.exists(os.path.join(ROOT, "host", "codec")):
+        import tempfile
+        exe = os.path.join(ROOT, "host", "codec")
+        d = tempfile.mkdtemp(prefix="dct3d_cli_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        try:
+            raw, enc, dec = (os.path.join(d, n) for n in ("clip.raw", "clip.dct", "clip.out"))
+            h_frames.numpy().tofile(raw)
+            cli = {"clip": f"{W}x{H}x{Fr} in tmpfs", "cores": os.cpu_count()}
+            for level in (9, 1):
+                env = dict(os.environ, DCT3D_ZLIB_LEVEL=str(level))
+                t0 = time.perf_counter()
+                r1 = subprocess.run([exe, "encode", raw, enc, str(W), str(H), str(Fr), str(local + 1)], env=env, stdout=subprocess.DEVNULL)
+                t1 = time.perf_counter()
+                r2 = subprocess.run([exe, "decode", enc, dec, str(W), str(H), str(Fr), str(local + 1)], env=env, stdout=subprocess.DEVNULL)
+                t2 = time.perf_counter()
+                ok = r1.returncode == 0 and r2.returncode == 0 and bool((np.fromfile(dec, np.uint8) == h_out.numpy().reshape(-1)).all())
+                cli[f"zlib{level}"] = {"encode_fps": Fr / (t1 - t0), "decode_fps": Fr / (t2 - t1), "file_bytes": os.path.getsize(enc),
+                                      "decoded_equals_library_decode": ok}
+            cli["note"] = ("wall clock of the whole process (context creation, file I/O, zlib); deflate runs on all cores "
+                           "(host/pdeflate.c), inflate is one serial zlib stream on its own thread")
+        finally:
+            import shutil
+            shutil.rmtree(d, ignore_errors=True)
+
     # ---- CPU baseline beside it + the four parity rules on the same sample slabs (rank 0, N = 1) -----------------
     cpu = parity = None
     if world == 1 and not args.no_cpu_baseline:
@@ -671,6 +697,7 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "wall_s": t_wall,
+            "cli": cli,
             "extra": extra,
         }
         print(json.dumps(line))
@@ -699,6 +726,7 @@ def main():
     ap.add_argument("--ref-slabs", type=int, default=4, help="reference arm: sample slabs of the workload per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-c", action="store_true")
+    ap.add_argument("--no-cli", action="store_true", help="skip timing the C codec command line")
     ap.add_argument("--quick", action="store_true", help="skip the seam, duplex and extra measurements")
     args = ap.parse_args()
     if args.impl == "reference":
