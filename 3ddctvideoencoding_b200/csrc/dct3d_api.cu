@@ -80,6 +80,7 @@ struct dct3d_ctx {
     int carry_bits = 0;
     // pipelined host-buffer paths (dct3d_encode_u8 / dct3d_decode_u8 and the range calls)
     int chunk_frames = 0;            // option: frames per pipeline chunk (0 = about 32 MB of pixels)
+    long piece_bytes = 0;            // option: stream bytes per upload piece of the pipelined decoder (0 = 8 MiB)
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
     std::vector<cudaEvent_t> pev;    // event pool (no timing)
     DevBuf ring[3];                  // frame chunks in flight
@@ -494,6 +495,11 @@ int dct3d_set_option(dct3d_ctx *ctx, const char *key, long value)
     }
     if (!strcmp(key, "rounding")) { ctx->rounding = value ? 1 : 0; return DCT3D_OK; }
     if (!strcmp(key, "kernel_times_reset")) { ctx->kcalls[0] = ctx->kcalls[1] = 0; return DCT3D_OK; }
+    if (!strcmp(key, "piece_bytes")) {
+        if (value < 0) return fail(ctx, DCT3D_E_INVALID, "piece_bytes must not be negative");
+        ctx->piece_bytes = value;
+        return DCT3D_OK;
+    }
     if (!strcmp(key, "chunk_frames")) {
         if (value < 0 || value % ctx->C) return fail(ctx, DCT3D_E_INVALID, "chunk_frames must be a non-negative multiple of the cube edge");
         ctx->chunk_frames = (int)value;
@@ -751,9 +757,16 @@ int dct3d_eg_encode_i16_dev(dct3d_ctx *ctx, const void *d_qcubes, size_t ncubes,
 struct PartOpts {
     uint64_t count_end_bit = 0;   // codes that start before this bit are counted
     int first_entry = 0;          // DecParams::first_entry
-    uint64_t ncodes = 0;          // out: codes that start in the part
+    // emit = true: a PIECE of a stream that is parsed piece by piece while it is still being uploaded (pipe_decode): the lists
+    // and row pointers of the whole clip are filled in as the pieces arrive, the counts continue from the bases
+    bool emit = false;
+    uint64_t code_base = 0, nz_base = 0;
+    uint64_t ncodes = 0;          // out: codes that start in the part (emit: + code_base)
+    uint64_t nz_total = 0;        // out (emit): non-zero codes so far
     uint32_t over_out = 0;        // out: how far the last of them runs past count_end_bit
     uint32_t entry_used = 0;      // out: entry point of the part's first segment
+    bool complete = false;        // out (emit): the clip's last code lies in this piece ...
+    uint64_t end_bit = 0;         // ... and ends here
 };
 
 static int parse_common(dct3d_ctx *ctx, const void *d_stream, size_t nbytes, uint64_t start_bit, size_t ncubes,
@@ -775,6 +788,8 @@ static int parse_common(dct3d_ctx *ctx, const void *d_stream, size_t nbytes, uin
     P.seg_bits = kSegWords * 32;
     P.count_end_bit = part ? std::min<unsigned long long>(part->count_end_bit, P.nbits_total) : P.nbits_total;
     P.first_entry = part ? part->first_entry : 0;
+    P.code_base = part ? part->code_base : 0;
+    P.nz_base = part ? part->nz_base : 0;
     if (part && (P.count_end_bit <= start_bit || (part->first_entry < 0 && start_bit < 128)))
         return fail(ctx, DCT3D_E_INVALID, "bad stream part");
     P.nseg = (P.count_end_bit - start_bit + P.seg_bits - 1) / P.seg_bits;
@@ -785,7 +800,7 @@ static int parse_common(dct3d_ctx *ctx, const void *d_stream, size_t nbytes, uin
     CU_CHECK(ctx, ctx->seglist.reserve(((n + 31) / 32) * 32 * kSegListVec * sizeof(uint4)));   // dense-addressed, only the heads are touched
     const long long stiles = (long long)((P.nseg + kScanThreads * kScanItems - 1) / (kScanThreads * kScanItems));
     CU_CHECK(ctx, ctx->ctrl.reserve(kCtrlBytes + (size_t)stiles * 16));
-    if (!locate_only && !part) {
+    if (!locate_only && (!part || part->emit)) {
         CU_CHECK(ctx, ctx->coo.reserve(ncubes * CS * sizeof(uint32_t) + 2048));   // worst case: every coefficient non-zero, + the tail of the last segment's list
         CU_CHECK(ctx, ctx->coocnt.reserve((ncubes + 1) * 8));
     }
@@ -818,7 +833,7 @@ static int parse_common(dct3d_ctx *ctx, const void *d_stream, size_t nbytes, uin
         }
         const long long grid = std::min<long long>(stiles, (long long)ctx->num_sms * 8);
         seg_prefix_kernel<<<(unsigned)grid, kScanThreads, 0, st>>>(P, status_words(ctx), status_words(ctx) + stiles, &dc->ticket);
-        if (part) { ctx->launches++; CU_CHECK(ctx, cudaGetLastError()); return DCT3D_OK; }
+        if (part && !part->emit) { ctx->launches++; CU_CHECK(ctx, cudaGetLastError()); return DCT3D_OK; }
         const unsigned pg = (unsigned)std::min<unsigned long long>((P.nseg + kEmitThreads - 1) / kEmitThreads, (unsigned long long)ctx->num_sms * 12);
         if (C == 8) seg_emit_kernel<8><<<pg, kEmitThreads, 0, st>>>(P); else seg_emit_kernel<4><<<pg, kEmitThreads, 0, st>>>(P);
         ctx->launches += 2;
@@ -834,6 +849,7 @@ static int parse_common(dct3d_ctx *ctx, const void *d_stream, size_t nbytes, uin
         if (!part) return DCT3D_OK;
         CU_CHECK(ctx, cudaMemcpyAsync(ctx->h_u64 + 1, P.seg_over + n, 4, cudaMemcpyDeviceToHost, st));
         CU_CHECK(ctx, cudaMemcpyAsync(ctx->h_u64 + 2, P.seg_used, 4, cudaMemcpyDeviceToHost, st));
+        CU_CHECK(ctx, cudaMemcpyAsync(ctx->h_u64 + 3, P.seg_nzfirst + n, 8, cudaMemcpyDeviceToHost, st));
         return DCT3D_OK;
     };
     CU_CHECK(ctx, cudaMemcpyAsync(ctx->h_u64, P.seg_first + n, 8, cudaMemcpyDeviceToHost, st));
@@ -859,6 +875,15 @@ static int parse_common(dct3d_ctx *ctx, const void *d_stream, size_t nbytes, uin
         part->ncodes = ctx->h_u64[0];
         part->over_out = (uint32_t)ctx->h_u64[1];
         part->entry_used = (uint32_t)ctx->h_u64[2];
+        part->nz_total = ctx->h_u64[3];
+        if (part->emit) {
+            part->complete = part->ncodes >= (unsigned long long)ncubes * CS;
+            part->end_bit = ctx->h_ctrl->end_bit;
+            if (part->complete && part->end_bit > P.nbits_total)
+                return fail(ctx, DCT3D_E_NEED_MORE, "the last code runs past the end of the buffered stream");
+            ctx->part_valid = false;
+            return DCT3D_OK;
+        }
         ctx->part_P = P;
         ctx->part_valid = true;
         return DCT3D_OK;
@@ -1165,47 +1190,103 @@ static int pipe_encode(dct3d_ctx *ctx, const uint8_t *frames, int nframes, size_
     return DCT3D_OK;
 }
 
-// Decodes `nframes` frames from a host stream whose bit `start_bit` is the first bit of the first cube; the parsed lists
-// cover the whole range, the inverse transform runs chunk by chunk beside the D2H copies of the frames.
+// Decodes `nframes` frames from a host stream whose bit `start_bit` is the first bit of the first cube.  The stream goes up
+// in pieces (option "piece_bytes", default 8 MiB) and is PARSED PIECE BY PIECE while the later pieces are still on their way:
+// index discovery is local to a piece once the counts and the overhang of the pieces before it are known, so the lists and
+// row pointers of the clip fill in as the pieces arrive, and every slab whose cubes are complete is reconstructed and
+// copied home at once.  (First version: upload all, parse all, then reconstruct chunk by chunk: the frame copies, which
+// bound the call, started 1.7 ms late on a 76 MB stream.)
 static int pipe_decode(dct3d_ctx *ctx, const uint8_t *stream, size_t nbytes, uint64_t start_bit, int nframes, uint8_t *frames, uint64_t *end_bit)
 {
     int rc;
-    const int C = ctx->C, nslabs = nframes / C;
+    const int C = ctx->C, CS = C * C * C, nslabs = nframes / C;
     const size_t slab_bytes = (size_t)ctx->W * ctx->H * C;
     cudaStream_t st = ctx->stream;
     ctx->range_valid = false;
     ctx->clean_ptr = nullptr;                                    // ctx->bits is about to hold foreign bytes
     const size_t padded = ((nbytes + 3) & ~(size_t)3) + 8;
     CU_CHECK(ctx, ctx->bits.reserve(padded));
-    CU_CHECK(ctx, cudaMemsetAsync((uint8_t *)ctx->bits.p + (nbytes & ~(size_t)3), 0, padded - (nbytes & ~(size_t)3), st));
-    H2D(ctx, ctx->bits.p, stream, nbytes);
     const int K = chunk_slabs(ctx, nslabs), nchunks = (nslabs + K - 1) / K;
     ctx->chunks_last = nchunks;
-    if (nchunks <= 1 || ctx->precision == 64) {
-        const size_t n = slab_bytes * nslabs;
-        CU_CHECK(ctx, ctx->ring[0].reserve(n + 16));
-        if ((rc = dct3d_decode_u8_dev(ctx, ctx->bits.p, nbytes, start_bit, nframes, ctx->ring[0].p, end_bit, nullptr))) return rc;
-        D2H(ctx, frames, ctx->ring[0].p, n);
-        SYNC(ctx);
-        return DCT3D_OK;
+    size_t piece = ctx->piece_bytes ? (size_t)ctx->piece_bytes : ((size_t)8 << 20);
+    piece = std::max<size_t>((piece + 4095) & ~(size_t)4095, 4096);
+    const size_t npieces = (nbytes + piece - 1) / piece;
+    if (nchunks <= 1 || ctx->precision == 64 || npieces <= 1) {
+        CU_CHECK(ctx, cudaMemsetAsync((uint8_t *)ctx->bits.p + (nbytes & ~(size_t)3), 0, padded - (nbytes & ~(size_t)3), st));
+        H2D(ctx, ctx->bits.p, stream, nbytes);
+        if (nchunks <= 1 || ctx->precision == 64) {
+            const size_t n = slab_bytes * nslabs;
+            CU_CHECK(ctx, ctx->ring[0].reserve(n + 16));
+            if ((rc = dct3d_decode_u8_dev(ctx, ctx->bits.p, nbytes, start_bit, nframes, ctx->ring[0].p, end_bit, nullptr))) return rc;
+            D2H(ctx, frames, ctx->ring[0].p, n);
+            SYNC(ctx);
+            return DCT3D_OK;
+        }
     }
     for (int b = 0; b < kRing; b++) CU_CHECK(ctx, ctx->ring[b].reserve((size_t)K * slab_bytes + 16));
-    auto ev = [&](int i, int what) { return pipe_event(ctx, (size_t)2 * i + what); };   // 0: chunk reconstructed, 1: chunk on the host
-    if (!ev(nchunks - 1, 1)) return fail(ctx, DCT3D_E_CUDA, "cudaEventCreate failed");
+    // events: one per piece (uploaded), then 2 per reconstruct launch (0: reconstructed, 1: on the host); pieces rarely end on
+    // chunk boundaries, so there can be more launches than ceil(nslabs / K)
+    auto ev_up = [&](size_t p) { return pipe_event(ctx, p); };
+    auto ev = [&](int i, int what) { return pipe_event(ctx, npieces + 1 + (size_t)2 * i + what); };
+    if (!ev(nchunks + (int)npieces + 1, 1)) return fail(ctx, DCT3D_E_CUDA, "cudaEventCreate failed");
     const Layout L = make_layout(ctx->W, ctx->H, C, nslabs);
-    if ((rc = parse_common(ctx, ctx->bits.p, nbytes, start_bit, (size_t)L.ncubes, end_bit, st))) return rc;
-    auto run = [&]() -> int {
-        for (int i = 0; i < nchunks; i++) {
-            const int s0 = i * K, ns = std::min(K, nslabs - s0), b = i % kRing;
-            if (i >= kRing) CU_CHECK(ctx, cudaStreamWaitEvent(st, ev(i - kRing, 1), 0));
+    const size_t cubes_per_slab = (size_t)L.by * L.bx;
+    int slabs_done = 0, chunk = 0;
+    auto reconstruct_upto = [&](int ready_slabs) -> int {        // slabs [slabs_done, ready_slabs): inverse transform + copy home
+        while (slabs_done < ready_slabs) {
+            const int ns = std::min(K, ready_slabs - slabs_done), b = chunk % kRing;
+            if (chunk >= kRing) CU_CHECK(ctx, cudaStreamWaitEvent(st, ev(chunk - kRing, 1), 0));
             const Layout Lc = make_layout(ctx->W, ctx->H, C, ns);
-            const long long base = (long long)s0 * L.by * L.bx;
+            const long long base = (long long)slabs_done * L.by * L.bx;
             if ((rc = C == 8 ? launch_reconstruct_coo<8>(ctx, Lc, ctx->ring[b].p, st, base) : launch_reconstruct_coo<4>(ctx, Lc, ctx->ring[b].p, st, base))) return rc;
-            CU_CHECK(ctx, cudaEventRecord(ev(i, 0), st));
-            CU_CHECK(ctx, cudaStreamWaitEvent(ctx->s_d2h, ev(i, 0), 0));
-            CU_CHECK(ctx, cudaMemcpyAsync(frames + (size_t)s0 * slab_bytes, ctx->ring[b].p, (size_t)ns * slab_bytes, cudaMemcpyDeviceToHost, ctx->s_d2h));
-            CU_CHECK(ctx, cudaEventRecord(ev(i, 1), ctx->s_d2h));
+            CU_CHECK(ctx, cudaEventRecord(ev(chunk, 0), st));
+            CU_CHECK(ctx, cudaStreamWaitEvent(ctx->s_d2h, ev(chunk, 0), 0));
+            CU_CHECK(ctx, cudaMemcpyAsync(frames + (size_t)slabs_done * slab_bytes, ctx->ring[b].p, (size_t)ns * slab_bytes, cudaMemcpyDeviceToHost, ctx->s_d2h));
+            CU_CHECK(ctx, cudaEventRecord(ev(chunk, 1), ctx->s_d2h));
+            slabs_done += ns;
+            chunk++;
         }
+        return DCT3D_OK;
+    };
+    auto run = [&]() -> int {
+        if (npieces <= 1) {                                      // a small stream: parse it whole
+            if ((rc = parse_common(ctx, ctx->bits.p, nbytes, start_bit, (size_t)L.ncubes, end_bit, st))) return rc;
+            if ((rc = reconstruct_upto(nslabs))) return rc;
+            CU_CHECK(ctx, cudaStreamSynchronize(ctx->s_d2h));
+            return DCT3D_OK;
+        }
+        // all uploads are queued at once on the copy stream (zero padding first: it overlaps the last word of the stream)
+        CU_CHECK(ctx, cudaMemsetAsync((uint8_t *)ctx->bits.p + (nbytes & ~(size_t)3), 0, padded - (nbytes & ~(size_t)3), ctx->s_h2d));
+        for (size_t p = 0; p < npieces; p++) {
+            const size_t off = p * piece, len = std::min(piece, nbytes - off);
+            CU_CHECK(ctx, cudaMemcpyAsync((uint8_t *)ctx->bits.p + off, stream + off, len, cudaMemcpyHostToDevice, ctx->s_h2d));
+            CU_CHECK(ctx, cudaEventRecord(ev_up(p), ctx->s_h2d));
+        }
+        PartOpts po;
+        po.emit = true;
+        uint64_t bit0 = start_bit;
+        bool complete = false;
+        for (size_t p = 0; p < npieces && !complete; p++) {
+            const bool final = p == npieces - 1;
+            const size_t uploaded = std::min(nbytes, (p + 1) * piece);
+            // codes that start 16 bytes or more before the end of what is on the device are there in full, look-ahead included
+            const uint64_t count_end = final ? (uint64_t)nbytes * 8 : (uint64_t)(uploaded - 16) * 8;
+            if (count_end <= bit0) continue;
+            CU_CHECK(ctx, cudaStreamWaitEvent(st, ev_up(p), 0));
+            po.count_end_bit = count_end;
+            if ((rc = parse_common(ctx, ctx->bits.p, final ? nbytes : uploaded, bit0, (size_t)L.ncubes, nullptr, st, false, nullptr, &po))) return rc;
+            po.code_base = po.ncodes;                            // the next piece continues where this one stopped
+            po.nz_base = po.nz_total;
+            po.first_entry = (int)po.over_out + 1;
+            bit0 = count_end;
+            complete = po.complete;
+            // a cube can be reconstructed once its successor's first code has been seen (that is when its row pointer is final)
+            const size_t ready_cubes = complete ? (size_t)L.ncubes : (po.ncodes ? (size_t)((po.ncodes - 1) / CS) : 0);
+            if ((rc = reconstruct_upto((int)(ready_cubes / cubes_per_slab)))) return rc;
+        }
+        if (!complete)
+            return fail(ctx, DCT3D_E_NEED_MORE, "stream holds %llu codes, %llu needed", (unsigned long long)po.ncodes, (unsigned long long)L.ncubes * CS);
+        if (end_bit) *end_bit = po.end_bit;
         CU_CHECK(ctx, cudaStreamSynchronize(ctx->s_d2h));
         return DCT3D_OK;
     };

@@ -859,6 +859,8 @@ struct DecParams {
     unsigned long long start_bit;
     unsigned long long count_end_bit;   // codes that START before this bit are counted (= nbits_total, except for a part of a stream
                                         // whose successor part is counted by another GPU: the window then extends past it)
+    unsigned long long code_base, nz_base;   // codes / non-zero codes of the clip in front of start_bit (a later piece of a stream
+                                             // that is parsed piece by piece: the prefix sums continue, lists and row pointers are global)
     int first_entry;                    // entry point of segment 0: 0 = the stream's first code starts at start_bit; -1 = unknown,
                                         // guess it like any other segment's (a part in the middle of a stream; needs 128 bits of
                                         // stream in front of start_bit); > 0 = that many bits + 1 (a verified overhang)
@@ -996,7 +998,7 @@ seg_prefix_kernel(const DecParams P, unsigned long long *status_codes, unsigned 
             for (int d = 1; d < 32; d <<= 1) { const unsigned long long o = __shfl_up_sync(0xffffffffu, wi, d); if (lane >= d) wi += o; }
             if (lane < kScanThreads / 32) s_wsum[q][lane] = wi - w;
             const unsigned long long total = __shfl_sync(0xffffffffu, wi, 31);
-            const unsigned long long off = tile_lookback(q == 0 ? status_codes : status_nz, tile, total, 0ull, lane, P.err);
+            const unsigned long long off = tile_lookback(q == 0 ? status_codes : status_nz, tile, total, q == 0 ? P.code_base : P.nz_base, lane, P.err);
             if (lane == 0) {
                 s_off[q] = off;
                 if (tile == ntiles - 1) (q == 0 ? P.seg_first : P.seg_nzfirst)[P.nseg] = off + total;

@@ -605,17 +605,25 @@ def run_ours(args):
             raw, enc, dec = (os.path.join(d, n) for n in ("clip.raw", "clip.dct", "clip.out"))
             h_frames.numpy().tofile(raw)
             cli = {"clip": f"{W}x{H}x{Fr} in tmpfs", "cores": os.cpu_count()}
+            def loop_s(err):                                   # "dct3d-cli ...: setup a s, loop b s, total c s" (DCT3D_CLI_TIMING)
+                for line in err.splitlines():
+                    if line.startswith("dct3d-cli"):
+                        return float(line.split("loop")[1].split("s")[0])
+                return None
             for level in (9, 1):
-                env = dict(os.environ, DCT3D_ZLIB_LEVEL=str(level))
+                env = dict(os.environ, DCT3D_ZLIB_LEVEL=str(level), DCT3D_CLI_TIMING="1")
                 t0 = time.perf_counter()
-                r1 = subprocess.run([exe, "encode", raw, enc, str(W), str(H), str(Fr), str(local + 1)], env=env, stdout=subprocess.DEVNULL)
+                r1 = subprocess.run([exe, "encode", raw, enc, str(W), str(H), str(Fr), str(local + 1)], env=env, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True)
                 t1 = time.perf_counter()
-                r2 = subprocess.run([exe, "decode", enc, dec, str(W), str(H), str(Fr), str(local + 1)], env=env, stdout=subprocess.DEVNULL)
+                r2 = subprocess.run([exe, "decode", enc, dec, str(W), str(H), str(Fr), str(local + 1)], env=env, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True)
                 t2 = time.perf_counter()
                 ok = r1.returncode == 0 and r2.returncode == 0 and bool((np.fromfile(dec, np.uint8) == h_out.numpy().reshape(-1)).all())
-                cli[f"zlib{level}"] = {"encode_fps": Fr / (t1 - t0), "decode_fps": Fr / (t2 - t1), "file_bytes": os.path.getsize(enc),
+                le, ld = loop_s(r1.stderr), loop_s(r2.stderr)
+                cli[f"zlib{level}"] = {"encode_fps": Fr / le if le else None, "decode_fps": Fr / ld if ld else None,
+                                      "encode_process_s": t1 - t0, "decode_process_s": t2 - t1, "file_bytes": os.path.getsize(enc),
                                       "decoded_equals_library_decode": ok}
-            cli["note"] = ("wall clock of the whole process (context creation, file I/O, zlib); deflate runs on all cores "
+            cli["note"] = ("*_fps: the codec's batch loop (file read -> GPU -> deflate -> file write and back), after context creation and "
+                           "buffer allocation; *_process_s: wall clock of the whole process; deflate runs on all cores "
                            "(host/pdeflate.c), inflate is one serial zlib stream on its own thread")
         finally:
             import shutil

@@ -15,10 +15,13 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include <zlib.h>
 
 #include "../include/dct3d.h"
 #include "codec.h"
+
+static double now_s(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9 * t.tv_nsec; }
 
 /* ---- output: frames of batch i are written while batch i+1 is decoded into the other buffer ------------------ */
 typedef struct {
@@ -115,6 +118,7 @@ static void *inflater_main(void *arg)
 
 int decode(char *inputFileName, char *outputFileName, int width, int height, int framesToDecode, int platformIndex)
 {
+    const double t_start = now_s();
     const size_t slabBytes = (size_t)width * height * DCT_BLOCK_DEPTH;
     const char *bs = getenv("DCT3D_BATCH_SLABS");
     int devices[64];
@@ -156,6 +160,7 @@ int decode(char *inputFileName, char *outputFileName, int width, int height, int
     }
 
     printf("Starting decoding process\n");
+    const double t_loop = now_s();
     int slabsDone = 0, cur = 0, rc = 0, inflated_all = 0;
     uint64_t bitpos = 0;
     size_t want = 0;                   /* bytes the window should hold before the next attempt (an estimate that only grows on NEED_MORE) */
@@ -242,6 +247,8 @@ int decode(char *inputFileName, char *outputFileName, int width, int height, int
     fclose(inputFile);
     dct3d_multi_destroy(ctx);
     dct3d_host_free(expGolombCodedData); dct3d_host_free(writer.buf[0]); dct3d_host_free(writer.buf[1]);
+    if (getenv("DCT3D_CLI_TIMING"))
+        fprintf(stderr, "dct3d-cli decode: setup %.3f s, loop %.3f s, total %.3f s\n", t_loop - t_start, now_s() - t_loop, now_s() - t_start);
     if (!rc) printf("Decoding process completed");
     return rc;
 }

@@ -23,12 +23,15 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include <unistd.h>
 #include <zlib.h>
 
 #include "../include/dct3d.h"
 #include "codec.h"
 #include "pdeflate.h"
+
+static double now_s(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9 * t.tv_nsec; }
 
 /* Input side of the batch pipeline: two page-locked buffers, filled in turn by the reader thread. */
 typedef struct {
@@ -87,6 +90,7 @@ static void *batch_reader_main(void *arg)
 
 int encode(char *inputFileName, char *outputFileName, int width, int height, int framesToEncode, int platformIndex)
 {
+    const double t_start = now_s();
     const size_t slabBytes = (size_t)width * height * DCT_BLOCK_DEPTH;
     const char *bs = getenv("DCT3D_BATCH_SLABS");
     int devices[64];
@@ -108,7 +112,7 @@ int encode(char *inputFileName, char *outputFileName, int width, int height, int
     /* page-locked staging buffers: the batch goes to the GPU at PCIe speed */
     reader.buf[0] = (unsigned char *)dct3d_host_alloc(batchBytes);
     reader.buf[1] = (unsigned char *)dct3d_host_alloc(batchBytes);
-    const size_t egCap = 4 * batchBytes + 64;                                          /* worst case, bounds-checked by the library */
+    size_t egCap = batchBytes / 2 + 4096;                        /* 4 bit/sample; grown on DCT3D_E_OVERFLOW (worst case 4 bytes/sample) */
     unsigned char *expGolombBuffer = (unsigned char *)dct3d_host_alloc(egCap);
     if (!reader.buf[0] || !reader.buf[1] || !expGolombBuffer) { printf("Error allocating host buffers\n"); return 1; }
 
@@ -137,6 +141,7 @@ int encode(char *inputFileName, char *outputFileName, int width, int height, int
     pthread_create(&readerThread, NULL, batch_reader_main, &reader);
 
     printf("Starting encoding process\n");
+    const double t_loop = now_s();
     int framesRead = 0, slabsDone = 0, cur = 0, rc = 0;
     while (slabsDone < totalSlabs) {
         const int n = totalSlabs - slabsDone < batchSlabs ? totalSlabs - slabsDone : batchSlabs;
@@ -154,8 +159,16 @@ int encode(char *inputFileName, char *outputFileName, int width, int height, int
 
         /* DCT + quantization + zig-zag + Exp-Golomb on the GPU; complete bytes come back */
         size_t expGolombCodedDataSize = 0;
-        if (dct3d_multi_stream_encode(ctx, frames, n * DCT_BLOCK_DEPTH, last, expGolombBuffer, egCap,
-                                      &expGolombCodedDataSize) != DCT3D_OK) {
+        int er;
+        /* a failed call leaves the carried partial byte untouched, so it can be repeated with a larger buffer */
+        while ((er = dct3d_multi_stream_encode(ctx, frames, n * DCT_BLOCK_DEPTH, last, expGolombBuffer, egCap,
+                                               &expGolombCodedDataSize)) == DCT3D_E_OVERFLOW && egCap < 4 * batchBytes + 64) {
+            dct3d_host_free(expGolombBuffer);
+            egCap = egCap * 4 < 4 * batchBytes + 64 ? egCap * 4 : 4 * batchBytes + 64;
+            expGolombBuffer = (unsigned char *)dct3d_host_alloc(egCap);
+            if (!expGolombBuffer) { printf("Error allocating host buffers\n"); return 1; }
+        }
+        if (er != DCT3D_OK) {
             printf("Error encoding slab: %s\n", dct3d_multi_last_error(ctx));
             rc = 1;
             break;
@@ -181,12 +194,14 @@ int encode(char *inputFileName, char *outputFileName, int width, int height, int
     pthread_cond_broadcast(&reader.cv);
     pthread_mutex_unlock(&reader.mu);
     pthread_join(readerThread, NULL);
-    if (pdeflate_close(zlibStream, NULL, NULL) && !rc) { printf("Error deflating output\n"); rc = 1; }
+    if (pdeflate_close(zlibStream, NULL, NULL) && !rc) { printf("Error deflating output\n"); rc = 1; }   /* waits for the deflate workers */
     fflush(outputFile);
     fclose(outputFile);
     close(reader.fd);
     dct3d_multi_destroy(ctx);
     dct3d_host_free(reader.buf[0]); dct3d_host_free(reader.buf[1]); dct3d_host_free(expGolombBuffer);
+    if (getenv("DCT3D_CLI_TIMING"))
+        fprintf(stderr, "dct3d-cli encode: setup %.3f s, loop %.3f s, total %.3f s\n", t_loop - t_start, now_s() - t_loop, now_s() - t_start);
     if (!rc) printf("Encoding process completed");
     return rc;
 }

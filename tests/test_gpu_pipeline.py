@@ -52,6 +52,38 @@ def test_pipelined_calls_equal_one_shot(codec_mod, oracle, synth, W, H, F, cube,
         assert nbits2 == nbits and again.tobytes() == stream.tobytes()
 
 
+@pytest.mark.parametrize("kind,piece", [("natural", 4096), ("natural", 20480), ("noise", 8192), ("constant", 4096)])
+def test_decode_parses_the_stream_piece_by_piece(codec_mod, synth, kind, piece):
+    """The pipelined decoder uploads the stream in pieces and parses each piece as it arrives (counts, overhang and list
+    ranks carried from piece to piece): same frames and end bit as the one-shot decode, for piece sizes that cut codes,
+    cubes and slabs anywhere; a stream that ends early is reported."""
+    W, H, F = 128, 64, 64
+    clip = synth.natural(W, H, F, 23) if kind == "natural" else synth.noise(W, H, F, 24) if kind == "noise" else synth.constant(W, H, F, 77)
+    with codec_mod.Codec(W, H, 8) as c:
+        c.set_option("chunk_frames", 1 << 20)
+        stream, nbits = c.encode_u8(clip, cap=4 * clip.size + 4096)
+        want = c.decode_u8(stream, F)
+        c.set_option("chunk_frames", 16)
+        c.set_option("piece_bytes", piece)
+        assert stream.size > 2 * piece
+        got, end = c.decode_u8_range(stream, 0, F)
+        assert end == nbits and (got == want).all()
+        # from a bit offset inside a longer buffer, with trailing bytes after the clip
+        pad = np.concatenate([np.full(5, 0xFF, np.uint8), np.zeros(0, np.uint8)])
+        shifted = pkg("sharding").shift_to_phase(stream, nbits, 3)
+        buf = np.concatenate([pad, shifted, np.full(9000, 0xFF, np.uint8)])
+        got2, end2 = c.decode_u8_range(buf, 5 * 8 + 3, F)
+        assert end2 == 5 * 8 + 3 + nbits and (got2 == want).all()
+        # truncated streams: an error at every cut position class
+        for cut in (stream.size // 3, stream.size - piece - 7, stream.size - 2):
+            with pytest.raises(codec_mod.Dct3dError):
+                c.decode_u8(stream[:cut], F)
+        # streaming decode asks for more instead
+        assert c.stream_decode(stream[: stream.size // 2], 0, F) is None
+        res = c.stream_decode(stream, 0, F)
+        assert res is not None and res[1] == nbits and (res[0] == want).all()
+
+
 def test_pipelined_noise_content(codec_mod, synth):
     """Dense content (3.3 bit/sample): long lists, large stream; chunks of one slab."""
     W, H, F = 128, 64, 32
