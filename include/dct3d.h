@@ -71,6 +71,9 @@ void dct3d_host_free(void *p);
  * beyond it in between.
  * "debug" (1 = print per-stage diagnostics to stderr).
  * "chunk_frames" (default 0 = about 32 MB of pixels): frames per pipeline chunk of the host-buffer calls.
+ * "piece_bytes" (default 0 = 32 MiB): stream bytes per upload piece of the host-buffer decoders, which parse a stream piece
+ * by piece while the later pieces are still being copied to the GPU.
+ * "kernel_times_reset": restarts the ring of kernel-time events behind the ns_*_kernel_avg statistics.
  * "precision" (32 [default] or 64): with 64 the fused and stage entry points (encode_u8, decode_u8, quantize_u8,
  * reconstruct_i16 and the streaming calls) compute in double like the Java reference (J/dct/DCT.java:41-59,
  * J/Encoder.java:82, J/Decoder.java:89,112): quantised cubes then equal the fp64 oracle without rounding-tie
