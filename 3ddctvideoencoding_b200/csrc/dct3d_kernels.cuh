@@ -429,8 +429,15 @@ struct EncSmem {
     static constexpr int TOTAL = BAR_OFF + kWarps * 16;
 };
 
+// Resident CTAs per SM (measured, round 2, 1920x1080x256): 4 CTAs = 128 registers (20 B of spills, tid-derived values re-read
+// from S2R all over the loop) 418 us; 3 CTAs = 168 registers, no spills, 5% fewer instructions: 394 us; 5 CTAs = 96 registers:
+// 607 us.  The kernel is issue-bound, so instructions count for more than resident warps.  Storing every quantised value
+// instead of only the non-zero ones (no compare, 64 unconditional STS.U16 per thread) loads the shared-memory pipe: 450-459 us.
+#ifndef DCT3D_ENC_CTAS
+#define DCT3D_ENC_CTAS 3
+#endif
 template <int C, int MODE>
-__global__ void __launch_bounds__(kThreads, 4)
+__global__ void __launch_bounds__(kThreads, DCT3D_ENC_CTAS)
 encode_kernel(const __grid_constant__ CUtensorMap tmap, const EncParams P)
 {
     using G = Geo<C>;
@@ -1219,7 +1226,8 @@ __device__ __forceinline__ void idct_store(float (&b)[C][C], uint8_t *xbuf, int 
 // Occupancy note (measured, round 2): the kernel runs 4 CTAs = 16 warps per SM at 128 registers.  Buying a fifth or sixth
 // CTA with fewer registers (96: 16 bytes of spills, 80: 144 bytes) and with the exchange buffer aliased onto the cubes made
 // it SLOWER (388 -> 417 us for the aliasing alone, 442 us at 5 CTAs, 528 us at 6): the shared-memory pipe and the issue slots
-// are co-limiters, so extra wipes and spill traffic cost more than the extra warps hide.
+// are co-limiters, so extra wipes and spill traffic cost more than the extra warps hide.  Allowing fewer CTAs changes nothing:
+// the compiler does not want more than 128 registers here.
 template <int C>
 struct CooSmem {
     using G = Geo<C>;
