@@ -686,8 +686,9 @@ constexpr int kPackThreads = kPackWorkers;
 // look-back: a chain of global-memory round trips), the 8 worker warps already run the count pass of tile i+1; the write
 // pass of tile i follows the barrier.  (First version: all 8 warps waited at a barrier around the look-back, 28% of the
 // kernel's warp time.)
+// 8 CTAs per SM = 32 registers = full occupancy: the serial bit append is latency-bound (39 registers at 6 CTAs: +6%)
 template <int C>
-__global__ void __launch_bounds__(kPackThreads)
+__global__ void __launch_bounds__(kPackThreads, 8)
 eg_pack_kernel(const EncParams P)
 {
     using G = Geo<C>;
