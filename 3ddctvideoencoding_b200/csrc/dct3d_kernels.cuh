@@ -1082,22 +1082,26 @@ seg_emit_kernel(const DecParams P)
             const uint32_t rel = e >> 17;
             P.coo[dst] = ((uint32_t)s_lin[(sp + rel) & (G::CS - 1)] << 16) | ((uint32_t)eg_unmap(e & 0x1ffffu) & 0xffffu);
         };
-        for (int s0 = 0; s0 < 32; s0 += 4) {
-            uint32_t sc[4], sp[4], e[4];
-            unsigned long long sz[4];
+#ifndef DCT3D_EMIT_FLIGHT
+#define DCT3D_EMIT_FLIGHT 4
+#endif
+        constexpr int NF = DCT3D_EMIT_FLIGHT;                        // lists in flight per warp
+        for (int s0 = 0; s0 < 32; s0 += NF) {
+            uint32_t sc[NF], sp[NF], e[NF];
+            unsigned long long sz[NF];
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
+            for (int q = 0; q < NF; q++) {
                 sc[q] = __shfl_sync(0xffffffffu, cnt, s0 + q);
                 sp[q] = __shfl_sync(0xffffffffu, pos0, s0 + q);
                 sz[q] = __shfl_sync(0xffffffffu, zr, s0 + q);
             }
 #pragma unroll
-            for (int q = 0; q < 4; q++) e[q] = (uint32_t)lane < sc[q] ? entry(s0 + q, lane) : 0u;
+            for (int q = 0; q < NF; q++) e[q] = (uint32_t)lane < sc[q] ? entry(s0 + q, lane) : 0u;
 #pragma unroll
-            for (int q = 0; q < 4; q++)
+            for (int q = 0; q < NF; q++)
                 if ((uint32_t)lane < sc[q]) emit_one(e[q], sp[q], sz[q] + lane);
 #pragma unroll
-            for (int q = 0; q < 4; q++)                              // lists longer than a warp: dense content
+            for (int q = 0; q < NF; q++)                             // lists longer than a warp: dense content
                 for (uint32_t i = 32 + lane; i < sc[q]; i += 32) emit_one(entry(s0 + q, i), sp[q], sz[q] + i);
         }
 

@@ -493,6 +493,11 @@ def run_ours(args):
         te_s += tb - ta
         e2e_decode()
         phases += np.array(e2e_state.get("phases", [tb - ta, 0, 0, 0]) + [time.perf_counter() - tb])
+        if xch is not None:
+            # the ranks start every step together: on this pool's hosts the links carry 110 GB/s when every GPU copies the same
+            # way but 51 GB/s each way when some upload while others download, so a rank that ran ahead into its next encode
+            # would slow everybody's decode (measured: 17.8 k -> 21 k frames/s at 2 GPUs)
+            xch.all_gather(0)
     host_barrier()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     te2 = torch.tensor([e2e_s, te_s / e2e_steps, concat_s / e2e_steps], dtype=torch.float64, device=dev)

@@ -25,6 +25,11 @@ def t(fn, reps=5):
 res = {"range_bytes": n}
 for phase in (0, 3):
     res[f"place_pinned_phase{phase}_ms"] = t(lambda: L.dct3d_encode_u8_place(c.h, phase, 1, pinned.data_ptr(), cap, C.byref(fb)))
+# destinations whose alignment differs from the source's (the range's first byte lands at an arbitrary byte of the stream)
+big = torch.zeros(cap + (1 << 20), dtype=torch.uint8, pin_memory=True)
+for off in (0, 4, 1, 2, 3, 12345, 12346, 12347, 12348):
+    sb = off * 8 + 3
+    res[f"place_pinned_byte0={off}_ms"] = t(lambda: L.dct3d_encode_u8_place(c.h, sb, 1, big.data_ptr(), cap + (1 << 20), C.byref(fb)))
 pn = pinned.numpy()
 def cp(): shm[:n] = pn[:n]
 res["memcpy_pinned_to_shm_ms"] = t(cp)
