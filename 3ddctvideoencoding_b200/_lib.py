@@ -37,6 +37,8 @@ SYMBOLS = {
     "dct3d_multi_encode_u8": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_size_t, _u64p, _szp, _u64p]),
     "dct3d_multi_locate": (C.c_int, [_vp, _vp, C.c_size_t, C.c_int, _u64p]),
     "dct3d_multi_decode_u8": (C.c_int, [_vp, _vp, C.c_size_t, C.c_int, _vp, _u64p]),
+    "dct3d_multi_set_weights": (C.c_int, [_vp, C.POINTER(C.c_double)]),
+    "dct3d_multi_probe_links": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "dct3d_multi_stream_begin": (C.c_int, [_vp]),
     "dct3d_multi_stream_encode": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, C.c_size_t, _szp]),
     "dct3d_multi_stream_decode": (C.c_int, [_vp, _vp, C.c_size_t, _u64p, C.c_int, _vp]),

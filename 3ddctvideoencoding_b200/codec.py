@@ -344,6 +344,17 @@ class MultiCodec:
         self._check(self.L.dct3d_multi_encode_u8(self.h, _ptr(fr), F, _ptr(out), cap, C.byref(nbits), C.byref(nbytes), starts))
         return out[: nbytes.value], nbits.value, list(starts)
 
+    def set_weights(self, weights=None):
+        """Shares of the slabs per GPU (None = equal)."""
+        arr = None if weights is None else (C.c_double * self.n)(*[float(w) for w in weights])
+        self._check(self.L.dct3d_multi_set_weights(self.h, arr))
+
+    def probe_links(self):
+        """-> (h2d GB/s, d2h GB/s, proposed weights) per GPU, all GPUs copying at once."""
+        up, down, w = ((C.c_double * self.n)() for _ in range(3))
+        self._check(self.L.dct3d_multi_probe_links(self.h, up, down, w))
+        return list(up), list(down), list(w)
+
     def stream_begin(self):
         self._check(self.L.dct3d_multi_stream_begin(self.h))
 

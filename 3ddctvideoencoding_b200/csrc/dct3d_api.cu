@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <condition_variable>
 #include <functional>
 #include <mutex>
@@ -1446,6 +1447,7 @@ struct dct3d_multi {
     std::string err;
     uint8_t carry_byte = 0;          // streaming state (dct3d_multi_stream_*), as in dct3d_ctx
     int carry_bits = 0;
+    std::vector<double> weight;      // share of the slabs every GPU gets (empty = equal shares): dct3d_multi_set_weights
 };
 
 namespace {
@@ -1482,6 +1484,17 @@ void slab_range(int nslabs, int g, int G, int &lo, int &hi)
 {
     lo = (int)((long long)g * nslabs / G);
     hi = (int)((long long)(g + 1) * nslabs / G);
+}
+
+// the same with the context's weights: GPU g gets slabs [round(n W_g), round(n W_{g+1})), W = normalised cumulative weights
+void slab_range_w(const dct3d_multi *m, int nslabs, int g, int &lo, int &hi)
+{
+    const int G = (int)m->ctx.size();
+    if (m->weight.empty()) { slab_range(nslabs, g, G, lo, hi); return; }
+    double total = 0, before = 0;
+    for (int j = 0; j < G; j++) { total += m->weight[j]; if (j < g) before += m->weight[j]; }
+    lo = g == 0 ? 0 : (int)(nslabs * (before / total) + 0.5);
+    hi = g == G - 1 ? nslabs : (int)(nslabs * ((before + m->weight[g]) / total) + 0.5);
 }
 
 // first failure of the per-GPU calls, with the failing context's message
@@ -1530,6 +1543,63 @@ int dct3d_multi_set_option(dct3d_multi *m, const char *key, long value)
     return DCT3D_OK;
 }
 
+int dct3d_multi_set_weights(dct3d_multi *m, const double *weights)
+{
+    if (!m) return mfail(nullptr, DCT3D_E_INVALID, "null context");
+    m->weight.clear();
+    if (!weights) return DCT3D_OK;                               // back to equal shares
+    double total = 0;
+    for (size_t g = 0; g < m->ctx.size(); g++) {
+        if (!(weights[g] >= 0)) return mfail(m, DCT3D_E_INVALID, "weights must not be negative");
+        total += weights[g];
+    }
+    if (!(total > 0)) return mfail(m, DCT3D_E_INVALID, "weights must not all be zero");
+    m->weight.assign(weights, weights + m->ctx.size());
+    return DCT3D_OK;
+}
+
+int dct3d_multi_probe_links(dct3d_multi *m, double *h2d_gbs, double *d2h_gbs, double *weights)
+{
+    if (!m) return mfail(nullptr, DCT3D_E_INVALID, "null context");
+    const int G = (int)m->ctx.size();
+    const size_t n = (size_t)32 << 20;
+    const int reps = 6;
+    std::vector<int> rcs(G, 0);
+    std::vector<double> up(G, 0), down(G, 0);
+    HostBarrier bar(G);
+    auto work = [&](int g) {
+        dct3d_ctx *ctx = m->ctx[g];
+        void *h = nullptr;
+        if ((rcs[g] = bind(ctx))) { bar.wait(); bar.wait(); bar.wait(); return; }
+        if (ctx->ring[0].reserve(n) != cudaSuccess || !(h = dct3d_host_alloc(n))) rcs[g] = fail(ctx, DCT3D_E_CUDA, "link probe: allocation failed");
+        for (int dir = 0; dir < 2; dir++) {
+            bar.wait();                                          // every GPU copies the same way at the same time
+            if (rcs[g]) continue;
+            const auto t0 = std::chrono::steady_clock::now();
+            for (int r = 0; r < reps; r++)
+                cudaMemcpyAsync(dir ? h : ctx->ring[0].p, dir ? ctx->ring[0].p : h, n, dir ? cudaMemcpyDeviceToHost : cudaMemcpyHostToDevice, ctx->stream);
+            if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { rcs[g] = fail(ctx, DCT3D_E_CUDA, "link probe: copy failed"); continue; }
+            const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            (dir ? down : up)[g] = (double)n * reps / s / 1e9;
+        }
+        bar.wait();
+        if (h) dct3d_host_free(h);
+    };
+    std::vector<std::thread> th;
+    for (int g = 1; g < G; g++) th.emplace_back(work, g);
+    work(0);
+    for (auto &t : th) t.join();
+    const int rc = first_failure(m, rcs);
+    if (rc) return rc;
+    for (int g = 0; g < G; g++) {
+        if (h2d_gbs) h2d_gbs[g] = up[g];
+        if (d2h_gbs) d2h_gbs[g] = down[g];
+        // a frame crosses the link once each way in an encode + decode: time per frame ~ 1/up + 1/down
+        if (weights) weights[g] = 1.0 / (1.0 / up[g] + 1.0 / down[g]);
+    }
+    return DCT3D_OK;
+}
+
 dct3d_ctx *dct3d_multi_context(dct3d_multi *m, int index)
 {
     return (m && index >= 0 && index < (int)m->ctx.size()) ? m->ctx[index] : nullptr;
@@ -1558,7 +1628,7 @@ int dct3d_multi_encode_u8(dct3d_multi *m, const uint8_t *frames, int nframes, ui
     HostBarrier bar(G);
     auto work = [&](int g) {
         int lo, hi;
-        slab_range(nslabs, g, G, lo, hi);
+        slab_range_w(m, nslabs, g, lo, hi);
         rcs[g] = dct3d_encode_u8_range(m->ctx[g], frames + (size_t)lo * slab_bytes, (hi - lo) * C, &bits[g]);
         bar.wait();                                              // every GPU's bit count is known
         for (int j = 0; j < G; j++) if (rcs[j]) return;
@@ -1646,7 +1716,7 @@ int multi_discover(dct3d_multi *m, const uint8_t *stream, size_t nbytes, uint64_
     const uint64_t total_bits = (uint64_t)nbytes * 8;
     if (total_bits <= start_bit) return mfail(m, DCT3D_E_NEED_MORE, "stream holds no data past the start bit");
     std::vector<int> lo(G + 1, nslabs);
-    for (int g = 0; g < G; g++) { int hi; slab_range(nslabs, g, G, lo[g], hi); }
+    for (int g = 0; g < G; g++) { int hi; slab_range_w(m, nslabs, g, lo[g], hi); }
     std::vector<int> rcs(G, 0);
     const uint64_t span = total_bits - start_bit;
     if (span < (uint64_t)G * (1u << 19)) {
@@ -1730,7 +1800,7 @@ int dct3d_multi_decode_u8(dct3d_multi *m, const uint8_t *stream, size_t nbytes, 
     std::vector<int> rcs(G, 0);
     auto work = [&](int g) {
         int lo, hi;
-        slab_range(nslabs, g, G, lo, hi);
+        slab_range_w(m, nslabs, g, lo, hi);
         if (hi == lo) return;
         // the range's last bit when known (the next non-empty range's first): bounds the H2D copy of the stream
         uint64_t hint = 0;
@@ -1775,7 +1845,7 @@ int dct3d_multi_stream_encode(dct3d_multi *m, const uint8_t *frames, int nframes
     const uint64_t carry = (uint64_t)m->carry_bits;
     auto work = [&](int g) {
         int lo, hi;
-        slab_range(nslabs, g, G, lo, hi);
+        slab_range_w(m, nslabs, g, lo, hi);
         rcs[g] = dct3d_encode_u8_range(m->ctx[g], frames + (size_t)lo * slab_bytes, (hi - lo) * C, &bits[g]);
         bar.wait();
         for (int j = 0; j < G; j++) if (rcs[j]) return;
@@ -1829,7 +1899,7 @@ int dct3d_multi_stream_decode(dct3d_multi *m, const uint8_t *in, size_t nbytes, 
     std::vector<int> rcs(G, 0);
     auto work = [&](int g) {
         int lo, hi;
-        slab_range(nslabs, g, G, lo, hi);
+        slab_range_w(m, nslabs, g, lo, hi);
         if (hi == lo) return;
         dct3d_ctx *ctx = m->ctx[g];
         if ((rcs[g] = bind(ctx))) return;

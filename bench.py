@@ -417,9 +417,57 @@ def run_ours(args):
     # comes back as host frames.  The chunked H2D / kernels / D2H overlap lives inside the library calls.  With N ranks
     # every rank places its range into the same shared-memory stream and decodes its range from it.
     lib = c.L
-    h_frames = torch.empty((Fr, H, W), dtype=torch.uint8, pin_memory=True)
-    h_frames.copy_(frames)
-    h_out = torch.empty((Fr, H, W), dtype=torch.uint8, pin_memory=True)
+    # Link-aware shares for the end-to-end path.  The GPUs of one box do not all get the same share of the host links (this
+    # pool, 8 GPUs copying at once: 24 / 12 GB/s up / down for GPUs 0-3, 39 / 20 for GPUs 4-7), and a host-buffer call is
+    # bound by its rank's link, so equal slab ranges leave the fast links idle while the slow ones finish.  Every rank
+    # measures its own rates while all ranks copy at once; the clip's slabs are then shared out in proportion to
+    # 1 / (1/up + 1/down).  The stream does not depend on the shares (same SHA-256); the device-resident measurement above
+    # keeps equal ranges.  --balance equal switches this off.
+    e_lo, e_hi, balance = lo, hi, None
+    if world > 1 and args.balance == "auto":
+        nprobe, reps = 32 << 20, 6
+        hp = torch.empty(nprobe, dtype=torch.uint8, pin_memory=True)
+        dp = torch.empty(nprobe, dtype=torch.uint8, device=dev)
+
+        def rate(up):
+            torch.cuda.synchronize()
+            xch.all_gather(0)
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                (dp.copy_(hp, non_blocking=True) if up else hp.copy_(dp, non_blocking=True))
+            torch.cuda.synchronize()
+            return nprobe * reps / (time.perf_counter() - t0) / 1e9
+        rate(True)
+        up_gbs, down_gbs = rate(True), rate(False)
+        ws = xch.all_gather(int(1e6 / (1.0 / up_gbs + 1.0 / down_gbs)))
+        ups, downs = xch.all_gather(int(up_gbs * 1000)), xch.all_gather(int(down_gbs * 1000))
+        balance = {"h2d_gbs": [u / 1000 for u in ups], "d2h_gbs": [d / 1000 for d in downs], "applied": False}
+        if os.environ.get("DCT3D_BALANCE_WEIGHTS"):             # testing: force the shares
+            ws = [int(1000 * float(x)) for x in os.environ["DCT3D_BALANCE_WEIGHTS"].split(",")][:world]
+        if max(ws) > 1.15 * min(ws):                            # uneven links: follow them
+            cum = [0.0]
+            for w in ws:
+                cum.append(cum[-1] + w)
+            bounds = [0] + [int(nslabs * cum[g + 1] / cum[-1] + 0.5) for g in range(world - 1)] + [nslabs]
+            e_lo, e_hi = bounds[rank], bounds[rank + 1]
+            balance.update(applied=True, frames_per_rank=[(bounds[g + 1] - bounds[g]) * cube for g in range(world)])
+        del hp, dp
+    Fe = (e_hi - e_lo) * cube                                   # this rank's frames of the end-to-end path
+    frames_e = frames if (e_lo, e_hi) == (lo, hi) else synth_slabs_torch(W, H, cube, e_lo, e_hi, 1, dev)
+    h_frames = torch.empty((Fe, H, W), dtype=torch.uint8, pin_memory=True)
+    h_frames.copy_(frames_e)
+    h_out = torch.empty((Fe, H, W), dtype=torch.uint8, pin_memory=True)
+    if frames_e is not frames:
+        # what the device-resident path decodes for this rank's share, to compare the host-buffer result with
+        cap_e = W * H * Fe // 2 + 4096
+        d_tmp = torch.zeros(cap_e, dtype=torch.uint8, device=dev)
+        d_out_e = torch.empty_like(frames_e)
+        end_e = c.encode_u8_dev(frames_e, Fe, d_tmp, cap_e, 0, st)
+        c.decode_u8_dev(d_tmp, end_e // 8 + 1, Fe, d_out_e, 0, st)
+        torch.cuda.synchronize()
+        del d_tmp
+    else:
+        d_out_e = d_out
     scap = (W * H * total_frames) // 2 + 4096
     shm = None
     if world > 1:
@@ -444,13 +492,13 @@ def run_ours(args):
     def e2e_encode():
         if world == 1:
             nb, ny = C.c_uint64(), C.c_size_t()
-            rc = lib.dct3d_encode_u8(c.h, h_frames.data_ptr(), Fr, stream_ptr, scap, C.byref(nb), C.byref(ny))
+            rc = lib.dct3d_encode_u8(c.h, h_frames.data_ptr(), Fe, stream_ptr, scap, C.byref(nb), C.byref(ny))
             assert rc == 0, lib.dct3d_last_error(c.h)
             e2e_state["offs"] = [0, nb.value]
             return 0.0
         nb = C.c_uint64()
         ta = time.perf_counter()
-        rc = lib.dct3d_encode_u8_range(c.h, h_frames.data_ptr(), Fr, C.byref(nb))
+        rc = lib.dct3d_encode_u8_range(c.h, h_frames.data_ptr(), Fe, C.byref(nb))
         assert rc == 0, lib.dct3d_last_error(c.h)
         t0 = time.perf_counter()                                # from here on: the concatenation
         o = sh.bit_offsets(xch.all_gather(nb.value))            # (waits for the slowest rank's range)
@@ -471,7 +519,7 @@ def run_ours(args):
     def e2e_decode():
         o = e2e_state["offs"]
         end = C.c_uint64()
-        rc = lib.dct3d_decode_u8_range(c.h, stream_ptr, o[-1] // 8 + 1, o[rank], o[rank + 1], Fr, h_out.data_ptr(), C.byref(end))
+        rc = lib.dct3d_decode_u8_range(c.h, stream_ptr, o[-1] // 8 + 1, o[rank], o[rank + 1], Fe, h_out.data_ptr(), C.byref(end))
         assert rc == 0, lib.dct3d_last_error(c.h)
         assert end.value == o[rank + 1]
 
@@ -514,7 +562,7 @@ def run_ours(args):
     phase_table = [[round(float(v), 2) for v in t.tolist()] for t in ph_all]
     e2e_value = total_frames / e2e_s
     chunks_per_call = c.stat("chunks")
-    roundtrip_ok = bool((h_out.to(dev) == d_out).all().item())
+    roundtrip_ok = bool((h_out.to(dev) == d_out_e).all().item())
     ok_t = torch.tensor([1 if roundtrip_ok else 0], device=dev)
     if world > 1:
         dist.all_reduce(ok_t, op=dist.ReduceOp.MIN)
@@ -699,7 +747,7 @@ def run_ours(args):
                     "steps": e2e_steps, "matches_device_path": roundtrip_ok, "encode_ms": e2e_enc_s * 1e3,
                     "decode_ms": (e2e_s - e2e_enc_s) * 1e3, "concat_ms": concat_s * 1e3,
                     "per_rank_ms[range,wait_counts,place,boundary,decode]": phase_table,
-                    "stream_sha256": sha, "duplex_value": duplex_value, "duplex_trace_ms": duplex_trace, "chunks_per_call": chunks_per_call,
+                    "stream_sha256": sha, "balance": balance, "duplex_value": duplex_value, "duplex_trace_ms": duplex_trace, "chunks_per_call": chunks_per_call,
                     "how": ("one dct3d_encode_u8 + one dct3d_decode_u8 per step on pinned host buffers" if world == 1 else
                             f"per rank: dct3d_encode_u8_range, {world} bit counts exchanged through a shared-memory table, dct3d_encode_u8_place "
                             "straight into the page-locked shared-memory stream at byte B_g/8, boundary byte OR-ed once the predecessor has landed (concat_ms = all of that, max over ranks), then "
@@ -740,6 +788,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-c", action="store_true")
     ap.add_argument("--no-cli", action="store_true", help="skip timing the C codec command line")
+    ap.add_argument("--balance", choices=["auto", "equal"], default="auto",
+                    help="N > 1, end-to-end path: share the slabs out by measured host-link rates (auto) or equally")
     ap.add_argument("--quick", action="store_true", help="skip the seam, duplex and extra measurements")
     args = ap.parse_args()
     if args.impl == "reference":

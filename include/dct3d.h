@@ -146,6 +146,13 @@ void dct3d_multi_destroy(dct3d_multi *m);
 const char *dct3d_multi_last_error(const dct3d_multi *m);
 int dct3d_multi_set_option(dct3d_multi *m, const char *key, long value);
 dct3d_ctx *dct3d_multi_context(dct3d_multi *m, int index);   /* the per-GPU context (statistics, options) */
+/* Shares of the slabs: GPU g codes a contiguous range of about weights[g] / sum(weights) of them (NULL = equal shares, the
+ * default).  The stream does not depend on the shares.  dct3d_multi_probe_links measures the host<->device copy rate of every
+ * GPU while all of them copy at once (GB/s each way, arrays of ndevices entries, any may be NULL) and proposes weights
+ * 1 / (1/h2d + 1/d2h): on hosts whose GPUs do not get the same share of the host links (this pool: 24/12 GB/s for four of
+ * eight GPUs, 39/20 for the others) the end-to-end calls are bound by the slowest link unless the ranges follow them. */
+int dct3d_multi_set_weights(dct3d_multi *m, const double *weights);
+int dct3d_multi_probe_links(dct3d_multi *m, double *h2d_gbs, double *d2h_gbs, double *weights);
 int dct3d_multi_encode_u8(dct3d_multi *m, const uint8_t *frames, int nframes, uint8_t *stream, size_t cap,
                           uint64_t *nbits, size_t *nbytes, uint64_t *range_start_bits);
 int dct3d_multi_locate(dct3d_multi *m, const uint8_t *stream, size_t nbytes, int nframes, uint64_t *range_start_bits);

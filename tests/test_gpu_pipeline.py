@@ -423,3 +423,25 @@ def test_multi_streaming_in_batches(codec_mod, synth, ndev, batch):
             pos %= 8
             done += n
         assert (np.concatenate(frames) == wdec).all()
+
+
+def test_multi_weighted_shares_give_the_same_stream(codec_mod, synth):
+    """Slab ranges that follow per-GPU weights (dct3d_multi_set_weights; the shares a link probe proposes on hosts whose GPUs
+    do not get equal host bandwidth): any shares, including zero for a GPU, give the one-shot stream and frames."""
+    W, H, F = 128, 64, 88
+    clip = synth.natural(W, H, F, 29)
+    want, wbits, wdec = one_shot(codec_mod, clip, W, H, 8)
+    with codec_mod.MultiCodec(W, H, 8, devices=[0] * 4) as m:
+        for weights in ([1, 2, 3, 4], [5, 1, 1, 0.2], [0, 1, 0, 1], [1, 0, 0, 0], None):
+            m.set_weights(weights)
+            stream, nbits, starts = m.encode_u8(clip)
+            assert nbits == wbits and stream.tobytes() == want.tobytes(), weights
+            assert (m.decode_u8(stream, F, starts) == wdec).all(), weights
+            assert (m.decode_u8(stream, F) == wdec).all(), weights
+        up, down, w = m.probe_links()
+        assert len(w) == 4 and all(x > 0 for x in up + down + w)
+        m.set_weights(w)
+        stream, nbits, _ = m.encode_u8(clip)
+        assert stream.tobytes() == want.tobytes()
+        with pytest.raises(codec_mod.Dct3dError):
+            m.set_weights([0, 0, 0, 0])
