@@ -70,7 +70,17 @@ for G in Gs:
         tn = min(dec(False) for _ in range(3))
         same = same and bool((out == ref).all())
         tl = min(loc() for _ in range(3)) if G > 1 else 0.0
-        rows.append({"gpus": G, "frames": F, "encode_fps": F / te, "decode_fps_side_info": F / td, "decode_fps_discovery": F / tn,
+        balanced = None
+        if G > 1:
+            # link-aware shares: probe every GPU's copy rates (all copying at once), share the slabs out accordingly
+            up, down, w = m.probe_links()
+            m.set_weights(w)
+            enc(); dec(True)
+            be, bd = min(enc() for _ in range(3)), min(dec(True) for _ in range(3))
+            balanced = {"h2d_gbs": [round(x, 1) for x in up], "d2h_gbs": [round(x, 1) for x in down], "encode_fps": F / be, "decode_fps_side_info": F / bd,
+                        "stream_sha256_equal": hashlib.sha256(stream[:nbytes.value].tobytes()).hexdigest() == sha}
+            m.set_weights(None)
+        rows.append({"gpus": G, "frames": F, "balanced": balanced, "encode_fps": F / te, "decode_fps_side_info": F / td, "decode_fps_discovery": F / tn,
                      "locate_ms": tl * 1e3, "encode_ms": te * 1e3, "decode_ms": td * 1e3, "decode_discovery_ms": tn * 1e3,
                      "stream_bytes": nbytes.value, "stream_sha256": sha, "frames_equal_first_config": same})
         print(json.dumps(rows[-1]), flush=True)
