@@ -56,13 +56,17 @@ struct dct3d_ctx {
     int device = 0, W = 0, H = 0, C = 8;
     int num_sms = 0;
     int use_tma = 1;
+    int zero_skip = 1;               // option: the fused 8^3 encoder tests groups of high diagonals for zero before quantising them
+    int tma_store = 1;               // option: the inverse kernel stores its pixel tiles by TMA (needs width % 32 == 0)
+    int col_classes = 0;             // option: ... and skips the upper half of the columns of a unit whose non-zero columns all lie in 0..3 (8^3)
     int precision = 32;              // option: 64 = the fused entry points compute in fp64 (Java parity)
     int rounding = 0;                // option, fp64 mode: 0 = Math.round (floor(v+0.5)), 1 = C round()
     int debug = 0;
+    int tma_store_used = 0;          // statistic: the last inverse-kernel launch stored by TMA
     int reuse_zeroed = 0;            // option: see dct3d_set_option
     const void *clean_ptr = nullptr; // stream buffer known to be zero beyond clean_dirty bytes
     size_t clean_cap = 0, clean_dirty = 0;
-    int occ_cache[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // cached occupancy / attribute set-up per kernel variant
+    int occ_cache[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // cached occupancy / attribute set-up per kernel variant
     long launches = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t aux = nullptr;      // side stream: the stream wipe of the fused encoder runs beside kernel 1
@@ -201,7 +205,8 @@ EncodeTiledFn get_encode_tiled()
 // Tensor map over the u8 frame stack [F][H][W], presented as {W, F, H} (frames before rows) so that one
 // box {32 px, C frames, C rows} lands in shared memory as [y][t][32 px] (SWIZZLE_32B): the image a warp
 // unit wants (unit_offset() in dct3d_kernels.cuh).
-bool make_tmap(CUtensorMap *tm, const void *frames, int W, int H, int F, int C)
+// swizzled = false: the same box with a linear shared-memory image (the inverse kernel's tile store).
+bool make_tmap(CUtensorMap *tm, const void *frames, int W, int H, int F, int C, bool swizzled = true)
 {
     EncodeTiledFn fn = get_encode_tiled();
     if (!fn) return false;
@@ -210,7 +215,7 @@ bool make_tmap(CUtensorMap *tm, const void *frames, int W, int H, int F, int C)
     cuuint32_t box[3] = {(cuuint32_t)kUnitW, (cuuint32_t)C, (cuuint32_t)C};
     cuuint32_t es[3] = {1, 1, 1};
     return fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void *>(frames), dims, strides, box, es,
-              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, swizzled ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -229,12 +234,12 @@ int check_frames(dct3d_ctx *ctx, int nframes)
     return DCT3D_OK;
 }
 
-template <int C, int MODE>
+template <int C, int MODE, bool SKIP = false>
 int launch_encode(dct3d_ctx *ctx, const EncParams &P, const CUtensorMap &tm, cudaStream_t st)
 {
-    auto kern = encode_kernel<C, MODE>;
+    auto kern = encode_kernel<C, MODE, SKIP>;
     const int smem = EncSmem<C>::TOTAL;
-    int &occ = ctx->occ_cache[(C == 8 ? 0 : 2) + MODE];
+    int &occ = ctx->occ_cache[SKIP ? 6 : (C == 8 ? 0 : 2) + MODE];
     if (occ == 0) {
         CU_CHECK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         CU_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem));
@@ -248,6 +253,13 @@ int launch_encode(dct3d_ctx *ctx, const EncParams &P, const CUtensorMap &tm, cud
     ctx->launches++;
     CU_CHECK(ctx, cudaGetLastError());
     return DCT3D_OK;
+}
+
+// the fused (zig-zag mode) encoder of the context's cube size and zero-skip option
+int launch_encode_zz(dct3d_ctx *ctx, const EncParams &P, const CUtensorMap &tm, cudaStream_t st)
+{
+    if (ctx->C == 4) return launch_encode<4, MODE_ZZ>(ctx, P, tm, st);
+    return ctx->zero_skip ? launch_encode<8, MODE_ZZ, true>(ctx, P, tm, st) : launch_encode<8, MODE_ZZ>(ctx, P, tm, st);
 }
 
 // zero the control block and the look-back status array
@@ -299,18 +311,28 @@ static int launch_reconstruct_coo(dct3d_ctx *ctx, const Layout &L, void *d_frame
 {
     // the lists hold at most one entry per coefficient of the parsed cubes; ctx->coo has room for Geo<C>::CS more
     const unsigned long long coo_limit = ctx->coo.cap >= (size_t)Geo<C>::CS * 8 ? (unsigned long long)(ctx->coo.cap / 4 - Geo<C>::CS) : 0ull;
-    auto kern = reconstruct_coo_kernel<C>;
+    // TMA tile store: a group of CPW cubes must be one unit of a cube row (width % 32 == 0) and the frames 16-byte aligned
+    const bool tma_out = ctx->tma_store && ctx->W % kUnitW == 0 && !((uintptr_t)d_frames & 15) && L.nslabs > 0 && get_encode_tiled();
+    ctx->tma_store_used = tma_out ? 1 : 0;
+    CUtensorMap tm;
+    memset(&tm, 0, sizeof tm);
+    if (tma_out && !make_tmap(&tm, d_frames, ctx->W, ctx->H, L.nslabs * C, C, false))
+        return fail(ctx, DCT3D_E_CUDA, "cuTensorMapEncodeTiled failed (set option tma_store=0 to use row stores)");
+    const bool classes = tma_out && C == 8 && ctx->col_classes;
+    auto kern = tma_out ? reconstruct_coo_kernel<C, TAIL_TMA> : reconstruct_coo_kernel<C, TAIL_ROWS>;
+    if constexpr (C == 8) { if (classes) kern = reconstruct_coo_kernel<C, TAIL_TMA_CLASSES>; }
     const int smem = CooSmem<C>::TOTAL;
-    int &occ = ctx->occ_cache[5];
+    int &occ = ctx->occ_cache[classes ? 8 : tma_out ? 7 : 5];
     if (occ == 0) {
         CU_CHECK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         CU_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem));
     }
     const long long groups = (L.ncubes + Geo<C>::CPW - 1) / Geo<C>::CPW;
+    if (groups > 0x7ff00000ll) return fail(ctx, DCT3D_E_INVALID, "too many cubes for one call");   // the kernel counts groups in 31 bits
     const long long grid = std::min<long long>((groups + kWarps - 1) / kWarps, (long long)ctx->num_sms * std::max(occ, 1));
     cudaEvent_t *kev = ctx->kev[1][ctx->kcalls[1] % kKevRing];
     cudaEventRecord(kev[0], st);
-    kern<<<(unsigned)grid, kThreads, smem, st>>>(L, (const uint32_t *)ctx->coo.p, (const unsigned long long *)ctx->coocnt.p, (uint8_t *)d_frames, cube_base, coo_limit);
+    kern<<<(unsigned)grid, kThreads, smem, st>>>(tm, L, (const uint32_t *)ctx->coo.p, (const unsigned long long *)ctx->coocnt.p, (uint8_t *)d_frames, cube_base, coo_limit);
     cudaEventRecord(kev[1], st);
     ctx->kcalls[1]++;
     ctx->launches++;
@@ -417,6 +439,10 @@ int dct3d_create(dct3d_ctx **out, int device, int width, int height, int cube)
     dct3d_ctx *ctx = new dct3d_ctx();
     ctx->device = device; ctx->W = width; ctx->H = height; ctx->C = cube;
     ctx->use_tma = (width % 16 == 0) ? 1 : 0;
+    // defaults of the kernel-variant options can be overridden from the environment (A/B runs of a whole test suite)
+    if (const char *e = getenv("DCT3D_ZERO_SKIP")) ctx->zero_skip = atoi(e) ? 1 : 0;
+    if (const char *e = getenv("DCT3D_TMA_STORE")) ctx->tma_store = atoi(e) ? 1 : 0;
+    if (const char *e = getenv("DCT3D_COL_CLASSES")) ctx->col_classes = atoi(e) ? 1 : 0;
     int rc = bind(ctx);
     if (rc == DCT3D_OK) {
         cudaError_t e = cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device);
@@ -489,6 +515,13 @@ int dct3d_set_option(dct3d_ctx *ctx, const char *key, long value)
         return DCT3D_OK;
     }
     if (!strcmp(key, "debug")) { ctx->debug = (int)value; return DCT3D_OK; }
+    if (!strcmp(key, "zero_skip")) { ctx->zero_skip = value ? 1 : 0; return DCT3D_OK; }
+    if (!strcmp(key, "col_classes")) { ctx->col_classes = value ? 1 : 0; return DCT3D_OK; }
+    if (!strcmp(key, "tma_store")) {
+        if (value && !get_encode_tiled()) return fail(ctx, DCT3D_E_CUDA, "cuTensorMapEncodeTiled unavailable");
+        ctx->tma_store = value ? 1 : 0;
+        return DCT3D_OK;
+    }
     if (!strcmp(key, "precision")) {
         if (value != 32 && value != 64) return fail(ctx, DCT3D_E_INVALID, "precision must be 32 or 64");
         ctx->precision = (int)value;
@@ -515,6 +548,10 @@ long dct3d_get_stat(const dct3d_ctx *ctx, const char *key)
     if (!ctx || !key) return -1;
     if (!strcmp(key, "launches")) return ctx->launches;
     if (!strcmp(key, "tma")) return ctx->use_tma;
+    if (!strcmp(key, "zero_skip")) return ctx->zero_skip;
+    if (!strcmp(key, "tma_store")) return ctx->tma_store;
+    if (!strcmp(key, "col_classes")) return ctx->col_classes;
+    if (!strcmp(key, "tma_store_used")) return ctx->tma_store_used;
     if (!strcmp(key, "num_sms")) return ctx->num_sms;
     if (!strcmp(key, "chunks")) return ctx->chunks_last;
     // device time of the last encode_kernel / reconstruct_coo_kernel launch, nanoseconds (CUDA events on
@@ -690,7 +727,7 @@ static int encode_common(dct3d_ctx *ctx, const void *d_frames, int nframes, void
     const long long ptiles = (P.L.ncubes + kPackWorkers - 1) / kPackWorkers;
     if ((rc = reset_ctrl(ctx, ptiles, st))) return rc;
     if (chain) {                                                   // the caller wiped the whole stream buffer once
-        rc = C == 8 ? launch_encode<8, MODE_ZZ>(ctx, P, tm, st) : launch_encode<4, MODE_ZZ>(ctx, P, tm, st);
+        rc = launch_encode_zz(ctx, P, tm, st);
         return rc ? rc : run_pack_noreset(ctx, P, d_stream, cap, 0, nullptr, st, chain);
     }
     // The wipe of the stream buffer only has to precede kernel 2: it is forked onto the side stream
@@ -700,7 +737,7 @@ static int encode_common(dct3d_ctx *ctx, const void *d_frames, int nframes, void
     CU_CHECK(ctx, cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0));
     rc = zero_stream(ctx, d_stream, cap, start_bit, ctx->aux);
     CU_CHECK(ctx, cudaEventRecord(ctx->ev_join, ctx->aux));
-    if (rc == DCT3D_OK) rc = C == 8 ? launch_encode<8, MODE_ZZ>(ctx, P, tm, st) : launch_encode<4, MODE_ZZ>(ctx, P, tm, st);
+    if (rc == DCT3D_OK) rc = launch_encode_zz(ctx, P, tm, st);
     CU_CHECK(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));     // join the wipe (also on the error path)
     if (rc) return rc;
     return run_pack_noreset(ctx, P, d_stream, cap, start_bit, end_bit, st);

@@ -32,6 +32,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "dct_math.h"
 #include "eg_bits.h"
 
@@ -141,6 +143,25 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *tmap, 
         ::"r"(smem_u32(dst)), "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
 }
 
+// TMA tile store (shared -> global) of one {32 px, C frames, C rows} box, bulk-group completion
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap *tmap, const void *src, int x, int y, int z)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
+        ::"l"(tmap), "r"(x), "r"(y), "r"(z), "r"(smem_u32(src)) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// the issuing thread waits until its bulk stores have READ their shared-memory source (the tile may be rewritten)
+__device__ __forceinline__ void tma_store_wait_read()
+{
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+// generic-proxy writes to shared memory become visible to the async proxy (TMA)
+__device__ __forceinline__ void fence_proxy_async_smem()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
 // ------------------------------------------------------------------------------------------
 // Unit geometry.  A unit is what one warp transforms per pass: 32 px x C rows x C frames =
 // 32/C cubes side by side.  Shared-memory image of a unit: [y][t][32 px], which is what one TMA
@@ -192,30 +213,33 @@ struct Xch {
     static constexpr int CUBE_BYTES = C * C * 16;
     static constexpr int WARP_BYTES = (32 / C) * CUBE_BYTES;
 
-    // a[k1][k2] (thread = t)  ->  b[t][k2] (thread = j = k1)
-    static __device__ __forceinline__ void transpose(uint8_t *wbuf, int cl, int r, const T (&a)[C][C], T (&b)[C][C])
+    // one round: vector h (elements h*VEC .. h*VEC+VEC-1) of every row
+    static __device__ __forceinline__ void round(uint8_t *wbuf, int cl, int r, const T (&a)[C][C], T (&b)[C][C], int h)
     {
         uint4 *base = reinterpret_cast<uint4 *>(wbuf + cl * CUBE_BYTES);
 #pragma unroll
-        for (int h = 0; h < VPR; h++) {
+        for (int k1 = 0; k1 < C; k1++) {
+            uint4 v;
+            T *pv = reinterpret_cast<T *>(&v);
 #pragma unroll
-            for (int k1 = 0; k1 < C; k1++) {
-                uint4 v;
-                T *pv = reinterpret_cast<T *>(&v);
-#pragma unroll
-                for (int e = 0; e < VEC; e++) pv[e] = a[k1][h * VEC + e];
-                base[r * C + (k1 ^ r)] = v;
-            }
-            __syncwarp();
-#pragma unroll
-            for (int t = 0; t < C; t++) {
-                const uint4 v = base[t * C + (r ^ t)];
-                const T *pv = reinterpret_cast<const T *>(&v);
-#pragma unroll
-                for (int e = 0; e < VEC; e++) b[t][h * VEC + e] = pv[e];
-            }
-            __syncwarp();
+            for (int e = 0; e < VEC; e++) pv[e] = a[k1][h * VEC + e];
+            base[r * C + (k1 ^ r)] = v;
         }
+        __syncwarp();
+#pragma unroll
+        for (int t = 0; t < C; t++) {
+            const uint4 v = base[t * C + (r ^ t)];
+            const T *pv = reinterpret_cast<const T *>(&v);
+#pragma unroll
+            for (int e = 0; e < VEC; e++) b[t][h * VEC + e] = pv[e];
+        }
+        __syncwarp();
+    }
+    // a[k1][k2] (thread = t)  ->  b[t][k2] (thread = j = k1)
+    static __device__ __forceinline__ void transpose(uint8_t *wbuf, int cl, int r, const T (&a)[C][C], T (&b)[C][C])
+    {
+#pragma unroll
+        for (int h = 0; h < VPR; h++) round(wbuf, cl, r, a, b, h);
     }
 };
 
@@ -436,7 +460,14 @@ struct EncSmem {
 #ifndef DCT3D_ENC_CTAS
 #define DCT3D_ENC_CTAS 3
 #endif
-template <int C, int MODE>
+
+// SKIP (C = 8, MODE_ZZ): zero-run skipping in the zig-zag stage.  97% of the quantised coefficients are zero, and the
+// high diagonals k0 + k2 of a unit are zero in nearly every lane (measured on the benchmark clip: k0 + k2 >= 8 holds a
+// non-zero in 4% of the units, 7 in 15%, 6 in 38%).  One FMNMX3 per three coefficients finds the largest magnitude of a
+// group of diagonals, one compare against the lane's zero threshold and a warp vote decide whether the warp runs the
+// group's quantiser (FFMA + compare + predicated STS.U16 per coefficient) at all.  Bit-identical: the skipped
+// coefficients are exactly those the quantiser would have found zero.
+template <int C, int MODE, bool SKIP = false>
 __global__ void __launch_bounds__(kThreads, DCT3D_ENC_CTAS)
 encode_kernel(const __grid_constant__ CUtensorMap tmap, const EncParams P)
 {
@@ -460,6 +491,13 @@ encode_kernel(const __grid_constant__ CUtensorMap tmap, const EncParams P)
         rq[s] = lane_scale<C>(r) / (float)quant_divisor(s + r);   // S[k1] of the scaled butterflies folded in
         zb[s] = zz_base<C>(r, s);
     }
+    // SKIP: zero thresholds of diagonals 6, 7 and 8; rq falls with s, so the threshold of 8 is a (sufficient) bound for
+    // every later diagonal
+    constexpr int SK0 = C == 8 ? 6 : G::NDIAG;                    // first diagonal that is tested before it is quantised
+    constexpr int SKG = C == 8 ? 8 : G::NDIAG;                    // diagonals from here on are tested as one group
+    const float thr_a = SKIP ? zero_threshold(rq[SK0 % G::NDIAG]) : 0.f;
+    const float thr_b = SKIP ? zero_threshold(rq[(SK0 + 1) % G::NDIAG]) : 0.f;
+    const float thr_g = SKIP ? zero_threshold(rq[SKG % G::NDIAG]) : 0.f;
     // unit counts fit 31 bits (checked by the host)
     const int nw = (int)gridDim.x * kWarps, nunits = (int)L.nunits;
     int u = (int)blockIdx.x * kWarps + warp;
@@ -562,16 +600,41 @@ encode_kernel(const __grid_constant__ CUtensorMap tmap, const EncParams P)
         }
         // zig-zag scatter into this warp's private cubes (runs of a diagonal are contiguous)
         int16_t *zz = s_zz + cl * G::ZZ_STRIDE;
+        // quantise + scatter the diagonals [s_lo, s_hi] of this thread's plane
+        auto scatter_diagonals = [&](int s_lo, int s_hi) {
 #pragma unroll
-        for (int k0 = 0; k0 < C; k0++) {
+            for (int k0 = 0; k0 < C; k0++) {
 #pragma unroll
-            for (int k2 = 0; k2 < C; k2++) {
-                const int s = k0 + k2;
-                const int k0min = s > C - 1 ? s - (C - 1) : 0;
-                // one FFMA quantises (magic rounding); a zero result is exactly the magic constant
-                const int bits = __float_as_int(fmaf(bq[k0][k2], rq[s], DCT_MAGIC));
-                if (bits != 0x4B400000) zz[zb[s] + (k0 - k0min)] = (int16_t)bits;
+                for (int k2 = 0; k2 < C; k2++) {
+                    const int s = k0 + k2;
+                    if (s < s_lo || s > s_hi) continue;
+                    const int k0min = s > C - 1 ? s - (C - 1) : 0;
+                    // one FFMA quantises (magic rounding); a zero result is exactly the magic constant
+                    const int bits = __float_as_int(fmaf(bq[k0][k2], rq[s], DCT_MAGIC));
+                    if (bits != 0x4B400000) zz[zb[s] + (k0 - k0min)] = (int16_t)bits;
+                }
             }
+        };
+        // largest magnitude on the diagonals [s_lo, s_hi]
+        auto max_abs = [&](int s_lo, int s_hi) {
+            float m = 0.f;
+#pragma unroll
+            for (int k0 = 0; k0 < C; k0++) {
+#pragma unroll
+                for (int k2 = 0; k2 < C; k2++) {
+                    const int s = k0 + k2;
+                    if (s >= s_lo && s <= s_hi) m = fmaxf(m, fabsf(bq[k0][k2]));
+                }
+            }
+            return m;
+        };
+        if (!SKIP) {
+            scatter_diagonals(0, G::NDIAG - 1);
+        } else {
+            scatter_diagonals(0, SK0 - 1);
+            if (__any_sync(0xffffffffu, max_abs(SK0, SK0) > thr_a)) scatter_diagonals(SK0, SK0);
+            if (__any_sync(0xffffffffu, max_abs(SK0 + 1, SK0 + 1) > thr_b)) scatter_diagonals(SK0 + 1, SK0 + 1);
+            if (__any_sync(0xffffffffu, max_abs(SKG, G::NDIAG - 1) > thr_g)) scatter_diagonals(SKG, G::NDIAG - 1);
         }
         __syncwarp();
         // chunk masks + sparse store: lane <-> 16-coefficient chunk
@@ -679,7 +742,10 @@ zz_gather_kernel(const EncParams P)
 // Measured and dropped in round 2: a software-pipelined CTA (a ninth "scanner" warp resolves the look-back of tile i while
 // the eight worker warps count tile i+1, aggregates published early): 340 us instead of 173 -- two barriers per tile, a
 // lower occupancy (48 registers) and an idle warp cost more than the 28% barrier stall it was meant to remove.
-constexpr int kPackWorkers = 256;                   // one cube each
+#ifndef DCT3D_PACK_WORKERS
+#define DCT3D_PACK_WORKERS 256
+#endif
+constexpr int kPackWorkers = DCT3D_PACK_WORKERS;    // one cube each
 constexpr int kPackThreads = kPackWorkers;
 
 // The CTA is software-pipelined over its tiles: while the scanner warp resolves the bit offset of tile i (decoupled
@@ -688,7 +754,7 @@ constexpr int kPackThreads = kPackWorkers;
 // kernel's warp time.)
 // 8 CTAs per SM = 32 registers = full occupancy: the serial bit append is latency-bound (39 registers at 6 CTAs: +6%)
 template <int C>
-__global__ void __launch_bounds__(kPackThreads, 8)
+__global__ void __launch_bounds__(kPackThreads, 2048 / kPackThreads)
 eg_pack_kernel(const EncParams P)
 {
     using G = Geo<C>;
@@ -1220,6 +1286,50 @@ __device__ __forceinline__ void idct_store(float (&b)[C][C], uint8_t *xbuf, int 
     }
 }
 
+// The same tail with the pixels leaving by TMA (reconstruct_coo_kernel<C, true>): after the y and x passes thread
+// (cube cl, frame r) packs its C rows into the warp's unit tile [y][t][32 px] in shared memory (the image of ONE box
+// {32 px, C frames, C rows} of the tensor {W, F, H}, the encoder's unit read backwards), and lane 0 hands the tile to the
+// TMA unit.  Why: the row stores of idct_store are 8 bytes per lane to 8 different frames, 16 data-pipe wavefronts per
+// STG.64 and 128 per unit, a third of all wavefronts of a kernel whose LSU data pipe is 87% busy; the tile costs 16
+// (C = 8: 8 STS.64 of 256 contiguous bytes) and the TMA unit reads shared memory beside the LSU.  The tile lives in the
+// exchange buffer, which is free between the exchange of this unit and the exchange of the next one; the store's read
+// of it is awaited (long finished) just before that next exchange.  Needs groups = units, i.e. bx % CPW == 0.
+// a[y][x]: the finished plane of thread (cube cl, frame r).  Clamp, truncate, pack into the warp's tile, hand it to TMA.
+template <int C>
+__device__ __forceinline__ void tile_store(float (&a)[C][C], uint8_t *xbuf, int cl, int r, int lane, const CUtensorMap *tmap,
+                                           const UnitPos &pos)
+{
+    // the last exchange round ended with __syncwarp(): every lane holds its vectors, the buffer is free
+    uint8_t *row = xbuf + r * kUnitW + cl * C;     // [y][t = r][x = cl * C ..]
+#pragma unroll
+    for (int y = 0; y < C; y++) {
+        uint32_t w[2] = {0, 0};
+#pragma unroll
+        for (int x = 0; x < C; x += 4) {
+            const uint32_t b0 = f2u8_sat(a[y][x]), b1 = f2u8_sat(a[y][x + 1]);
+            const uint32_t b2 = f2u8_sat(a[y][x + 2]), b3 = f2u8_sat(a[y][x + 3]);
+            w[x / 4] = __byte_perm(__byte_perm(b0, b1, 0x0040), __byte_perm(b2, b3, 0x0040), 0x5410);
+        }
+        if (C == 8) *reinterpret_cast<uint2 *>(row + y * C * kUnitW) = make_uint2(w[0], w[1]);
+        else *reinterpret_cast<uint32_t *>(row + y * C * kUnitW) = w[0];
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) tma_store_3d(tmap, xbuf, pos.bxu * kUnitW, pos.slab * C, pos.byi * C);
+}
+
+template <int C>
+__device__ __forceinline__ void idct_tile_store(float (&b)[C][C], uint8_t *xbuf, int cl, int r, int lane, uint32_t colmask,
+                                                const CUtensorMap *tmap, const UnitPos &pos)
+{
+    float a[C][C];
+    if (lane == 0) tma_store_wait_read();          // the previous unit's tile has been read
+    __syncwarp();
+    Xch<C, float>::transpose(xbuf, cl, r, b, a);
+    inv_yx_n_masked<C, float>(a, colmask);
+    tile_store<C>(a, xbuf, cl, r, lane, tmap, pos);
+}
+
 // Non-zero lists -> u8 frames (the decoder's inverse kernel).  Per warp and group of CPW cubes:
 // C lanes per cube scatter the cube's entries, ALREADY DEQUANTISED (one multiply by the table entry
 // max(1,5(k0+k1+k2)) * S[k0] S[k1] S[k2], so that all three butterfly passes run un-normalised), into
@@ -1233,20 +1343,49 @@ __device__ __forceinline__ void idct_store(float (&b)[C][C], uint8_t *xbuf, int 
 // it SLOWER (388 -> 417 us for the aliasing alone, 442 us at 5 CTAs, 528 us at 6): the shared-memory pipe and the issue slots
 // are co-limiters, so extra wipes and spill traffic cost more than the extra warps hide.  Allowing fewer CTAs changes nothing:
 // the compiler does not want more than 128 registers here.
+#ifndef DCT3D_CLASS_VARIANT
+#define DCT3D_CLASS_VARIANT 2
+#endif
+#ifndef DCT3D_COO_PRE
+#define DCT3D_COO_PRE 3
+#endif
+#ifndef DCT3D_NAT_PAD
+#define DCT3D_NAT_PAD 4
+#endif
 template <int C>
 struct CooSmem {
     using G = Geo<C>;
-    static constexpr int NAT_WARP = G::CPW * G::CS * 4;            // bytes: CPW natural-order float cubes
+    // The cubes of a warp sit DCT3D_NAT_PAD floats further apart than their size: the same coefficient of the CPW cubes (the
+    // lanes of the cubes scatter their lists in step: DC first) then lies in CPW different banks instead of one (round 2:
+    // 29 of the 38 wavefronts of the scatter and wipe stores of a unit were bank conflicts).  A multiple of 4 floats keeps
+    // the rows 16-byte aligned and the row loads of a quarter warp (one cube) conflict-free.
+    static constexpr int CUBE_STRIDE = G::CS + DCT3D_NAT_PAD;     // floats
+    static constexpr int NAT_WARP = (G::CPW * CUBE_STRIDE * 4 + 255) / 256 * 256;   // bytes: CPW natural-order float cubes; the exchange
+                                                                  // buffer behind them stays 256-byte aligned (TMA tile)
     static constexpr int WARP_BYTES = NAT_WARP + Xch<C, float>::WARP_BYTES;
     static constexpr int TAB_OFF = kWarps * WARP_BYTES;            // float[CS] dequantiser table
     static constexpr int TOTAL = TAB_OFF + G::CS * 4;
 };
 
-template <int C>
+// TAIL: 0 = row stores (idct_store), 1 = TMA tile store (idct_tile_store), 2 = TMA tile store + column classes (C = 8).
+// Column classes: a unit whose non-zero k2 columns all lie in 0..3 (warp-uniform; 25% of the units of the benchmark clip)
+// reads half of its cube rows, runs one exchange round instead of two and the x butterflies with four live inputs
+// (dct8_inv_n_lo4): 96 of about 270 data-pipe wavefronts and 110 of about 1000 instructions less for such a unit, inside ONE
+// tail.  (First version, measured: three specialised copies of the whole tail -- columns 0..3 / 0..5 / all, the middle one
+// with an exchange round of 8-byte vectors -- made the kernel 3248 instructions = 52 KB, beyond the 32 KB instruction cache:
+// 405 us instead of 348.)  Bit-identical to the unspecialised tail.
+constexpr int TAIL_ROWS = 0, TAIL_TMA = 1, TAIL_TMA_CLASSES = 2;
+
+template <int C, int TAIL = TAIL_ROWS>
 __global__ void __launch_bounds__(kThreads, 4)
-reconstruct_coo_kernel(const Layout L, const uint32_t *__restrict__ coo, const unsigned long long *__restrict__ coo_start_all,
-                       uint8_t *__restrict__ frames, const long long cube_base, const unsigned long long coo_limit)
+reconstruct_coo_kernel(const __grid_constant__ CUtensorMap tmap_out, const Layout L, const uint32_t *__restrict__ coo,
+                       const unsigned long long *__restrict__ coo_start_all, uint8_t *__restrict__ frames, const long long cube_base,
+                       const unsigned long long coo_limit)
 {
+    // TMA_OUT: the pixels leave as one TMA box per unit (idct_tile_store; tmap_out is the tensor map of `frames`), else by
+    // row stores (idct_store; tmap_out is not looked at)
+    constexpr bool TMA_OUT = TAIL != TAIL_ROWS;
+    constexpr bool CLASSES = TAIL == TAIL_TMA_CLASSES && C == 8;
     // coo_limit: row pointers are clamped to it, so that a launch that runs ahead of the host's look at the control
     // block (lists of a stream whose index discovery has not converged, or of a damaged stream) stays inside the buffer
     // cube_base: the launch reconstructs cubes [cube_base, cube_base + L.ncubes) of the parsed stream into a frame buffer
@@ -1254,25 +1393,26 @@ reconstruct_coo_kernel(const Layout L, const uint32_t *__restrict__ coo, const u
     const unsigned long long *__restrict__ coo_start = coo_start_all + cube_base;
     using G = Geo<C>;
     using S = CooSmem<C>;
-    constexpr int PRE = 3;                                          // prefetched entries per lane
+    constexpr int PRE = DCT3D_COO_PRE;                              // prefetched entries per lane
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int cl = lane / C, r = lane % C;
-    float *nat = reinterpret_cast<float *>(smem + warp * S::WARP_BYTES) + cl * G::CS;   // this thread's cube
+    float *nat = reinterpret_cast<float *>(smem + warp * S::WARP_BYTES) + cl * S::CUBE_STRIDE;   // this thread's cube
     uint8_t *xbuf = smem + warp * S::WARP_BYTES + S::NAT_WARP;
     float *tab = reinterpret_cast<float *>(smem + S::TAB_OFF);
     build_dequant_table<C>(tab, tid);
     for (int i = lane; i < S::NAT_WARP / 16; i += 32) reinterpret_cast<uint4 *>(smem + warp * S::WARP_BYTES)[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
 
-    const long long ngroups = (L.ncubes + G::CPW - 1) / G::CPW;
-    const long long stride = (long long)gridDim.x * kWarps;
-    long long g = (long long)blockIdx.x * kWarps + warp;
+    // group counts fit 31 bits with room for two strides (checked by the host): 32-bit loop state, three registers less
+    const int ngroups = (int)((L.ncubes + G::CPW - 1) / G::CPW);
+    const int stride = (int)gridDim.x * kWarps;
+    int g = (int)blockIdx.x * kWarps + warp;
     // pipeline: row pointers two groups ahead, the first PRE*C entries one group ahead
     unsigned long long z_nn = 0, z_n = 0;      // first entry of this thread's cube, groups g+2 and g+1
     uint32_t zend_nn = 0, c_n = 0, e_n[PRE];   // low word of the next row pointer: the count is formed a pass later
-    auto fetch_rows = [&](long long grp) {
-        const long long cube = grp * G::CPW + cl;
+    auto fetch_rows = [&](int grp) {
+        const long long cube = (long long)grp * G::CPW + cl;
         const bool ok = grp < ngroups && cube < L.ncubes;
         z_nn = ok ? min(__ldg(coo_start + cube), coo_limit) : 0ull;
         zend_nn = ok ? __ldg(reinterpret_cast<const uint32_t *>(coo_start + cube + 1)) : 0u;
@@ -1293,13 +1433,16 @@ reconstruct_coo_kernel(const Layout L, const uint32_t *__restrict__ coo, const u
     rotate_rows();
     fetch_entries();
     fetch_rows(g + stride);
+    // TMA_OUT: group g is unit g of the encoder's numbering (the host checked bx % CPW == 0); the unit counts fit 31 bits
+    UnitPos upos = unit_pos(L, TMA_OUT ? (long long)min(g, ngroups) : 0ll);
+    const UnitPos ustep = unit_pos(L, TMA_OUT ? (long long)stride : 0ll);
     for (; g < ngroups; g += stride) {
         const uint32_t cnt = c_n;
         const unsigned long long z0 = z_n;
         uint32_t e[PRE];
 #pragma unroll
         for (int k = 0; k < PRE; k++) e[k] = e_n[k];
-        const long long cube = g * G::CPW + cl;
+        const long long cube = (long long)g * G::CPW + cl;
         rotate_rows();
         fetch_entries();                        // group g + stride
         fetch_rows(g + 2 * stride);
@@ -1330,6 +1473,92 @@ reconstruct_coo_kernel(const Layout L, const uint32_t *__restrict__ coo, const u
         // columns that are zero in all cubes of this pass skip their t and y transforms
         const uint32_t colmask = __reduce_or_sync(0xffffffffu, colbits);
         __syncwarp();
+        // wipe what was scattered (after the t pass: by now every lane's row loads have long landed)
+        auto wipe = [&]() {
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < PRE; k++)
+                if ((uint32_t)(r + k * C) < cnt) nat[(e[k] >> 16) & (G::CS - 1)] = 0.0f;
+            for (uint32_t i = r + PRE * C; i < cnt; i += 4 * C) {
+                uint32_t x[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) x[k] = i + k * C < cnt ? __ldg(coo + z0 + i + k * C) : 0u;
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (i + k * C < cnt) nat[(x[k] >> 16) & (G::CS - 1)] = 0.0f;
+            }
+        };
+        if constexpr (CLASSES) {
+            // column classes: a unit whose non-zero columns all lie in 0..3 (warp-uniform) neither loads, transforms nor
+            // exchanges the upper half of its rows, and runs the x butterflies with four live inputs
+            const bool hi = (colmask & 0xf0u) != 0;
+            float b[C][C], a[C][C];                              // columns 4..7 are only touched when hi
+#if DCT3D_CLASS_VARIANT == 2
+#pragma unroll
+            for (int k2 = 0; k2 < C; k2 += 4) {
+#pragma unroll
+                for (int k0 = 0; k0 < C; k0++) {
+                    const float4 v = *reinterpret_cast<const float4 *>(nat + (k0 * C + r) * C + (k2 ^ (r & 4)));   // coo_swizzle
+                    b[k0][k2] = v.x; b[k0][k2 + 1] = v.y; b[k0][k2 + 2] = v.z; b[k0][k2 + 3] = v.w;
+                }
+            }
+            inv_t_n_masked<C, float>(b, colmask);
+#else
+#pragma unroll
+            for (int k0 = 0; k0 < C; k0++) {
+                const float4 v = *reinterpret_cast<const float4 *>(nat + (k0 * C + r) * C + (r & 4));   // coo_swizzle
+                b[k0][0] = v.x; b[k0][1] = v.y; b[k0][2] = v.z; b[k0][3] = v.w;
+            }
+            if (hi) {
+#pragma unroll
+                for (int k0 = 0; k0 < C; k0++) {
+                    const float4 v = *reinterpret_cast<const float4 *>(nat + (k0 * C + r) * C + (4 ^ (r & 4)));
+                    b[k0][4] = v.x; b[k0][5] = v.y; b[k0][6] = v.z; b[k0][7] = v.w;
+                }
+            }
+#pragma unroll
+            for (int x = 0; x < 4; x++)
+                if ((colmask >> x) & 1u) Dct1D<C, float>::template inv_n<C>(&b[0][x]);
+            if (hi) {
+#pragma unroll
+                for (int x = 4; x < C; x++)
+                    if ((colmask >> x) & 1u) Dct1D<C, float>::template inv_n<C>(&b[0][x]);
+            }
+#endif
+            wipe();
+            if (lane == 0) tma_store_wait_read();                // the previous unit's tile (in xbuf) has been read
+            __syncwarp();
+            Xch<C, float>::round(xbuf, cl, r, b, a, 0);
+#if DCT3D_CLASS_VARIANT == 1
+            if (hi) {
+                Xch<C, float>::round(xbuf, cl, r, b, a, 1);
+            } else {
+#pragma unroll
+                for (int t = 0; t < C; t++) a[t][4] = a[t][5] = a[t][6] = a[t][7] = 0.0f;
+            }
+            inv_yx_n_masked<C, float>(a, colmask);
+#else
+            if (hi) Xch<C, float>::round(xbuf, cl, r, b, a, 1);
+#pragma unroll
+            for (int x = 0; x < 4; x++)
+                if ((colmask >> x) & 1u) Dct1D<C, float>::template inv_n<C>(&a[0][x]);
+            if (hi) {
+#pragma unroll
+                for (int x = 4; x < C; x++)
+                    if ((colmask >> x) & 1u) Dct1D<C, float>::template inv_n<C>(&a[0][x]);
+#pragma unroll
+                for (int y = 0; y < C; y++) Dct1D<C, float>::template inv_n<1>(&a[y][0]);
+            } else {
+#pragma unroll
+                for (int y = 0; y < C; y++) {
+                    float *v = &a[y][0];
+                    dct8_inv_n_lo4<float>(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
+                }
+            }
+#endif
+            tile_store<C>(a, xbuf, cl, r, lane, &tmap_out, upos);
+            unit_advance(L, upos, ustep);
+        } else {
         float b[C][C];
         // first halves of all rows, then second halves: the t pass of columns 0..3 starts while the
         // second halves are still in flight
@@ -1343,21 +1572,16 @@ reconstruct_coo_kernel(const Layout L, const uint32_t *__restrict__ coo, const u
             }
         }
         inv_t_n_masked<C, float>(b, colmask);
-        // wipe what was scattered, after the t pass: by now every lane's row loads have long landed
-        __syncwarp();
-#pragma unroll
-        for (int k = 0; k < PRE; k++)
-            if ((uint32_t)(r + k * C) < cnt) nat[(e[k] >> 16) & (G::CS - 1)] = 0.0f;
-        for (uint32_t i = r + PRE * C; i < cnt; i += 4 * C) {
-            uint32_t x[4];
-#pragma unroll
-            for (int k = 0; k < 4; k++) x[k] = i + k * C < cnt ? __ldg(coo + z0 + i + k * C) : 0u;
-#pragma unroll
-            for (int k = 0; k < 4; k++)
-                if (i + k * C < cnt) nat[(x[k] >> 16) & (G::CS - 1)] = 0.0f;
+        wipe();
+        if (TMA_OUT) {
+            idct_tile_store<C>(b, xbuf, cl, r, lane, colmask, &tmap_out, upos);
+            unit_advance(L, upos, ustep);
+        } else {
+            idct_store<C, true, true>(b, xbuf, cl, r, cube < L.ncubes, L, cube, frames, colmask);
         }
-        idct_store<C, true, true>(b, xbuf, cl, r, cube < L.ncubes, L, cube, frames, colmask);
+        }
     }
+    if (TMA_OUT && lane == 0) tma_store_wait_read();   // the last tile must have been read before the CTA's shared memory goes
 }
 
 // int16 natural-order cubes -> u8 frames: dequantise, inverse butterflies, clamp, truncate.

@@ -445,3 +445,36 @@ def test_multi_weighted_shares_give_the_same_stream(codec_mod, synth):
         assert stream.tobytes() == want.tobytes()
         with pytest.raises(codec_mod.Dct3dError):
             m.set_weights([0, 0, 0, 0])
+
+
+@pytest.mark.parametrize("W,H,F,cube,kind", [(256, 64, 24, 8, "natural"), (1920, 136, 16, 8, "natural"), (128, 64, 16, 8, "noise"),
+                                             (96, 32, 16, 8, "constant"), (200, 24, 16, 8, "natural"), (128, 32, 8, 4, "natural"),
+                                             (64, 64, 16, 8, "sparse")])
+def test_kernel_variants_are_bit_identical(codec_mod, oracle, synth, W, H, F, cube, kind):
+    """Round-2 kernel variants -- the encoder's zero-run skip (option zero_skip), the inverse kernel's TMA tile store
+    (tma_store) and its column classes (col_classes) -- against the plain paths: same stream, same frames, and the frames
+    within +-1 of the oracle.  Widths that are not a multiple of 32 must fall back to row stores by themselves."""
+    if kind == "sparse":                       # mostly flat cubes with a few textured ones: all three column classes occur
+        rng = np.random.default_rng(3)
+        clip = np.full((F, H, W), 120, np.uint8)
+        clip[:, :16, :24] = rng.integers(0, 256, size=(F, 16, 24), dtype=np.uint8)
+        clip[:, 32:40, :] = (np.arange(W)[None, None, :] * 3 % 256).astype(np.uint8)
+        clip[:, 48:, 32:] = synth.natural(W - 32, H - 48, F, 5)
+    else:
+        clip = getattr(synth, kind)(W, H, F, 9) if kind != "constant" else synth.constant(W, H, F, 77)
+    outs = {}
+    for skip, tma, classes in [(0, 0, 0), (1, 0, 0), (0, 1, 0), (0, 1, 1), (1, 1, 1)]:
+        with codec_mod.Codec(W, H, cube) as c:
+            c.set_option("zero_skip", skip)
+            c.set_option("tma_store", tma)
+            c.set_option("col_classes", classes)
+            stream, nbits = c.encode_u8(clip)
+            dec = c.decode_u8(stream, F)
+            assert c.stat("tma_store_used") == (1 if tma and W % 32 == 0 else 0)
+            outs[(skip, tma, classes)] = (stream.tobytes(), nbits, dec)
+    base = outs[(0, 0, 0)]
+    for key, (s, n, d) in outs.items():
+        assert n == base[1] and s == base[0], f"stream differs for variant {key}"
+        assert (d == base[2]).all(), f"frames differ for variant {key}: {int((d != base[2]).sum())} pixels"
+    odec = oracle.decode_u8(np.frombuffer(base[0], np.uint8), W, H, F // cube * cube, cube)
+    assert np.abs(base[2][: F // cube * cube].astype(int) - odec.astype(int)).max() <= 1

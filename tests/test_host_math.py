@@ -14,11 +14,13 @@ ROOT = os.path.dirname(HERE)
 
 @pytest.fixture(scope="module")
 def hh():
-    so = os.path.join(HERE, "_host_harness.so")
+    # DCT3D_HH_DEFS: extra -D flags, to run this file against a compile-time variant of the device arithmetic
+    defs = os.environ.get("DCT3D_HH_DEFS", "").split()
+    so = os.path.join(HERE, "_host_harness%s.so" % ("_" + "_".join(d.removeprefix("-D").replace("=", "") for d in defs) if defs else ""))
     srcs = [os.path.join(HERE, "host_harness.cpp")] + [
         os.path.join(ROOT, "3ddctvideoencoding_b200", "csrc", f) for f in ("dct_math.h", "eg_bits.h")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
-        subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-o", so, srcs[0]])
+        subprocess.check_call(["g++", "-O2", "-fPIC", "-shared"] + defs + ["-o", so, srcs[0]])
     L = C.CDLL(so)
     f32 = np.ctypeslib.ndpointer(np.float32, flags="C")
     f64 = np.ctypeslib.ndpointer(np.float64, flags="C")
@@ -181,3 +183,62 @@ def test_scan_rejects_17_bit_code_numbers_beyond_int16(hh, oracle):
     assert end == 36 and "".join(format(b, "08b") for b in stream)[:36] == ok[:36]
     for m in (65536, 65538, 0x1FFFF):
         assert scan("111" + "0" * 16 + format(m, "017b") + "1" * 40)[0] == -1
+
+
+def _bind_round2(hh):
+    f32 = np.ctypeslib.ndpointer(np.float32, flags="C")
+    hh.hh_zero_threshold.argtypes = [C.c_float]
+    hh.hh_zero_threshold.restype = C.c_float
+    hh.hh_quantize_recip.argtypes = [C.c_float, C.c_float]
+    hh.hh_quantize_recip.restype = C.c_int
+    hh.hh_inv8_live.argtypes = [f32, C.c_int, f32, f32]
+
+
+def test_zero_threshold_is_the_quantisers_zero_set(hh):
+    """The fused encoder skips the quantiser of a group of diagonals when every |coefficient| <= zero_threshold(recip).
+    For every reciprocal the kernel uses (S[k1] / max(1, 5 (s + k1)), float arithmetic as in encode_kernel) the threshold
+    must split the floats exactly where the one-FFMA quantiser switches between zero and non-zero."""
+    _bind_round2(hh)
+    S = np.array([0.35355339059327376220, 0.49039264020161522456, 0.46193976625564337806, 0.41573480615127261854,
+                  0.35355339059327376220, 0.27778511650980111237, 0.46193976625564337806, 0.09754516100806413392], np.float32)
+    rng = np.random.default_rng(11)
+    for k1 in range(8):
+        for s in range(15):
+            div = np.float32(1 if s + k1 == 0 else 5 * (s + k1))
+            rq = np.float32(S[k1] / div)
+            t = np.float32(hh.hh_zero_threshold(float(rq)))
+            ti = int(t.view(np.int32))
+            # the floats around the threshold, both signs
+            for d in range(-4, 5):
+                x = np.array([ti + d], np.int32).view(np.float32)[0]
+                for v in (x, -x):
+                    q = hh.hh_quantize_recip(float(v), float(rq))
+                    assert (q == 0) == (d <= 0), (k1, s, d, float(v), q)
+            # random magnitudes: the two tests agree everywhere
+            xs = (rng.standard_normal(200) * float(t) * 1.5).astype(np.float32)
+            for v in xs:
+                assert (hh.hh_quantize_recip(float(v), float(rq)) == 0) == (abs(v) <= t)
+    # thresholds grow with the diagonal: the bound of diagonal 8 is sufficient for 9..14
+    for k1 in range(8):
+        ts = [hh.hh_zero_threshold(float(np.float32(S[k1] / np.float32(5 * (s + k1))))) for s in range(8, 15)]
+        assert all(a <= b for a, b in zip(ts, ts[1:]))
+
+
+@pytest.mark.parametrize("live", [4])
+def test_inverse_butterfly_with_zero_high_inputs(hh, live):
+    """dct8_inv_n_lo4 (the inverse kernel's column classes) equals dct8_inv_n on inputs whose four high frequencies are
+    zero, bit for bit (the sign of a zero aside)."""
+    _bind_round2(hh)
+    rng = np.random.default_rng(5 + live)
+    for trial in range(2000):
+        scale = 10.0 ** rng.integers(-3, 4)
+        x = (rng.standard_normal(8) * scale).astype(np.float32)
+        if trial % 7 == 0:
+            x[rng.integers(0, live)] = 0.0
+        if trial % 50 == 0:
+            x[:] = 0.0
+        full = np.zeros(8, np.float32)
+        lo = np.zeros(8, np.float32)
+        hh.hh_inv8_live(x, live, full, lo)
+        same = (full.view(np.uint32) == lo.view(np.uint32)) | ((full == 0) & (lo == 0))
+        assert same.all(), (x, full, lo)
