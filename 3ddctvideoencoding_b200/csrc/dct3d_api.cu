@@ -58,7 +58,7 @@ struct dct3d_ctx {
     int use_tma = 1;
     int zero_skip = 1;               // option: the fused 8^3 encoder tests groups of high diagonals for zero before quantising them
     int tma_store = 1;               // option: the inverse kernel stores its pixel tiles by TMA (needs width % 32 == 0)
-    int col_classes = 0;             // option: ... and skips the upper half of the columns of a unit whose non-zero columns all lie in 0..3 (8^3)
+    int pack_sort = 1;               // option: the bit packer deals the cubes of a tile to its threads in order of their chunk counts
     int precision = 32;              // option: 64 = the fused entry points compute in fp64 (Java parity)
     int rounding = 0;                // option, fp64 mode: 0 = Math.round (floor(v+0.5)), 1 = C round()
     int debug = 0;
@@ -205,8 +205,8 @@ EncodeTiledFn get_encode_tiled()
 // Tensor map over the u8 frame stack [F][H][W], presented as {W, F, H} (frames before rows) so that one
 // box {32 px, C frames, C rows} lands in shared memory as [y][t][32 px] (SWIZZLE_32B): the image a warp
 // unit wants (unit_offset() in dct3d_kernels.cuh).
-// swizzled = false: the same box with a linear shared-memory image (the inverse kernel's tile store).
-bool make_tmap(CUtensorMap *tm, const void *frames, int W, int H, int F, int C, bool swizzled = true)
+// The inverse kernel's tile store uses the same map over its output frames.
+bool make_tmap(CUtensorMap *tm, const void *frames, int W, int H, int F, int C)
 {
     EncodeTiledFn fn = get_encode_tiled();
     if (!fn) return false;
@@ -215,7 +215,7 @@ bool make_tmap(CUtensorMap *tm, const void *frames, int W, int H, int F, int C, 
     cuuint32_t box[3] = {(cuuint32_t)kUnitW, (cuuint32_t)C, (cuuint32_t)C};
     cuuint32_t es[3] = {1, 1, 1};
     return fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void *>(frames), dims, strides, box, es,
-              CU_TENSOR_MAP_INTERLEAVE_NONE, swizzled ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -316,13 +316,11 @@ static int launch_reconstruct_coo(dct3d_ctx *ctx, const Layout &L, void *d_frame
     ctx->tma_store_used = tma_out ? 1 : 0;
     CUtensorMap tm;
     memset(&tm, 0, sizeof tm);
-    if (tma_out && !make_tmap(&tm, d_frames, ctx->W, ctx->H, L.nslabs * C, C, false))
+    if (tma_out && !make_tmap(&tm, d_frames, ctx->W, ctx->H, L.nslabs * C, C))
         return fail(ctx, DCT3D_E_CUDA, "cuTensorMapEncodeTiled failed (set option tma_store=0 to use row stores)");
-    const bool classes = tma_out && C == 8 && ctx->col_classes;
     auto kern = tma_out ? reconstruct_coo_kernel<C, TAIL_TMA> : reconstruct_coo_kernel<C, TAIL_ROWS>;
-    if constexpr (C == 8) { if (classes) kern = reconstruct_coo_kernel<C, TAIL_TMA_CLASSES>; }
     const int smem = CooSmem<C>::TOTAL;
-    int &occ = ctx->occ_cache[classes ? 8 : tma_out ? 7 : 5];
+    int &occ = ctx->occ_cache[tma_out ? 7 : 5];
     if (occ == 0) {
         CU_CHECK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         CU_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem));
@@ -442,7 +440,7 @@ int dct3d_create(dct3d_ctx **out, int device, int width, int height, int cube)
     // defaults of the kernel-variant options can be overridden from the environment (A/B runs of a whole test suite)
     if (const char *e = getenv("DCT3D_ZERO_SKIP")) ctx->zero_skip = atoi(e) ? 1 : 0;
     if (const char *e = getenv("DCT3D_TMA_STORE")) ctx->tma_store = atoi(e) ? 1 : 0;
-    if (const char *e = getenv("DCT3D_COL_CLASSES")) ctx->col_classes = atoi(e) ? 1 : 0;
+    if (const char *e = getenv("DCT3D_PACK_SORT")) ctx->pack_sort = atoi(e) ? 1 : 0;
     int rc = bind(ctx);
     if (rc == DCT3D_OK) {
         cudaError_t e = cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device);
@@ -516,7 +514,7 @@ int dct3d_set_option(dct3d_ctx *ctx, const char *key, long value)
     }
     if (!strcmp(key, "debug")) { ctx->debug = (int)value; return DCT3D_OK; }
     if (!strcmp(key, "zero_skip")) { ctx->zero_skip = value ? 1 : 0; return DCT3D_OK; }
-    if (!strcmp(key, "col_classes")) { ctx->col_classes = value ? 1 : 0; return DCT3D_OK; }
+    if (!strcmp(key, "pack_sort")) { ctx->pack_sort = value ? 1 : 0; return DCT3D_OK; }
     if (!strcmp(key, "tma_store")) {
         if (value && !get_encode_tiled()) return fail(ctx, DCT3D_E_CUDA, "cuTensorMapEncodeTiled unavailable");
         ctx->tma_store = value ? 1 : 0;
@@ -549,8 +547,8 @@ long dct3d_get_stat(const dct3d_ctx *ctx, const char *key)
     if (!strcmp(key, "launches")) return ctx->launches;
     if (!strcmp(key, "tma")) return ctx->use_tma;
     if (!strcmp(key, "zero_skip")) return ctx->zero_skip;
+    if (!strcmp(key, "pack_sort")) return ctx->pack_sort;
     if (!strcmp(key, "tma_store")) return ctx->tma_store;
-    if (!strcmp(key, "col_classes")) return ctx->col_classes;
     if (!strcmp(key, "tma_store_used")) return ctx->tma_store_used;
     if (!strcmp(key, "num_sms")) return ctx->num_sms;
     if (!strcmp(key, "chunks")) return ctx->chunks_last;
@@ -637,14 +635,13 @@ static int run_pack_noreset(dct3d_ctx *ctx, EncParams &P, void *d_stream, size_t
     P.tile_status = status_words(ctx);
     P.ticket = &dc->ticket; P.err = &dc->err; P.end_bit = &dc->end_bit;
     if (chain) { P.start_bit_dev = chain->d_start; P.end_bit = chain->d_end; P.end_bit_host = chain->h_end; P.err = chain->d_err; }
-    int &occ = ctx->occ_cache[4];
-    if (occ == 0) {
-        if (ctx->C == 8) CU_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, eg_pack_kernel<8>, kPackThreads, 0));
-        else CU_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, eg_pack_kernel<4>, kPackThreads, 0));
-    }
+    // the grid must be resident as a whole: a tile's look-back spins on its predecessors
+    void (*kern)(const EncParams) = ctx->pack_sort ? (ctx->C == 8 ? eg_pack_sorted_kernel<8> : eg_pack_sorted_kernel<4>)
+                                                   : (ctx->C == 8 ? eg_pack_kernel<8> : eg_pack_kernel<4>);
+    int &occ = ctx->occ_cache[ctx->pack_sort ? 9 : 4];
+    if (occ == 0) CU_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kPackThreads, 0));
     const long long grid = std::min<long long>(ptiles, (long long)ctx->num_sms * std::max(occ, 1));
-    if (ctx->C == 8) eg_pack_kernel<8><<<(unsigned)grid, kPackThreads, 0, st>>>(P);
-    else eg_pack_kernel<4><<<(unsigned)grid, kPackThreads, 0, st>>>(P);
+    kern<<<(unsigned)grid, kPackThreads, 0, st>>>(P);
     ctx->launches++;
     CU_CHECK(ctx, cudaGetLastError());
     if (end_bit) {

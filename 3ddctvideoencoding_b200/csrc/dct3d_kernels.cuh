@@ -815,6 +815,116 @@ eg_pack_kernel(const EncParams P)
     }
 }
 
+// The same packer with the cubes of a tile dealt to the threads in order of their chunk counts.  A thread's work is
+// proportional to the number of non-zero chunks of its cube, and a warp runs as long as its longest lane: in stream order a
+// warp of the benchmark clip runs 5.3 chunk iterations for a mean of 3.3 per cube (62% lane efficiency); sorted inside the
+// tile it runs 3.6 (91%).  Which thread packs which cube is free -- only the prefix sum of the bit counts has to follow
+// the stream order -- so the tile is counting-sorted by popc(chunk mask) in shared memory (33 keys, warp-aggregated
+// histogram), thread t counts and later writes cube perm[t], and the bit counts meet in stream order in shared memory for
+// the scan.  Same stream, bit for bit.
+template <int C>
+__global__ void __launch_bounds__(kPackThreads, 2048 / kPackThreads)
+eg_pack_sorted_kernel(const EncParams P)
+{
+    using G = Geo<C>;
+    constexpr int NW = kPackThreads / 32;
+    static_assert(NW <= 32 && kPackWorkers <= 65536, "tile geometry");
+    __shared__ uint32_t s_wsum[NW];
+    __shared__ uint32_t s_bits[kPackWorkers];       // bit counts of the tile's cubes in stream order, then their exclusive offsets
+    __shared__ uint16_t s_perm[kPackWorkers];       // sorted position -> cube of the tile
+    __shared__ uint32_t s_hist[33];                 // cubes per chunk count
+    __shared__ unsigned long long s_off;
+    __shared__ long long s_tile;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long ntiles = (P.L.ncubes + kPackWorkers - 1) / kPackWorkers;
+    const unsigned long long start_bit = P.start_bit_dev ? *P.start_bit_dev : P.start_bit;
+    for (;;) {
+        if (tid == 0) s_tile = (long long)atomicAdd(P.ticket, 1u);
+        if (tid < 33) s_hist[tid] = 0u;
+        __syncthreads();
+        const long long tile = s_tile;
+        if (tile >= ntiles) break;
+        // ---- counting sort of the tile by chunk count ------------------------------------------------------------
+        {
+            const long long cube_t = tile * kPackWorkers + tid;
+            const uint32_t key = cube_t < P.L.ncubes ? (uint32_t)__popc(P.cmask[cube_t]) : 0u;     // 0..32
+            const uint32_t peers = __match_any_sync(0xffffffffu, key);
+            const int leader = __ffs((int)peers) - 1;
+            uint32_t base = 0;
+            if (lane == leader) base = atomicAdd(&s_hist[key], (uint32_t)__popc(peers));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            const uint32_t rank = base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+            __syncthreads();                            // the histogram is complete
+            // every warp forms the exclusive prefix of keys 0..31 for itself (key 32 starts at their total)
+            const uint32_t h = s_hist[lane];
+            uint32_t incl = h;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += o;
+            }
+            const uint32_t first = __shfl_sync(0xffffffffu, incl - h, (int)(key & 31u));
+            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+            s_perm[(key < 32u ? first : total) + rank] = (uint16_t)tid;
+        }
+        __syncthreads();
+        // ---- count pass, on the cube this thread was dealt -----------------------------------------------------------
+        const int j = s_perm[tid];
+        const long long cube = tile * kPackWorkers + j;
+        const bool valid = cube < P.L.ncubes;
+        const int16_t *zz = valid ? cube_chunks<C>(P, cube) : P.zzg;
+        const uint32_t cm = valid ? P.cmask[cube] : 0u;
+        const uint32_t nbj = valid ? eg_count_cube<G::CS, true>(zz, cm) : 0u;
+        s_bits[j] = nbj;
+        __syncthreads();
+        // ---- scan in stream order ------------------------------------------------------------------------------------
+        const uint32_t nb = s_bits[tid];
+        uint32_t incl = nb;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += o;
+        }
+        if (lane == 31) s_wsum[warp] = incl;
+        __syncthreads();
+        {
+            // every warp scans the warp sums for itself; warp 0 also resolves the tile's bit offset
+            const uint32_t w = lane < NW ? s_wsum[lane] : 0u;
+            uint32_t wi = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xffffffffu, wi, d);
+                if (lane >= d) wi += o;
+            }
+            const uint32_t wexcl = __shfl_sync(0xffffffffu, wi - w, warp);
+            s_bits[tid] = wexcl + (incl - nb);          // exclusive offset of cube `tid` inside the tile (own slot: no reader yet)
+            if (warp == 0) {
+                const uint32_t total = __shfl_sync(0xffffffffu, wi, 31);
+                const unsigned long long off = tile_lookback(P.tile_status, tile, total, start_bit, lane, P.err);
+                if (lane == 0) {
+                    s_off = off;
+                    if (tile == ntiles - 1) {
+                        *P.end_bit = off + total;
+                        if (P.end_bit_host) *P.end_bit_host = off + total;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // ---- write pass ----------------------------------------------------------------------------------------------
+        if (valid) {
+            const unsigned long long off = s_off + s_bits[j];
+            if (off + nbj + 64 > P.cap_bits) {
+                atomicOr(P.err, 1u);
+            } else {
+                GlobalSink sink{P.out_words};
+                eg_write_cube<G::CS, GlobalSink, true>(zz, cm, off, sink);
+            }
+        }
+        __syncthreads();                                // s_tile, s_hist, s_perm, s_bits, s_wsum and s_off are reused
+    }
+}
+
 // Placement of a slab range's stream inside the clip's one stream (the rule of ExpGolomb.c:112-130 with
 // encoder.c:263-271): a GPU codes its range from bit 0 of its own buffer; once the bit counts of the ranges before it are
 // known, its bits move to phase = (global start bit) % 8, so that the host only has to copy whole bytes to byte
@@ -1027,9 +1137,12 @@ seg_fix_kernel(const DecParams P, unsigned int round)
 }
 
 // Exclusive prefix sums over all segments of (a) the code counts and (b) the non-zero code counts:
-// 1024 segments per CTA tile, block scan, decoupled look-back across tiles (same machinery as the
+// 4096 segments per CTA tile (16 per thread; round 2: 4 per thread left the kernel a chain of look-back hops, 19 -> 16 us), block scan, decoupled look-back across tiles (same machinery as the
 // bit packer; one status array per quantity).  seg_first[nseg] / seg_nzfirst[nseg] = totals.
-constexpr int kScanThreads = 256, kScanItems = 4;
+#ifndef DCT3D_SCAN_ITEMS
+#define DCT3D_SCAN_ITEMS 16
+#endif
+constexpr int kScanThreads = 256, kScanItems = DCT3D_SCAN_ITEMS;
 
 __global__ void __launch_bounds__(kScanThreads)
 seg_prefix_kernel(const DecParams P, unsigned long long *status_codes, unsigned long long *status_nz, unsigned int *ticket)
@@ -1299,8 +1412,10 @@ template <int C>
 __device__ __forceinline__ void tile_store(float (&a)[C][C], uint8_t *xbuf, int cl, int r, int lane, const CUtensorMap *tmap,
                                            const UnitPos &pos)
 {
-    // the last exchange round ended with __syncwarp(): every lane holds its vectors, the buffer is free
-    uint8_t *row = xbuf + r * kUnitW + cl * C;     // [y][t = r][x = cl * C ..]
+    // the last exchange round ended with __syncwarp(): every lane holds its vectors, the buffer is free.
+    // The tile has the encoder's SWIZZLE_32B image (unit_offset): the 16-byte halves of rows 4..7 of every 8 are exchanged,
+    // so the 16 lanes a 64-bit store is served for (two cubes x 8 frames: half a row each) cover all 32 banks once.  (Linear,
+    // rows 0..3 and 4..7 met in the same banks: 4 wavefronts per STS.64 instead of 2, measured.)
 #pragma unroll
     for (int y = 0; y < C; y++) {
         uint32_t w[2] = {0, 0};
@@ -1310,8 +1425,9 @@ __device__ __forceinline__ void tile_store(float (&a)[C][C], uint8_t *xbuf, int 
             const uint32_t b2 = f2u8_sat(a[y][x + 2]), b3 = f2u8_sat(a[y][x + 3]);
             w[x / 4] = __byte_perm(__byte_perm(b0, b1, 0x0040), __byte_perm(b2, b3, 0x0040), 0x5410);
         }
-        if (C == 8) *reinterpret_cast<uint2 *>(row + y * C * kUnitW) = make_uint2(w[0], w[1]);
-        else *reinterpret_cast<uint32_t *>(row + y * C * kUnitW) = w[0];
+        uint8_t *dst = xbuf + unit_offset<C>(y, r, cl * C);        // [y][t = r][x = cl * C ..]
+        if (C == 8) *reinterpret_cast<uint2 *>(dst) = make_uint2(w[0], w[1]);
+        else *reinterpret_cast<uint32_t *>(dst) = w[0];
     }
     fence_proxy_async_smem();
     __syncwarp();
@@ -1343,12 +1459,12 @@ __device__ __forceinline__ void idct_tile_store(float (&b)[C][C], uint8_t *xbuf,
 // it SLOWER (388 -> 417 us for the aliasing alone, 442 us at 5 CTAs, 528 us at 6): the shared-memory pipe and the issue slots
 // are co-limiters, so extra wipes and spill traffic cost more than the extra warps hide.  Allowing fewer CTAs changes nothing:
 // the compiler does not want more than 128 registers here.
-#ifndef DCT3D_CLASS_VARIANT
-#define DCT3D_CLASS_VARIANT 2
-#endif
 #ifndef DCT3D_COO_PRE
 #define DCT3D_COO_PRE 3
 #endif
+// reconstruct_coo_kernel: a cube with more than PRE * C + kWipeAllOver list entries is wiped as a whole after the t pass
+// instead of entry by entry (one pass of the entry loop serves 4 * C entries)
+constexpr int kWipeAllOver = 32;
 #ifndef DCT3D_NAT_PAD
 #define DCT3D_NAT_PAD 4
 #endif
@@ -1367,14 +1483,13 @@ struct CooSmem {
     static constexpr int TOTAL = TAB_OFF + G::CS * 4;
 };
 
-// TAIL: 0 = row stores (idct_store), 1 = TMA tile store (idct_tile_store), 2 = TMA tile store + column classes (C = 8).
-// Column classes: a unit whose non-zero k2 columns all lie in 0..3 (warp-uniform; 25% of the units of the benchmark clip)
-// reads half of its cube rows, runs one exchange round instead of two and the x butterflies with four live inputs
-// (dct8_inv_n_lo4): 96 of about 270 data-pipe wavefronts and 110 of about 1000 instructions less for such a unit, inside ONE
-// tail.  (First version, measured: three specialised copies of the whole tail -- columns 0..3 / 0..5 / all, the middle one
-// with an exchange round of 8-byte vectors -- made the kernel 3248 instructions = 52 KB, beyond the 32 KB instruction cache:
-// 405 us instead of 348.)  Bit-identical to the unspecialised tail.
-constexpr int TAIL_ROWS = 0, TAIL_TMA = 1, TAIL_TMA_CLASSES = 2;
+// TAIL: 0 = row stores (idct_store), 1 = TMA tile store (idct_tile_store).
+// Measured and dropped in round 2 (profiles/r2_runs/ab_variants_s2.jsonl): "column classes" -- units whose non-zero k2
+// columns all lie in 0..3 (25% of the benchmark clip) or 0..5 (65%) taking tails that neither load, exchange nor transform
+// the columns known to be zero (dct8_inv_n with four / six live inputs, an exchange round of 8-byte vectors).  Three copies
+// of the tail made the kernel 3248 instructions = 52 KB, beyond the 32 KB instruction cache: 405 us against 348; one tail
+// with a warp-uniform branch around the upper half: 352 us against 346 (the branches cost what the skipped work saves).
+constexpr int TAIL_ROWS = 0, TAIL_TMA = 1;
 
 template <int C, int TAIL = TAIL_ROWS>
 __global__ void __launch_bounds__(kThreads, 4)
@@ -1385,7 +1500,6 @@ reconstruct_coo_kernel(const __grid_constant__ CUtensorMap tmap_out, const Layou
     // TMA_OUT: the pixels leave as one TMA box per unit (idct_tile_store; tmap_out is the tensor map of `frames`), else by
     // row stores (idct_store; tmap_out is not looked at)
     constexpr bool TMA_OUT = TAIL != TAIL_ROWS;
-    constexpr bool CLASSES = TAIL == TAIL_TMA_CLASSES && C == 8;
     // coo_limit: row pointers are clamped to it, so that a launch that runs ahead of the host's look at the control
     // block (lists of a stream whose index discovery has not converged, or of a damaged stream) stays inside the buffer
     // cube_base: the launch reconstructs cubes [cube_base, cube_base + L.ncubes) of the parsed stream into a frame buffer
@@ -1414,11 +1528,13 @@ reconstruct_coo_kernel(const __grid_constant__ CUtensorMap tmap_out, const Layou
     auto fetch_rows = [&](int grp) {
         const long long cube = (long long)grp * G::CPW + cl;
         const bool ok = grp < ngroups && cube < L.ncubes;
-        z_nn = ok ? min(__ldg(coo_start + cube), coo_limit) : 0ull;
+        // raw values: nothing may consume the loads here, a pass before they are needed (round 2: the clamp sat right behind
+        // the load and cost a full L2 round trip per pass, 3% of the kernel's samples)
+        z_nn = ok ? __ldg(coo_start + cube) : 0ull;
         zend_nn = ok ? __ldg(reinterpret_cast<const uint32_t *>(coo_start + cube + 1)) : 0u;
     };
     auto rotate_rows = [&]() {
-        z_n = z_nn;
+        z_n = min(z_nn, coo_limit);
         c_n = min(zend_nn - (uint32_t)z_nn, (uint32_t)G::CS);
     };
     auto fetch_entries = [&]() {               // for the group whose row pointers are in z_n / c_n
@@ -1460,13 +1576,16 @@ reconstruct_coo_kernel(const __grid_constant__ CUtensorMap tmap_out, const Layou
             for (int k = 0; k < PRE; k++)
                 if ((uint32_t)(r + k * C) < cnt) { nat[ix[k]] = tv[k]; colbits |= 1u << (coo_swizzle<C>(ix[k]) & (C - 1)); }
         }
-        // dense cubes: the rest of the list, four independent loads at a time
-        for (uint32_t i = r + PRE * C; i < cnt; i += 4 * C) {
-            uint32_t x[4];
+        // dense cubes: the rest of the list, DENSE_LD independent loads at a time (the transform's registers are not live
+        // here; on noise content, 64 entries per lane, the loop is a chain of L2 round trips: 8 in flight instead of 4
+        // halves their number)
+        constexpr int DENSE_LD = 8;
+        for (uint32_t i = r + PRE * C; i < cnt; i += DENSE_LD * C) {
+            uint32_t x[DENSE_LD];
 #pragma unroll
-            for (int k = 0; k < 4; k++) x[k] = i + k * C < cnt ? __ldg(coo + z0 + i + k * C) : 0u;
+            for (int k = 0; k < DENSE_LD; k++) x[k] = i + k * C < cnt ? __ldg(coo + z0 + i + k * C) : 0u;
 #pragma unroll
-            for (int k = 0; k < 4; k++)
+            for (int k = 0; k < DENSE_LD; k++)
                 if (i + k * C < cnt) put(x[k]);
         }
         if (cnt > (uint32_t)(PRE * C)) colbits = (1u << C) - 1u;   // a dense cube: no pruning, and no bookkeeping in its loop
@@ -1479,86 +1598,22 @@ reconstruct_coo_kernel(const __grid_constant__ CUtensorMap tmap_out, const Layou
 #pragma unroll
             for (int k = 0; k < PRE; k++)
                 if ((uint32_t)(r + k * C) < cnt) nat[(e[k] >> 16) & (G::CS - 1)] = 0.0f;
-            for (uint32_t i = r + PRE * C; i < cnt; i += 4 * C) {
-                uint32_t x[4];
+            if (cnt > (uint32_t)(PRE * C + kWipeAllOver)) {
+                // a dense cube is wiped as a whole -- CS / C floats per lane as interleaved 16-byte stores, no list re-read
+                // (round 2, measured on noise: the re-read of 64 entries per lane was a second chain of L2 round trips)
 #pragma unroll
-                for (int k = 0; k < 4; k++) x[k] = i + k * C < cnt ? __ldg(coo + z0 + i + k * C) : 0u;
+                for (int i = 0; i < G::CS / (4 * C); i++) reinterpret_cast<float4 *>(nat)[i * C + r] = make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+                for (uint32_t i = r + PRE * C; i < cnt; i += 4 * C) {
+                    uint32_t x[4];
 #pragma unroll
-                for (int k = 0; k < 4; k++)
-                    if (i + k * C < cnt) nat[(x[k] >> 16) & (G::CS - 1)] = 0.0f;
+                    for (int k = 0; k < 4; k++) x[k] = i + k * C < cnt ? __ldg(coo + z0 + i + k * C) : 0u;
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        if (i + k * C < cnt) nat[(x[k] >> 16) & (G::CS - 1)] = 0.0f;
+                }
             }
         };
-        if constexpr (CLASSES) {
-            // column classes: a unit whose non-zero columns all lie in 0..3 (warp-uniform) neither loads, transforms nor
-            // exchanges the upper half of its rows, and runs the x butterflies with four live inputs
-            const bool hi = (colmask & 0xf0u) != 0;
-            float b[C][C], a[C][C];                              // columns 4..7 are only touched when hi
-#if DCT3D_CLASS_VARIANT == 2
-#pragma unroll
-            for (int k2 = 0; k2 < C; k2 += 4) {
-#pragma unroll
-                for (int k0 = 0; k0 < C; k0++) {
-                    const float4 v = *reinterpret_cast<const float4 *>(nat + (k0 * C + r) * C + (k2 ^ (r & 4)));   // coo_swizzle
-                    b[k0][k2] = v.x; b[k0][k2 + 1] = v.y; b[k0][k2 + 2] = v.z; b[k0][k2 + 3] = v.w;
-                }
-            }
-            inv_t_n_masked<C, float>(b, colmask);
-#else
-#pragma unroll
-            for (int k0 = 0; k0 < C; k0++) {
-                const float4 v = *reinterpret_cast<const float4 *>(nat + (k0 * C + r) * C + (r & 4));   // coo_swizzle
-                b[k0][0] = v.x; b[k0][1] = v.y; b[k0][2] = v.z; b[k0][3] = v.w;
-            }
-            if (hi) {
-#pragma unroll
-                for (int k0 = 0; k0 < C; k0++) {
-                    const float4 v = *reinterpret_cast<const float4 *>(nat + (k0 * C + r) * C + (4 ^ (r & 4)));
-                    b[k0][4] = v.x; b[k0][5] = v.y; b[k0][6] = v.z; b[k0][7] = v.w;
-                }
-            }
-#pragma unroll
-            for (int x = 0; x < 4; x++)
-                if ((colmask >> x) & 1u) Dct1D<C, float>::template inv_n<C>(&b[0][x]);
-            if (hi) {
-#pragma unroll
-                for (int x = 4; x < C; x++)
-                    if ((colmask >> x) & 1u) Dct1D<C, float>::template inv_n<C>(&b[0][x]);
-            }
-#endif
-            wipe();
-            if (lane == 0) tma_store_wait_read();                // the previous unit's tile (in xbuf) has been read
-            __syncwarp();
-            Xch<C, float>::round(xbuf, cl, r, b, a, 0);
-#if DCT3D_CLASS_VARIANT == 1
-            if (hi) {
-                Xch<C, float>::round(xbuf, cl, r, b, a, 1);
-            } else {
-#pragma unroll
-                for (int t = 0; t < C; t++) a[t][4] = a[t][5] = a[t][6] = a[t][7] = 0.0f;
-            }
-            inv_yx_n_masked<C, float>(a, colmask);
-#else
-            if (hi) Xch<C, float>::round(xbuf, cl, r, b, a, 1);
-#pragma unroll
-            for (int x = 0; x < 4; x++)
-                if ((colmask >> x) & 1u) Dct1D<C, float>::template inv_n<C>(&a[0][x]);
-            if (hi) {
-#pragma unroll
-                for (int x = 4; x < C; x++)
-                    if ((colmask >> x) & 1u) Dct1D<C, float>::template inv_n<C>(&a[0][x]);
-#pragma unroll
-                for (int y = 0; y < C; y++) Dct1D<C, float>::template inv_n<1>(&a[y][0]);
-            } else {
-#pragma unroll
-                for (int y = 0; y < C; y++) {
-                    float *v = &a[y][0];
-                    dct8_inv_n_lo4<float>(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
-                }
-            }
-#endif
-            tile_store<C>(a, xbuf, cl, r, lane, &tmap_out, upos);
-            unit_advance(L, upos, ustep);
-        } else {
         float b[C][C];
         // first halves of all rows, then second halves: the t pass of columns 0..3 starts while the
         // second halves are still in flight
@@ -1578,7 +1633,6 @@ reconstruct_coo_kernel(const __grid_constant__ CUtensorMap tmap_out, const Layou
             unit_advance(L, upos, ustep);
         } else {
             idct_store<C, true, true>(b, xbuf, cl, r, cube < L.ncubes, L, cube, frames, colmask);
-        }
         }
     }
     if (TMA_OUT && lane == 0) tma_store_wait_read();   // the last tile must have been read before the CTA's shared memory goes

@@ -30,27 +30,6 @@ template <typename T> DCT_HD T fma_t(T a, T b, T c);
 template <> DCT_HD float fma_t<float>(float a, float b, float c) { return fmaf(a, b, c); }
 template <> DCT_HD double fma_t<double>(double a, double b, double c) { return fma(a, b, c); }
 
-// a product that must be rounded on its own: the compiler may not contract it with a following addition into an FMA
-template <typename T> DCT_HD T mul_rn(T a, T b);
-template <> DCT_HD float mul_rn<float>(float a, float b)
-{
-#if defined(__CUDA_ARCH__)
-    return __fmul_rn(a, b);
-#else
-    volatile float p = a * b;
-    return p;
-#endif
-}
-template <> DCT_HD double mul_rn<double>(double a, double b)
-{
-#if defined(__CUDA_ARCH__)
-    return __dmul_rn(a, b);
-#else
-    volatile double p = a * b;
-    return p;
-#endif
-}
-
 // cos(k*pi/16) / 2 for k = 1..7 (the a_k = 1/2 normalisation folded in), and 1/sqrt(8).
 #define DCT_H1 0.49039264020161522456
 #define DCT_H2 0.46193976625564337806
@@ -145,26 +124,6 @@ DCT_HD void dct8_inv_n(T &x0, T &x1, T &x2, T &x3, T &x4, T &x5, T &x6, T &x7)
     const T o1 = fma_t<T>(x7, (T)(-DCT_H5 / DCT_H7), fma_t<T>(x5, (T)(-DCT_H1 / DCT_H5), fma_t<T>(x3, (T)(-DCT_H7 / DCT_H3), x1 * (T)(DCT_H3 / DCT_H1))));
     const T o2 = fma_t<T>(x7, (T)(DCT_H3 / DCT_H7), fma_t<T>(x5, (T)(DCT_H7 / DCT_H5), fma_t<T>(x3, (T)(-DCT_H1 / DCT_H3), x1 * (T)(DCT_H5 / DCT_H1))));
     const T o3 = fma_t<T>(x7, (T)(-DCT_H1 / DCT_H7), fma_t<T>(x5, (T)(DCT_H3 / DCT_H5), fma_t<T>(x3, (T)(-DCT_H5 / DCT_H3), x1 * (T)(DCT_H7 / DCT_H1))));
-    x0 = e0 + o0; x7 = e0 - o0;
-    x1 = e1 + o1; x6 = e1 - o1;
-    x2 = e2 + o2; x5 = e2 - o2;
-    x3 = e3 + o3; x4 = e3 - o3;
-}
-
-// dct8_inv_n for inputs whose last four frequencies are zero (x4 = ... = x7 = 0): the same operations in the same order
-// with the zero terms left out.  x + 0 = x and fma(0, c, y) = y exactly, so every output equals dct8_inv_n's (up to the
-// sign of a zero, which no later operation can turn into a different value).  20 instead of 31 instructions; x4..x7 are
-// not read.
-template <typename T>
-DCT_HD void dct8_inv_n_lo4(T &x0, T &x1, T &x2, T &x3, T &x4, T &x5, T &x6, T &x7)
-{
-    const T ba = (T)(DCT_H6 / DCT_H2);
-    const T u3 = mul_rn<T>(x2, ba);
-    const T e0 = x0 + x2, e3 = x0 - x2, e1 = x0 + u3, e2 = x0 - u3;
-    const T o0 = x1 + x3;
-    const T o1 = fma_t<T>(x3, (T)(-DCT_H7 / DCT_H3), x1 * (T)(DCT_H3 / DCT_H1));
-    const T o2 = fma_t<T>(x3, (T)(-DCT_H1 / DCT_H3), x1 * (T)(DCT_H5 / DCT_H1));
-    const T o3 = fma_t<T>(x3, (T)(-DCT_H5 / DCT_H3), x1 * (T)(DCT_H7 / DCT_H1));
     x0 = e0 + o0; x7 = e0 - o0;
     x1 = e1 + o1; x6 = e1 - o1;
     x2 = e2 + o2; x5 = e2 - o2;

@@ -44,7 +44,7 @@ torch.cuda.synchronize()
 te = sum(a.elapsed_time(b) for a, b, d in evs) / steps
 td = sum(b.elapsed_time(d) for a, b, d in evs) / steps
 print(json.dumps({"lib": os.path.basename(os.environ.get("DCT3D_LIB", "in-tree")),
-                  "opts": {k: c.stat(k) for k in ("zero_skip", "tma_store", "col_classes", "tma_store_used")}, "frames": F, "cube": cube, "kind": kind, "precision": precision,
+                  "opts": {k: c.stat(k) for k in ("zero_skip", "tma_store", "pack_sort", "tma_store_used")}, "frames": F, "cube": cube, "kind": kind, "precision": precision,
                   "ms_per_step": e0.elapsed_time(e1) / steps, "encode_ms": te, "decode_ms": td,
                   "encode_kernel_ms": c.stat("ns_encode_kernel_avg") * 1e-6, "reconstruct_kernel_ms": c.stat("ns_reconstruct_kernel_avg") * 1e-6,
                   "fps": F * steps / (e0.elapsed_time(e1) * 1e-3), "bits": end,

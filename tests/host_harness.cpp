@@ -86,16 +86,6 @@ int hh_quantize(float coef, int ksum) { return quantize_f32(coef, 1.0f / (float)
 // the fused encoder's zero-run test: threshold of a reciprocal, and the quantiser's own verdict for a coefficient
 float hh_zero_threshold(float recip) { return zero_threshold(recip); }
 int hh_quantize_recip(float coef, float recip) { return quantize_f32(coef, recip); }
-// dct8_inv_n on in[0..3] followed by zeros (full[8]) and its specialisation for four live inputs (lo[8])
-void hh_inv8_live(const float *in, int live, float *full, float *lo)
-{
-    float f[8], l[8];
-    for (int i = 0; i < 8; i++) { f[i] = i < live ? in[i] : 0.0f; l[i] = i < live ? in[i] : -123456.0f; }   // lo must not read past live
-    dct8_inv_n<float>(f[0], f[1], f[2], f[3], f[4], f[5], f[6], f[7]);
-    dct8_inv_n_lo4<float>(l[0], l[1], l[2], l[3], l[4], l[5], l[6], l[7]);
-    memcpy(full, f, sizeof f);
-    memcpy(lo, l, sizeof l);
-}
 
 // zz: ncubes x cs int16 in zig-zag order.  Writes the stream into out (cap bytes, zeroed by the
 // caller) starting at start_bit; returns the end bit.  Uses count + write exactly as the kernel.

@@ -452,8 +452,8 @@ def test_multi_weighted_shares_give_the_same_stream(codec_mod, synth):
                                              (64, 64, 16, 8, "sparse")])
 def test_kernel_variants_are_bit_identical(codec_mod, oracle, synth, W, H, F, cube, kind):
     """Round-2 kernel variants -- the encoder's zero-run skip (option zero_skip), the inverse kernel's TMA tile store
-    (tma_store) and its column classes (col_classes) -- against the plain paths: same stream, same frames, and the frames
-    within +-1 of the oracle.  Widths that are not a multiple of 32 must fall back to row stores by themselves."""
+    (tma_store) and the packer's sorted deal (pack_sort) -- against the plain paths: same stream, same frames, and the
+    frames within +-1 of the oracle.  Widths that are not a multiple of 32 must fall back to row stores by themselves."""
     if kind == "sparse":                       # mostly flat cubes with a few textured ones: all three column classes occur
         rng = np.random.default_rng(3)
         clip = np.full((F, H, W), 120, np.uint8)
@@ -463,15 +463,15 @@ def test_kernel_variants_are_bit_identical(codec_mod, oracle, synth, W, H, F, cu
     else:
         clip = getattr(synth, kind)(W, H, F, 9) if kind != "constant" else synth.constant(W, H, F, 77)
     outs = {}
-    for skip, tma, classes in [(0, 0, 0), (1, 0, 0), (0, 1, 0), (0, 1, 1), (1, 1, 1)]:
+    for skip, tma, psort in [(0, 0, 0), (1, 0, 0), (0, 1, 0), (0, 0, 1), (1, 1, 1)]:
         with codec_mod.Codec(W, H, cube) as c:
             c.set_option("zero_skip", skip)
             c.set_option("tma_store", tma)
-            c.set_option("col_classes", classes)
+            c.set_option("pack_sort", psort)
             stream, nbits = c.encode_u8(clip)
             dec = c.decode_u8(stream, F)
             assert c.stat("tma_store_used") == (1 if tma and W % 32 == 0 else 0)
-            outs[(skip, tma, classes)] = (stream.tobytes(), nbits, dec)
+            outs[(skip, tma, psort)] = (stream.tobytes(), nbits, dec)
     base = outs[(0, 0, 0)]
     for key, (s, n, d) in outs.items():
         assert n == base[1] and s == base[0], f"stream differs for variant {key}"
