@@ -440,7 +440,7 @@ int dct3d_create(dct3d_ctx **out, int device, int width, int height, int cube)
     // defaults of the kernel-variant options can be overridden from the environment (A/B runs of a whole test suite)
     if (const char *e = getenv("DCT3D_ZERO_SKIP")) ctx->zero_skip = atoi(e) ? 1 : 0;
     if (const char *e = getenv("DCT3D_TMA_STORE")) ctx->tma_store = atoi(e) ? 1 : 0;
-    if (const char *e = getenv("DCT3D_PACK_SORT")) ctx->pack_sort = atoi(e) ? 1 : 0;
+    if (const char *e = getenv("DCT3D_PACK_SORT")) ctx->pack_sort = std::min(std::max(atoi(e), 0), 2);
     int rc = bind(ctx);
     if (rc == DCT3D_OK) {
         cudaError_t e = cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device);
@@ -514,7 +514,11 @@ int dct3d_set_option(dct3d_ctx *ctx, const char *key, long value)
     }
     if (!strcmp(key, "debug")) { ctx->debug = (int)value; return DCT3D_OK; }
     if (!strcmp(key, "zero_skip")) { ctx->zero_skip = value ? 1 : 0; return DCT3D_OK; }
-    if (!strcmp(key, "pack_sort")) { ctx->pack_sort = value ? 1 : 0; return DCT3D_OK; }
+    if (!strcmp(key, "pack_sort")) {
+        if (value < 0 || value > 2) return fail(ctx, DCT3D_E_INVALID, "pack_sort must be 0, 1 or 2");
+        ctx->pack_sort = (int)value;
+        return DCT3D_OK;
+    }
     if (!strcmp(key, "tma_store")) {
         if (value && !get_encode_tiled()) return fail(ctx, DCT3D_E_CUDA, "cuTensorMapEncodeTiled unavailable");
         ctx->tma_store = value ? 1 : 0;
@@ -636,9 +640,12 @@ static int run_pack_noreset(dct3d_ctx *ctx, EncParams &P, void *d_stream, size_t
     P.ticket = &dc->ticket; P.err = &dc->err; P.end_bit = &dc->end_bit;
     if (chain) { P.start_bit_dev = chain->d_start; P.end_bit = chain->d_end; P.end_bit_host = chain->h_end; P.err = chain->d_err; }
     // the grid must be resident as a whole: a tile's look-back spins on its predecessors
-    void (*kern)(const EncParams) = ctx->pack_sort ? (ctx->C == 8 ? eg_pack_sorted_kernel<8> : eg_pack_sorted_kernel<4>)
-                                                   : (ctx->C == 8 ? eg_pack_kernel<8> : eg_pack_kernel<4>);
-    int &occ = ctx->occ_cache[ctx->pack_sort ? 9 : 4];
+    // pack_sort: 0 = cubes in stream order, 1 = sorted deal, 2 = sorted deal with balanced warps (tiles of 2 x kPackThreads
+    // cubes: the status words and ptiles above, counted in tiles of kPackWorkers, are more than it needs)
+    void (*kern)(const EncParams) = ctx->pack_sort == 2 ? (ctx->C == 8 ? eg_pack_balanced_kernel<8> : eg_pack_balanced_kernel<4>)
+                                    : ctx->pack_sort ? (ctx->C == 8 ? eg_pack_sorted_kernel<8> : eg_pack_sorted_kernel<4>)
+                                                     : (ctx->C == 8 ? eg_pack_kernel<8> : eg_pack_kernel<4>);
+    int &occ = ctx->occ_cache[ctx->pack_sort == 2 ? 10 : ctx->pack_sort ? 9 : 4];
     if (occ == 0) CU_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kPackThreads, 0));
     const long long grid = std::min<long long>(ptiles, (long long)ctx->num_sms * std::max(occ, 1));
     kern<<<(unsigned)grid, kPackThreads, 0, st>>>(P);

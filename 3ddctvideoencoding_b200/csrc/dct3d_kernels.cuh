@@ -15,16 +15,21 @@
 //   * In that layout the elements a thread owns on one diagonal k0+k2 are CONTIGUOUS in the
 //     reference's zig-zag order (CubeUtils.c:17-42: slices of constant x+y+z, y outer, z middle),
 //     so the zig-zag reorder is a predicated STS.U16 per non-zero with per-lane base registers and
-//     immediate offsets; the non-zero 16-coefficient chunks go to a sparsely touched scratch.
-//   * eg_pack_kernel: one thread per cube: count pass, block scan, decoupled look-back across tiles
-//     for the global bit offset, write pass straight to the global stream (plain stores inside a
-//     cube, OR-merge for the two boundary words).  The bitstream never visits the host
-//     (reference: ExpGolomb.c:32-64 on one host thread).
+//     immediate offsets; the non-zero 16-coefficient chunks go to a sparsely touched scratch.  Groups of
+//     high diagonals are first tested against the lane's exact zero threshold and skipped when the whole warp
+//     has nothing there (97% of the coefficients are zero).
+//   * eg_pack_kernel / eg_pack_sorted_kernel: one thread per cube: count pass, block scan, decoupled look-back
+//     across tiles for the global bit offset, write pass straight to the global stream (plain stores inside a
+//     cube, OR-merge for the two boundary words).  The sorted kernel deals the cubes of a tile to the threads in
+//     order of their chunk counts, so that the lanes of a warp carry like loads.  The bitstream never visits the
+//     host (reference: ExpGolomb.c:32-64 on one host thread).
 //   * Decode: index discovery over 1024-bit segments (seg_scan_kernel with a lead-in walk that
 //     guesses every entry point, keeping the non-zero codes it decodes; seg_fix_kernel; two prefix
 //     sums), seg_emit_kernel turns the segment lists into CSR rows of the cubes, and
 //     reconstruct_coo_kernel scatters the dequantised non-zeros into a float cube, runs the inverse
-//     butterflies (skipping all-zero columns), clamps, truncates and stores u8 rows.
+//     butterflies (skipping all-zero columns), clamps, truncates and hands the warp's pixel tile to TMA
+//     (one cp.async.bulk.tensor store per unit: the encoder's box read backwards; row stores for widths that
+//     are not a multiple of 32).
 //   * transform_kernel: the f32 / f64 transform seams; rgb_planes_kernel: RGBUtils split / mix;
 //     quant_f64_kernel and friends: the fp64 mode.
 #pragma once
@@ -378,15 +383,18 @@ constexpr unsigned long long kFlagAgg = 1ull << 62;
 constexpr unsigned long long kFlagPrefix = 2ull << 62;
 constexpr unsigned long long kValMask = (1ull << 62) - 1;
 
+// A status word carries its flag AND its value in one 64-bit word and publishes nothing else, so relaxed gpu-scope accesses
+// are enough.  (Round 2: they were acquire / release; every acquire poll of the look-back is a CCTL.IVALL, an invalidation
+// of the SM's whole L1 -- 279 k of them per launch of the packer, whose write pass re-reads the chunks its count pass loaded.)
 __device__ __forceinline__ unsigned long long ld_status(const unsigned long long *p)
 {
     unsigned long long v;
-    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ void st_status(unsigned long long *p, unsigned long long v)
 {
-    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
 // Called by ONE full warp.  total = this tile's bit count.  Returns the absolute bit offset of
@@ -919,6 +927,140 @@ eg_pack_sorted_kernel(const EncParams P)
             } else {
                 GlobalSink sink{P.out_words};
                 eg_write_cube<G::CS, GlobalSink, true>(zz, cm, off, sink);
+            }
+        }
+        __syncthreads();                                // s_tile, s_hist, s_perm, s_bits, s_wsum and s_off are reused
+    }
+}
+
+// The sorted deal with BALANCED warps.  With one cube per thread the sorted order gives warp 0 the lightest 32 cubes of a
+// tile and the last warp the heaviest: the light warps wait at the tile's barriers (barrier stalls rose from 33% to 44% of
+// the warp samples with the sort).  Here a tile is 2 x kPackThreads cubes, cut into 2 NW sorted blocks of 32, and warp w
+// packs blocks w and 2 NW - 1 - w -- a light one and a heavy one: every warp's lanes still run cubes of like size, and
+// every warp carries about the same load.  Between the passes a thread keeps nothing but its place: what it needs of a
+// cube (mask, chunk pointer) is found again from the permutation, which costs a few L1 hits and keeps the kernel at 32
+// registers.
+// Measured (profiles/r2_runs/ab_variants_s2_call6.jsonl), against the sorted deal: 4^3 cubes -45 us per 256 frames, 8^3
+// natural content +6 us, 8^3 noise +230 us (two dense cubes in a row per thread, half as many tiles in flight).  It is
+// option pack_sort = 2, not the default.
+constexpr int kPackBalTile = 2 * kPackThreads;
+
+template <int C>
+__global__ void __launch_bounds__(kPackThreads, 2048 / kPackThreads)
+eg_pack_balanced_kernel(const EncParams P)
+{
+    using G = Geo<C>;
+    constexpr int NW = kPackThreads / 32, TILE = kPackBalTile;
+    static_assert(NW <= 32 && TILE <= 65536, "tile geometry");
+    __shared__ uint32_t s_wsum[NW];
+    __shared__ uint32_t s_bits[TILE];               // bit counts of the tile's cubes in stream order, then their exclusive offsets
+    __shared__ uint16_t s_perm[TILE];               // sorted position -> cube of the tile
+    __shared__ uint32_t s_hist[33];                 // cubes per chunk count
+    __shared__ unsigned long long s_off;
+    __shared__ long long s_tile;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long ntiles = (P.L.ncubes + TILE - 1) / TILE;
+    const unsigned long long start_bit = P.start_bit_dev ? *P.start_bit_dev : P.start_bit;
+    // this thread's two places in the sorted order: a block from the light end and its mirror from the heavy end
+    const int place_light = warp * 32 + lane, place_heavy = (2 * NW - 1 - warp) * 32 + lane;
+    for (;;) {
+        if (tid == 0) s_tile = (long long)atomicAdd(P.ticket, 1u);
+        if (tid < 33) s_hist[tid] = 0u;
+        __syncthreads();
+        const long long tile = s_tile;
+        if (tile >= ntiles) break;
+        const long long cube0 = tile * TILE;
+        // ---- counting sort of the tile by chunk count (two cubes per thread: tid and kPackThreads + tid) ----------
+        {
+            uint32_t key[2], rank[2];
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                const long long c = cube0 + q * kPackThreads + tid;
+                key[q] = c < P.L.ncubes ? (uint32_t)__popc(P.cmask[c]) : 0u;              // 0..32
+                const uint32_t peers = __match_any_sync(0xffffffffu, key[q]);
+                const int leader = __ffs((int)peers) - 1;
+                uint32_t base = 0;
+                if (lane == leader) base = atomicAdd(&s_hist[key[q]], (uint32_t)__popc(peers));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                rank[q] = base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+            }
+            __syncthreads();                            // the histogram is complete
+            const uint32_t h = s_hist[lane];
+            uint32_t incl = h;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += o;
+            }
+            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                const uint32_t first = __shfl_sync(0xffffffffu, incl - h, (int)(key[q] & 31u));
+                s_perm[(key[q] < 32u ? first : total) + rank[q]] = (uint16_t)(q * kPackThreads + tid);
+            }
+        }
+        __syncthreads();
+        // ---- count pass ------------------------------------------------------------------------------------------
+#pragma unroll 1
+        for (int q = 0; q < 2; q++) {
+            const int j = s_perm[q ? place_heavy : place_light];
+            const long long cube = cube0 + j;
+            uint32_t nb = 0;
+            if (cube < P.L.ncubes) nb = eg_count_cube<G::CS, true>(cube_chunks<C>(P, cube), P.cmask[cube]);
+            s_bits[j] = nb;
+        }
+        __syncthreads();
+        // ---- scan in stream order: thread t owns cubes 2t and 2t + 1 of the tile --------------------------------------
+        {
+            const uint32_t b0 = s_bits[2 * tid], b1 = s_bits[2 * tid + 1];
+            const uint32_t sum = b0 + b1;
+            uint32_t incl = sum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += o;
+            }
+            if (lane == 31) s_wsum[warp] = incl;
+            __syncthreads();
+            const uint32_t w = lane < NW ? s_wsum[lane] : 0u;
+            uint32_t wi = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xffffffffu, wi, d);
+                if (lane >= d) wi += o;
+            }
+            const uint32_t excl = __shfl_sync(0xffffffffu, wi - w, warp) + (incl - sum);
+            s_bits[2 * tid] = excl;                     // own slots: nobody else reads them before the next barrier
+            s_bits[2 * tid + 1] = excl + b0;
+            if (warp == 0) {
+                const uint32_t total = __shfl_sync(0xffffffffu, wi, 31);
+                const unsigned long long off = tile_lookback(P.tile_status, tile, total, start_bit, lane, P.err);
+                if (lane == 0) {
+                    s_off = off;
+                    if (tile == ntiles - 1) {
+                        *P.end_bit = off + total;
+                        if (P.end_bit_host) *P.end_bit_host = off + total;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // ---- write pass ----------------------------------------------------------------------------------------------
+#pragma unroll 1
+        for (int q = 0; q < 2; q++) {
+            const int j = s_perm[q ? place_heavy : place_light];
+            const long long cube = cube0 + j;
+            if (cube < P.L.ncubes) {
+                const unsigned long long off = s_off + s_bits[j];
+                // the cube's own bit count: the next cube's offset minus this one's (the tile total for the last cube)
+                const int16_t *zz = cube_chunks<C>(P, cube);
+                const uint32_t cm = P.cmask[cube];
+                if (off + (uint32_t)G::CS * 33u + 64 > P.cap_bits && off + eg_count_cube<G::CS, true>(zz, cm) + 64 > P.cap_bits) {
+                    atomicOr(P.err, 1u);
+                } else {
+                    GlobalSink sink{P.out_words};
+                    eg_write_cube<G::CS, GlobalSink, true>(zz, cm, off, sink);
+                }
             }
         }
         __syncthreads();                                // s_tile, s_hist, s_perm, s_bits, s_wsum and s_off are reused

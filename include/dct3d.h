@@ -74,6 +74,12 @@ void dct3d_host_free(void *p);
  * "piece_bytes" (default 0 = 32 MiB): stream bytes per upload piece of the host-buffer decoders, which parse a stream piece
  * by piece while the later pieces are still being copied to the GPU.
  * "kernel_times_reset": restarts the ring of kernel-time events behind the ns_*_kernel_avg statistics.
+ * Kernel variants, all bit-identical in their results (defaults can also be set for a whole process through the
+ * environment: DCT3D_ZERO_SKIP, DCT3D_TMA_STORE, DCT3D_PACK_SORT): "zero_skip" (default 1; 8x8x8 fused encoder: groups
+ * of high diagonals are tested for zero before they are quantised), "tma_store" (default 1: the inverse kernel stores
+ * its pixel tiles by TMA when width % 32 == 0 and the frame buffer is 16-byte aligned; statistic "tma_store_used"
+ * tells whether the last launch did), "pack_sort" (0 = the bit packer takes the cubes of a tile in stream order,
+ * 1 = dealt to its threads by chunk count, 2 = the same with balanced warps).
  * "precision" (32 [default] or 64): with 64 the fused and stage entry points (encode_u8, decode_u8, quantize_u8,
  * reconstruct_i16 and the streaming calls) compute in double like the Java reference (J/dct/DCT.java:41-59,
  * J/Encoder.java:82, J/Decoder.java:89,112): quantised cubes then equal the fp64 oracle without rounding-tie

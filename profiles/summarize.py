@@ -22,13 +22,14 @@ ROWS = [
     ("DRAM write (MB)", "dram__bytes_write.sum"),
     ("DRAM % of peak", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
     ("SM % of peak", "sm__throughput.avg.pct_of_peak_sustained_elapsed"),
-    ("issue slots busy %", "smsp__issue_active.avg.pct"),
+    ("issue slots busy %", "smsp__issue_active.avg.pct_of_peak_sustained_active"),
+    ("LSU data pipe % (wavefronts)", "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"),
     ("FMA pipe %", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"),
     ("ALU pipe %", "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active"),
     ("warps active %", "sm__warps_active.avg.pct_of_peak_sustained_active"),
     ("regs/thread", "launch__registers_per_thread"),
     ("grid", "launch__grid_size"),
-    ("warp instructions", "sm__inst_executed.sum"),
+    ("warp instructions", "smsp__inst_executed.sum"),
     ("smem wavefronts", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"),
     ("smem bank conflicts", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"),
 ]

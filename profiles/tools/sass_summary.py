@@ -17,9 +17,9 @@ ops = ['UTMALDG', 'UTMASTG', 'SYNCS', 'FFMA', 'FADD', 'FMUL', 'DFMA', 'DADD', 'D
        'ATOMG', 'REDG', 'HMMA', 'UTCHMMA', 'UTCQMMA']
 lines = ['# Round 2 SASS opcode summary (libdct3d.so, sm_100a)', '',
          'Static instruction counts per kernel from `cuobjdump -sass 3ddctvideoencoding_b200/libdct3d.so` (regenerate: `python profiles/tools/sass_summary.py`).',
-         '`UTMALDG` = TMA tensor loads (the warp-private unit loads of `encode_kernel`), `SYNCS` = mbarrier operations; there is no `UTMASTG` (the inverse '
-         'kernel stores rows with `STG.64`; a TMA store would add shared-memory traffic to a kernel whose shared-memory pipe is a co-limiter, DESIGN.md 3.5) '
-         'and no tensor-core instruction (`HMMA`/`UTC*MMA`): the north star excludes tensor cores for this path.', '',
+         '`UTMALDG` = TMA tensor loads (the warp-private unit loads of `encode_kernel`), `UTMASTG` = TMA tensor stores (the pixel tile of '
+         '`reconstruct_coo_kernel<., TAIL_TMA>`, one per unit, DESIGN.md 3.5), `SYNCS` = mbarrier operations; there is '
+         'no tensor-core instruction (`HMMA`/`UTC*MMA`): the north star excludes tensor cores for this path.', '',
          '| kernel | total | ' + ' | '.join(ops) + ' |', '|---|---|' + '---|' * len(ops)]
 for k, c in counts.items():
     lines.append(f'| {k} | {sum(c.values())} | ' + ' | '.join(str(c.get(o, 0)) for o in ops) + ' |')

@@ -9,7 +9,7 @@ import io
 import subprocess
 import sys
 
-KERNELS = ["encode_kernel", "eg_pack_kernel", "seg_scan_kernel", "seg_emit_kernel", "reconstruct_coo_kernel"]
+KERNELS = ["encode_kernel", "eg_pack_(sorted_)?kernel", "seg_scan_kernel", "seg_emit_kernel", "reconstruct_coo_kernel"]
 
 
 def page(rep, kernel):
